@@ -1,0 +1,185 @@
+/*
+ * xmc_loss.h — C ABI of libxmcloss.so, the sm_100a CUDA implementation of the XMC-GAN
+ * cross-modal contrastive-loss hot path.
+ *
+ * The reference (Eun0/XMC-GAN) is pure Python/PyTorch and has NO native interface; the
+ * functions below are what a ctypes/cffi binding of the reference's loss block
+ * (xmc_gan/train_gan.py:72-139 and the unimplemented word_loss named at :220-222, :267-269)
+ * would bind.  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions (all entry points)
+ *  - Plain pointers and sizes; no torch / C++ types.  Every pointer is DEVICE memory owned by
+ *    the caller (inputs, outputs, saved statistics, workspace).  The library never allocates,
+ *    frees or retains pointers past return.
+ *  - All work is enqueued on the cudaStream_t passed as `stream` (void* here so that C callers
+ *    need no CUDA headers).  No internal synchronisation, no default-stream use.  Stateless and
+ *    re-entrant: forward may run on one host thread and backward on another (PyTorch's autograd
+ *    worker).
+ *  - Return 0 (XMC_OK) on success, otherwise an xmc_status; xmc_last_error() returns a
+ *    thread-local message.  No exceptions, no exit(), no stdout.  There is NO CPU fallback.
+ *  - Matrices are row-major and contiguous unless a leading dimension is given.  Base pointers
+ *    must be 16-byte aligned.  D must be a multiple of 128 for the similarity losses (256, 512
+ *    and 768 in the reference) and one of 64/128/256 for the word-region kernels.
+ *  - dtype: XMC_F32 or XMC_BF16 is the STORAGE type of embedding operands; all arithmetic and
+ *    all statistics / gradients of statistics are fp32.
+ */
+#ifndef XMC_LOSS_H_
+#define XMC_LOSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XMC_ABI_VERSION 1
+
+typedef enum {
+  XMC_OK = 0,
+  XMC_ERR_INVALID_ARG = 1,  /* bad shape / null pointer                     */
+  XMC_ERR_UNSUPPORTED = 2,  /* dtype or dimension outside the supported set */
+  XMC_ERR_ALIGNMENT = 3,    /* pointer not 16-byte aligned                  */
+  XMC_ERR_WORKSPACE = 4,    /* workspace too small                          */
+  XMC_ERR_CUDA = 5          /* launch / driver error (see xmc_last_error)   */
+} xmc_status;
+
+typedef enum { XMC_F32 = 0, XMC_BF16 = 1 } xmc_dtype;
+
+/* Word-region compute path: CUDA-core fp32 (operands fp32, tolerance 1e-4) or
+ * tcgen05/TMEM tensor-core path (operands bf16, fp32 accumulate, tolerance 2e-2). */
+typedef enum { XMC_PATH_FP32_SIMT = 0, XMC_PATH_BF16_TCGEN05 = 1 } xmc_path;
+
+int xmc_version(void);
+const char* xmc_last_error(void);
+/* 0 when the current device is compute capability 10.x; XMC_ERR_UNSUPPORTED otherwise. */
+int xmc_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row/column statistics of an InfoNCE problem.  For logits Z = scale * S:
+ *   stats[0*n + k] = logsumexp of Z over the other axis
+ *   stats[1*n + k] = sum of labels
+ *   stats[2*n + k] = sum of labels * Z
+ * row_stats has 3*Bq floats, col_stats 3*Bk floats.
+ * labels == NULL means "identity with column offset": L[i][j] = (j == i + diag_offset), which is
+ * what make_labels returns when b_global is False (xmc_gan/train_gan.py:74); diag_offset is the
+ * global column index of local row 0 (non-zero only for rank-sharded global negatives).
+ * ------------------------------------------------------------------------------------------- */
+
+/* cosine_scores(emb0, emb1)  — xmc_gan/train_gan.py:85-91.
+ * scores[Bq,Bk] = normalize(a) @ normalize(b)^T ; inv_norm_*[k] = 1/max(||x_k||, 1e-12)
+ * (either inv_norm pointer may be NULL). */
+int xmc_cosine_scores(const void* a, const void* b, int Bq, int Bk, int D, int dtype,
+                      float* scores, float* inv_norm_a, float* inv_norm_b, void* stream);
+
+/* Fused forward of sent_loss / img_loss up to the statistics — train_gan.py:93-111 / 117-135:
+ * L2-normalise, cosine matrix, scale (=1/tau; the reference has no temperature: 1.0),
+ * log-sum-exp over rows and over columns and the label-weighted sums, ONE kernel.
+ * Writes scores[Bq,Bk] (kept for backward), inv norms and both statistics blocks. */
+int xmc_simloss_forward(const void* a, const void* b, int Bq, int Bk, int D, int dtype,
+                        const float* labels, int diag_offset, float scale,
+                        float* scores, float* inv_norm_a, float* inv_norm_b,
+                        float* row_stats, float* col_stats, void* stream);
+
+/* Same statistics from a given score matrix (used for the word-region scores, scale = rho3). */
+int xmc_infonce_stats(const float* scores, int Bq, int Bk, const float* labels, int diag_offset,
+                      float scale, float* row_stats, float* col_stats, void* stream);
+
+/* Loss from statistics — train_gan.py:104-113 (s0 = column direction, s1 = row direction).
+ * row_div[Bq] / col_div[Bk]: per-row / per-column divisor ("num_pos" when it is the
+ * (labels>0).sum(1) vector, :99); NULL means the scalar num_pos (1 or 2, :94-97).
+ * rows_total / cols_total are the GLOBAL matrix sizes the two means divide by (== Bq, Bk on one
+ * GPU).  loss_out[0] = s0_part + s1_part, [1] = s0_part, [2] = s1_part, where s1_part sums the Bq
+ * local rows and s0_part the columns [col_begin, col_begin+col_count) — all Bk columns on one
+ * GPU, the rank's own columns when the matrix is sharded by rows (so that parts add up). */
+int xmc_infonce_loss(const float* row_stats, const float* col_stats, int Bq, int Bk,
+                     const float* row_div, const float* col_div, float num_pos,
+                     int rows_total, int cols_total, int col_begin, int col_count,
+                     float* loss_out, void* stream);
+
+/* d loss / d scores (closed form of the autograd of train_gan.py:103-113), times *grad_out
+ * (device scalar) times scale.  col_stats must already be the statistics over ALL rows. */
+int xmc_infonce_grad(const float* scores, int Bq, int Bk, const float* labels, int diag_offset,
+                     float scale, const float* row_stats, const float* col_stats,
+                     const float* row_div, const float* col_div, float num_pos,
+                     int rows_total, int cols_total, const float* grad_out,
+                     float* dscores, void* stream);
+
+/* Fused backward of sent_loss / img_loss: d scores on the fly, dA = dS * Bhat, dB = dS^T * Ahat
+ * and the backward of F.normalize, ONE kernel.  da / db may be NULL (img_loss only needs db,
+ * train_gan.py:271-278; the D step only needs da, :194,218).  Outputs have dtype `dtype`. */
+int xmc_simloss_backward(const void* a, const void* b, int Bq, int Bk, int D, int dtype,
+                         const float* scores, const float* inv_norm_a, const float* inv_norm_b,
+                         const float* labels, int diag_offset, float scale,
+                         const float* row_stats, const float* col_stats,
+                         const float* row_div, const float* col_div, float num_pos,
+                         int rows_total, int cols_total, const float* grad_out,
+                         void* da, void* db, void* stream);
+
+/* make_labels soft-positive path — train_gan.py:72-83.  sim[B,B] is cosine_scores(sent, sent).
+ * smooth_global != 0: weight = smooth_global; == 0: weight_j = 1/(max(count_j,1)+1) (:79-81),
+ * broadcast along columns (:82).  Writes labels[B,B] and row_count[B] = (labels>0).sum(1). */
+int xmc_make_labels(const float* sim, int B, float p, float smooth_global,
+                    float* labels, float* row_count, float* tmp_count /*[B] scratch*/,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Word-region attention contrastive loss (the `word_loss` the reference names but does not
+ * implement, train_gan.py:220-222, 267-269).  Pipeline:
+ *   normalize_transpose(words)   [Bc,D,T] -> qn [Bc*T, D]         (layout: encoder.py:68,140)
+ *   normalize_transpose(regions) [Bi,D,R] -> kn [Bi,Rpad,D], rnorm[Bi,Rpad]
+ *   wordregion_forward           -> per (image, word) statistics lsum, cnorm, rel  [Bi, NQ]
+ *   word_scores                  -> S_word [Bi, Bc]  (masked log-sum-exp over words)
+ *   infonce_stats / loss / grad  (scale = rho3)
+ *   word_scores_backward         -> grel [Bi, NQ]
+ *   wordregion_backward          -> dqn [NQ,D], dkn [Bi,Rpad,D], drnorm [Bi,Rpad]   (fp32)
+ *   normalize_transpose_backward -> d words, d regions in the caller's layout
+ * The [Bi,Bc,T,R] score tensor never exists in global memory.
+ * ------------------------------------------------------------------------------------------- */
+
+/* x[B, D, L] (channel-major, L contiguous) -> xn[B, Lpad, D] = x / max(||x||,1e-12) per (b,l),
+ * rows l >= L zero-filled; norm[B, Lpad] = max(||x||,1e-12) (0 for padding rows). */
+int xmc_normalize_transpose(const void* x, int B, int D, int L, int Lpad, int in_dtype,
+                            int out_dtype, void* xn, float* norm, void* stream);
+
+/* Backward of the above.  dxn[B,Lpad,D] fp32 is the gradient w.r.t. the unit rows; dnorm[B,Lpad]
+ * (nullable) the gradient w.r.t. the norm.  dx[B,D,L] has dtype out_dtype. */
+int xmc_normalize_transpose_backward(const void* xn, const float* norm, const float* dxn,
+                                     const float* dnorm, int B, int D, int L, int Lpad,
+                                     int xn_dtype, int out_dtype, void* dx, void* stream);
+
+size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad, int D);
+
+/* qn[NQ,D]: unit word rows (NQ = Bc*T); kn[Bi,Rpad,D]: unit region rows; rnorm[Bi,Rpad]: region
+ * norms used as value weights (NULL: values are the unit regions, "normalize_values").
+ * Outputs per (image i, word row q), each [Bi, NQ] fp32:
+ *   lsum  = sum_r exp(rho1*(s_qr - 1))     (softmax denominator, constant shift rho1)
+ *   cnorm = || c_q ||                       (norm of the attended context)
+ *   rel   = cos(e_q, c_q)
+ * Rpad must be a multiple of 16 and >= R. */
+int xmc_wordregion_forward(int path, const void* qn, const void* kn, const float* rnorm,
+                           int NQ, int Bi, int R, int Rpad, int D, float rho1,
+                           float* lsum, float* cnorm, float* rel,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* grel[Bi,NQ] = d loss / d rel.  dqn[NQ,D], dkn[Bi,Rpad,D], drnorm[Bi,Rpad] (nullable iff rnorm
+ * is NULL) are fp32 and are ACCUMULATED into: the caller zero-fills them first. */
+int xmc_wordregion_backward(int path, const void* qn, const void* kn, const float* rnorm,
+                            int NQ, int Bi, int R, int Rpad, int D, float rho1,
+                            const float* lsum, const float* cnorm, const float* rel,
+                            const float* grel, float* dqn, float* dkn, float* drnorm,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* scores[Bi,Bc] = (1/rho2) * log sum_{t: !mask[c][t]} exp(rho2 * rel[i][c*T+t]);
+ * mask[Bc,T] bytes, non-zero = padding (encoder.py:61,149), NULL = no padding.
+ * A fully padded caption scores 0 and receives zero gradient. */
+int xmc_word_scores(const float* rel, const uint8_t* mask, int Bi, int Bc, int T, float rho2,
+                    float* scores, void* stream);
+int xmc_word_scores_backward(const float* rel, const uint8_t* mask, const float* scores,
+                             const float* dscores, int Bi, int Bc, int T, float rho2,
+                             float* grel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XMC_LOSS_H_ */

@@ -1,0 +1,52 @@
+"""Load the reference's own loss functions, unmodified, for pinning the oracle.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  ``import xmc_gan.train_gan``
+is impossible in this image (``easydict``, ``sentence_transformers`` and
+``pytorch_fid`` are absent and the module has import-time side effects), so the
+four ``FunctionDef`` nodes ``make_labels``, ``cosine_scores``, ``sent_loss`` and
+``img_loss`` (``xmc_gan/train_gan.py:72-139``) are parsed out of the read-only
+file with ``ast`` and executed in a namespace holding ``torch``, ``F`` and a
+stub ``cfg``.  No reference source is copied into this repo.
+
+Only usable where ``/root/reference`` exists (the build container); the GPU box
+has no such path, so nothing that runs there may call this.
+"""
+from __future__ import annotations
+
+import ast
+import contextlib
+import os
+from types import SimpleNamespace
+
+import torch
+import torch.nn.functional as F
+
+REFERENCE_FILE = "/root/reference/xmc_gan/train_gan.py"
+_WANTED = ("make_labels", "cosine_scores", "sent_loss", "img_loss")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(REFERENCE_FILE)
+
+
+def load_reference_losses(smooth_global: float = 0.5) -> SimpleNamespace:
+    """Return a namespace with the reference's four functions and its ``cfg`` stub."""
+    with open(REFERENCE_FILE, "r") as f:
+        tree = ast.parse(f.read(), REFERENCE_FILE)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in _WANTED]
+    assert sorted(n.name for n in keep) == sorted(_WANTED), "reference layout changed"
+    cfg = SimpleNamespace(TRAIN=SimpleNamespace(SMOOTH=SimpleNamespace(GLOBAL=smooth_global)))
+    ns = {"torch": torch, "F": F, "cfg": cfg}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), REFERENCE_FILE, "exec"), ns)
+    return SimpleNamespace(cfg=cfg, **{k: ns[k] for k in _WANTED})
+
+
+@contextlib.contextmanager
+def cuda_is_identity():
+    """``make_labels`` hard-codes ``.cuda()`` (train_gan.py:74); make it a no-op on CPU."""
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = saved

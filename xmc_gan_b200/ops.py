@@ -1,0 +1,235 @@
+"""Thin tensor-level wrappers over the C ABI (one method per entry point of ``include/xmc_loss.h``).
+
+``CudaOps`` is the only product backend.  It takes CUDA tensors, allocates outputs with the
+PyTorch caching allocator (the library never allocates), passes raw device pointers plus the
+current stream, and raises on any non-zero status.  There is no CPU path: a non-CUDA tensor is an
+error.  The autograd layer (``losses.py``) is written against this interface so that the
+multi-rank plumbing can be exercised on CPU/gloo in ``tests/`` with a checker backend injected —
+the product never does that.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.XMC_F32, torch.bfloat16: _lib.XMC_BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"xmc_gan_b200 supports float32 and bfloat16 operands, got {t.dtype}") from None
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("xmc_gan_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t):
+    return None if t is None else t.to(torch.float32).contiguous()
+
+
+class CudaOps:
+    """Calls into libxmcloss.so.  Stateless; safe from the autograd worker thread."""
+
+    name = "libxmcloss"
+
+    def __init__(self):
+        self.L = _lib.lib()
+        self.launches = 0      # kernels launched through this backend (bench.py's gpu_launches)
+
+    # -- similarity losses ------------------------------------------------------------------
+    def cosine_scores(self, a, b):
+        _cuda(a, b)
+        a, b = a.contiguous(), b.contiguous()
+        Bq, D = a.shape
+        Bk = b.shape[0]
+        scores = torch.empty(Bq, Bk, device=a.device, dtype=torch.float32)
+        with torch.cuda.device_of(a):
+            _lib.check(self.L.xmc_cosine_scores(_p(a), _p(b), Bq, Bk, D, _dt(a), _p(scores), None, None, _stream()))
+        self.launches += 1
+        return scores
+
+    def simloss_forward(self, a, b, labels, diag, scale):
+        _cuda(a, b, labels)
+        Bq, D = a.shape
+        Bk = b.shape[0]
+        dev = a.device
+        scores = torch.empty(Bq, Bk, device=dev, dtype=torch.float32)
+        inv_a = torch.empty(Bq, device=dev, dtype=torch.float32)
+        inv_b = torch.empty(Bk, device=dev, dtype=torch.float32)
+        row_stats = torch.empty(3, Bq, device=dev, dtype=torch.float32)
+        col_stats = torch.empty(3, Bk, device=dev, dtype=torch.float32)
+        with torch.cuda.device_of(a):
+            _lib.check(self.L.xmc_simloss_forward(_p(a), _p(b), Bq, Bk, D, _dt(a), _p(labels), diag, scale,
+                                                  _p(scores), _p(inv_a), _p(inv_b), _p(row_stats), _p(col_stats),
+                                                  _stream()))
+        self.launches += 1
+        return scores, inv_a, inv_b, row_stats, col_stats
+
+    def simloss_backward(self, a, b, scores, inv_a, inv_b, labels, diag, scale, row_stats, col_stats,
+                         row_div, col_div, num_pos, rows_total, cols_total, grad_out, need_a, need_b):
+        _cuda(a, b, grad_out)
+        Bq, D = a.shape
+        Bk = b.shape[0]
+        da = torch.empty_like(a) if need_a else None
+        db = torch.empty_like(b) if need_b else None
+        if not (need_a or need_b):
+            return None, None
+        with torch.cuda.device_of(a):
+            _lib.check(self.L.xmc_simloss_backward(
+                _p(a), _p(b), Bq, Bk, D, _dt(a), _p(scores), _p(inv_a), _p(inv_b), _p(labels), diag, scale,
+                _p(row_stats), _p(col_stats), _p(row_div), _p(col_div), float(num_pos), rows_total, cols_total,
+                _p(grad_out), _p(da), _p(db), _stream()))
+        self.launches += 1
+        return da, db
+
+    # -- InfoNCE tail over a given score matrix -----------------------------------------------
+    def infonce_stats(self, scores, labels, diag, scale):
+        _cuda(scores, labels)
+        Bq, Bk = scores.shape
+        row_stats = torch.empty(3, Bq, device=scores.device, dtype=torch.float32)
+        col_stats = torch.empty(3, Bk, device=scores.device, dtype=torch.float32)
+        with torch.cuda.device_of(scores):
+            _lib.check(self.L.xmc_infonce_stats(_p(scores), Bq, Bk, _p(labels), diag, scale,
+                                                _p(row_stats), _p(col_stats), _stream()))
+        self.launches += 1
+        return row_stats, col_stats
+
+    def infonce_loss(self, row_stats, col_stats, row_div, col_div, num_pos, rows_total, cols_total,
+                     col_begin, col_count):
+        _cuda(row_stats, col_stats)
+        out = torch.empty(3, device=row_stats.device, dtype=torch.float32)
+        with torch.cuda.device_of(row_stats):
+            _lib.check(self.L.xmc_infonce_loss(_p(row_stats), _p(col_stats), row_stats.shape[1], col_stats.shape[1],
+                                               _p(row_div), _p(col_div), float(num_pos), rows_total, cols_total,
+                                               col_begin, col_count, _p(out), _stream()))
+        self.launches += 1
+        return out
+
+    def infonce_grad(self, scores, labels, diag, scale, row_stats, col_stats, row_div, col_div, num_pos,
+                     rows_total, cols_total, grad_out):
+        _cuda(scores, grad_out)
+        Bq, Bk = scores.shape
+        ds = torch.empty_like(scores)
+        with torch.cuda.device_of(scores):
+            _lib.check(self.L.xmc_infonce_grad(_p(scores), Bq, Bk, _p(labels), diag, scale, _p(row_stats),
+                                               _p(col_stats), _p(row_div), _p(col_div), float(num_pos),
+                                               rows_total, cols_total, _p(grad_out), _p(ds), _stream()))
+        self.launches += 1
+        return ds
+
+    def make_labels(self, sim, p, smooth_global):
+        _cuda(sim)
+        B = sim.shape[0]
+        labels = torch.empty(B, B, device=sim.device, dtype=torch.float32)
+        row_count = torch.empty(B, device=sim.device, dtype=torch.float32)
+        tmp = torch.empty(B, device=sim.device, dtype=torch.float32)
+        with torch.cuda.device_of(sim):
+            _lib.check(self.L.xmc_make_labels(_p(sim), B, float(p), float(smooth_global), _p(labels),
+                                              _p(row_count), _p(tmp), _stream()))
+        self.launches += 2
+        return labels, row_count
+
+    # -- word-region --------------------------------------------------------------------------
+    def normalize_transpose(self, x, Lpad, out_dtype):
+        _cuda(x)
+        B, D, L = x.shape
+        xn = torch.empty(B, Lpad, D, device=x.device, dtype=out_dtype)
+        norm = torch.empty(B, Lpad, device=x.device, dtype=torch.float32)
+        with torch.cuda.device_of(x):
+            _lib.check(self.L.xmc_normalize_transpose(_p(x), B, D, L, Lpad, _dt(x), _DT[out_dtype],
+                                                      _p(xn), _p(norm), _stream()))
+        self.launches += 1
+        return xn, norm
+
+    def normalize_transpose_backward(self, xn, norm, dxn, dnorm, L, out_dtype):
+        _cuda(xn, dxn)
+        B, Lpad, D = xn.shape
+        dx = torch.empty(B, D, L, device=xn.device, dtype=out_dtype)
+        with torch.cuda.device_of(xn):
+            _lib.check(self.L.xmc_normalize_transpose_backward(_p(xn), _p(norm), _p(dxn), _p(dnorm), B, D, L, Lpad,
+                                                               _dt(xn), _DT[out_dtype], _p(dx), _stream()))
+        self.launches += 1
+        return dx
+
+    def _workspace(self, path, NQ, Bi, R, Rpad, D, dev):
+        n = self.L.xmc_wordregion_workspace_bytes(path, NQ, Bi, R, Rpad, D)
+        return (torch.empty(n, device=dev, dtype=torch.uint8) if n else None), n
+
+    def wordregion_forward(self, path, qn, kn, rnorm, R, rho1):
+        _cuda(qn, kn, rnorm)
+        NQ, D = qn.shape
+        Bi, Rpad, _ = kn.shape
+        dev = qn.device
+        lsum = torch.empty(Bi, NQ, device=dev, dtype=torch.float32)
+        cnorm = torch.empty_like(lsum)
+        rel = torch.empty_like(lsum)
+        ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
+        with torch.cuda.device_of(qn):
+            _lib.check(self.L.xmc_wordregion_forward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
+                                                     _p(lsum), _p(cnorm), _p(rel), _p(ws), n, _stream()))
+        self.launches += 1
+        return lsum, cnorm, rel
+
+    def wordregion_backward(self, path, qn, kn, rnorm, R, rho1, lsum, cnorm, rel, grel):
+        _cuda(qn, kn, grel)
+        NQ, D = qn.shape
+        Bi, Rpad, _ = kn.shape
+        dev = qn.device
+        dqn = torch.zeros(NQ, D, device=dev, dtype=torch.float32)
+        dkn = torch.zeros(Bi, Rpad, D, device=dev, dtype=torch.float32)
+        drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if rnorm is not None else None
+        ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
+        with torch.cuda.device_of(qn):
+            _lib.check(self.L.xmc_wordregion_backward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
+                                                      _p(lsum), _p(cnorm), _p(rel), _p(grel), _p(dqn), _p(dkn),
+                                                      _p(drnorm), _p(ws), n, _stream()))
+        self.launches += 1
+        return dqn, dkn, drnorm
+
+    def word_scores(self, rel, mask_u8, Bc, T, rho2):
+        _cuda(rel, mask_u8)
+        Bi = rel.shape[0]
+        scores = torch.empty(Bi, Bc, device=rel.device, dtype=torch.float32)
+        with torch.cuda.device_of(rel):
+            _lib.check(self.L.xmc_word_scores(_p(rel), _p(mask_u8), Bi, Bc, T, float(rho2), _p(scores), _stream()))
+        self.launches += 1
+        return scores
+
+    def word_scores_backward(self, rel, mask_u8, scores, dscores, T, rho2):
+        _cuda(rel, dscores)
+        Bi, Bc = scores.shape
+        grel = torch.empty_like(rel)
+        with torch.cuda.device_of(rel):
+            _lib.check(self.L.xmc_word_scores_backward(_p(rel), _p(mask_u8), _p(scores), _p(dscores), Bi, Bc, T,
+                                                       float(rho2), _p(grel), _stream()))
+        self.launches += 1
+        return grel
+
+
+_default = None
+
+
+def default_ops() -> CudaOps:
+    """The product backend.  Raises when libxmcloss.so is missing or no sm_100 device is current."""
+    global _default
+    if _default is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("xmc_gan_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        ops = CudaOps()
+        _lib.check(ops.L.xmc_check_device())
+        _default = ops
+    return _default

@@ -1,0 +1,87 @@
+"""Drop-in mirror of the reference's loss block (``xmc_gan/train_gan.py:72-139``).
+
+Same module-level names, same positional/keyword parameter names and the same ``cfg`` access
+(``cfg.TRAIN.SMOOTH.GLOBAL``), so the reference's call sites (``:213, 218, 265, 278``) work
+unchanged after ``from xmc_gan_b200.train_gan import make_labels, cosine_scores, sent_loss,
+img_loss, word_loss``.  ``word_loss`` is the loss the reference names (``:222, 269``) but leaves
+as ``raise NotImplementedError``.
+
+Everything runs in hand-written sm_100a kernels through ``libxmcloss.so``; non-CUDA tensors raise.
+New options are keyword-only and default to the reference's behaviour:
+
+* ``tau``    — temperature of the logits (reference: none, i.e. 1.0);
+* ``group``  — a ``torch.distributed`` process group: global negatives across ranks.  NB this is
+  NOT the reference's ``b_global`` flag, which means in-batch soft positives (``:72-83``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import losses as _L
+from .config import cfg  # noqa: F401  (re-exported: callers set cfg.TRAIN.SMOOTH.GLOBAL here)
+from .ops import default_ops
+
+__all__ = ["cfg", "make_labels", "cosine_scores", "sent_loss", "img_loss", "word_loss"]
+
+
+def make_labels(batch_size, sent_embs, b_global, p=0.6, *, group=None, device=None):
+    """Label matrix of the contrastive losses — ``xmc_gan/train_gan.py:72-83``.
+
+    ``b_global=False``: identity ``[B, B]`` (``:74``).  The returned dense tensor is tagged so the
+    loss kernels take "identity + offset" instead of reading it.  ``b_global=True``: soft positives
+    where ``cos(sent_i, sent_j) > p`` (``:76-82``), computed on the GPU by ``xmc_cosine_scores`` +
+    ``xmc_make_labels``; the row counts ``(labels > 0).sum(1)`` come back with it (``:99``).
+    With ``group``, returns the rank's rows ``[B, B_global]`` of the global label matrix.
+    """
+    ops = default_ops()
+    comm = _L.Comm(group)
+    if device is None:
+        device = sent_embs.device if (sent_embs is not None and sent_embs.is_cuda) else torch.device("cuda")
+    if not b_global:
+        B_all = batch_size * comm.world
+        labels = torch.zeros(batch_size, B_all, device=device, dtype=torch.float32)
+        labels.diagonal(comm.rank * batch_size).fill_(1.0)
+        labels._xmc_identity = True
+        return labels
+    s = sent_embs.detach()
+    if s.dtype not in (torch.float32, torch.bfloat16):
+        s = s.to(torch.float32)
+    s_all = comm.all_gather_cat(s.contiguous())
+    sim = ops.cosine_scores(s_all, s_all)
+    labels, row_count = ops.make_labels(sim, p, cfg.TRAIN.SMOOTH.GLOBAL)
+    if comm.active:
+        lo = comm.rank * batch_size
+        labels = labels[lo:lo + batch_size].contiguous()
+        row_count = row_count[lo:lo + batch_size].contiguous()
+    labels._xmc_identity = False
+    labels._xmc_row_count = row_count
+    return labels
+
+
+def cosine_scores(emb0, emb1):
+    """``normalize(emb0) @ normalize(emb1).T`` — ``xmc_gan/train_gan.py:85-91`` (no autograd)."""
+    return default_ops().cosine_scores(emb0.detach(), emb1.detach())
+
+
+def sent_loss(imgs, txts, labels, b_global, *, tau=1.0, group=None):
+    """Sentence–image InfoNCE, rows = images, cols = texts — ``xmc_gan/train_gan.py:93-115``."""
+    return _L.SimLossFn.apply(imgs, txts, labels, bool(b_global), 1.0 / tau, group, default_ops())
+
+
+def img_loss(real_imgs, fake_imgs, labels, b_global, *, tau=1.0, group=None):
+    """Real–fake image InfoNCE, rows = real, cols = fake — ``xmc_gan/train_gan.py:117-139``."""
+    return _L.SimLossFn.apply(real_imgs, fake_imgs, labels, bool(b_global), 1.0 / tau, group, default_ops())
+
+
+def word_loss(imgs, words, mask, labels, b_global, *, rho1=5.0, rho2=5.0, rho3=10.0,
+              normalize_values=False, precision=None, group=None):
+    """Word–region attention contrastive loss (name pinned by ``train_gan.py:222, 269``).
+
+    imgs: region features ``[B, D, H, W]`` (or ``[B, D, R]``); words ``[B, D, T]`` and
+    mask ``[B, T]`` (True = padding) as produced by the reference's encoders
+    (``xmc_gan/model/encoder.py:61,68,140,149``).  Rows = images, cols = captions.
+    ``precision``: ``"fp32"`` (CUDA-core fp32, rel 1e-4) or ``"bf16"`` (tcgen05, bf16 operands,
+    fp32 accumulate, rel 2e-2); default follows the input dtype.
+    """
+    return _L.WordLossFn.apply(imgs, words, mask, labels, bool(b_global), float(rho1), float(rho2), float(rho3),
+                               bool(normalize_values), precision, group, default_ops())
