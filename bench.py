@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py — contrastive-loss forward+backward throughput (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+
+One "step" = forward+backward of ALL THREE losses (sent_loss D=256, img_loss D=512, word_loss
+T=18 R=17x17 D=256) on one synthetic COCO-shaped batch of 256 per GPU (BASELINE config 2;
+with --gpus N>1 config 3: global negatives, 256 per GPU, rows local / columns all-gathered).
+Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same
+metric through the public API with pinned-host inputs copied H2D and the loss read back D2H inside
+the timed region.  `roofline` is for the dominant kernel (word-region backward), timed live with
+CUDA events on the launching stream.  `cpu_baseline` / `--impl reference` time the CPU oracle
+(the reference's own functions restated, plus this repo's word-loss restatement) on host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_LOCAL, D_SENT, D_IMG, D_WORD, T_WORDS, R_SIDE = 256, 256, 512, 256, 18, 17
+RHO = (5.0, 5.0, 10.0)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"], "tensor": p["bf16_tflops_sustained"],
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def make_inputs(B, seed, dtype=torch.float32):
+    """Synthetic COCO-shaped batch, generated on CPU so oracle and GPU see identical values."""
+    g = torch.Generator().manual_seed(seed)
+    R = R_SIDE * R_SIDE
+    words = torch.randn(B, D_WORD, T_WORDS, generator=g)
+    regions = torch.randn(B, D_WORD, R, generator=g) + 0.3 * words[:, :, torch.randint(0, T_WORDS, (R,), generator=g)]
+    lens = torch.randint(5, T_WORDS + 1, (B,), generator=g)
+    d = {
+        "sent": torch.randn(B, D_SENT, generator=g),
+        "img": torch.randn(B, D_SENT, generator=g),
+        "real": torch.randn(B, D_IMG, generator=g),
+        "fake": torch.randn(B, D_IMG, generator=g),
+        "words": words,
+        "regions": regions.view(B, D_WORD, R_SIDE, R_SIDE),
+        "mask": torch.arange(T_WORDS).unsqueeze(0) >= lens.unsqueeze(1),
+    }
+    return {k: (v.to(dtype) if v.dtype.is_floating_point else v) for k, v in d.items()}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        rows = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+def oracle_step(inp, words_slice=None):
+    """All three losses fwd+bwd with the CPU oracle (float32, as the reference would run)."""
+    import oracle
+    B = inp["sent"].shape[0]
+    labels = oracle.make_labels(B, inp["sent"], False)
+    leaf = lambda x: x.clone().requires_grad_()
+    i_, s_, f_, w_, v_ = leaf(inp["img"]), leaf(inp["sent"]), leaf(inp["fake"]), leaf(inp["words"]), leaf(inp["regions"])
+    loss = (oracle.sent_loss(i_, s_, labels, False) + oracle.img_loss(inp["real"], f_, labels, False)
+            + oracle.word_loss(v_, w_, inp["mask"], labels, False, 0.5, *RHO, img_block=8))
+    loss.backward()
+    return float(loss.detach())
+
+
+def time_oracle(steps, warmup, B):
+    torch.set_num_threads(os.cpu_count())
+    inp = make_inputs(B, 0)
+    for _ in range(warmup):
+        oracle_step(inp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(inp)
+    dt = (time.perf_counter() - t0) / steps
+    return B / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on host cores, same metric/config, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    sps, dt = time_oracle(steps, warmup, B_LOCAL)
+    cores = os.cpu_count()
+    sample = (f"full COCO-256 batch (B=256, T=18, R=289, D=256; sent D=256, img D=512), fp32, "
+              f"{steps} timed + {warmup} warm-up fwd+bwd steps; reference functions restated "
+              f"(train_gan.py:72-139) + this repo's word-loss restatement (reference has none)")
+    line = {
+        "impl": "reference", "metric": "contrastive-loss fwd+bwd samples/sec", "value": sps, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "COCO-256: sent_loss+img_loss+word_loss fwd+bwd, B=256 T=18 R=289 D=256, CPU"},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=B_LOCAL)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from xmc_gan_b200 import train_gan as T
+    from xmc_gan_b200.ops import default_ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        group = dist.group.WORLD
+    dev = torch.device("cuda", local_rank)
+    ops = default_ops()
+    precision = args.precision or os.environ.get("XMC_BENCH_PRECISION", "fp32")
+    in_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+    B = args.batch
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    host = make_inputs(B, 1000 + rank, in_dtype)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    devin = {k: v.to(dev) for k, v in host.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def step(x):
+        leaf = lambda t: t.detach().requires_grad_()
+        i_, s_, f_, w_, v_ = leaf(x["img"]), leaf(x["sent"]), leaf(x["fake"]), leaf(x["words"]), leaf(x["regions"])
+        labels = T.make_labels(B, x["sent"], False, group=group)
+        loss = (T.sent_loss(i_, s_, labels, False, group=group) + T.img_loss(x["real"], f_, labels, False, group=group)
+                + T.word_loss(v_, w_, x["mask"], labels, False, rho1=RHO[0], rho2=RHO[1], rho3=RHO[2],
+                              precision=precision, group=group))
+        loss.backward()
+        return loss, (i_.grad, s_.grad, f_.grad, w_.grad, v_.grad)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(group)
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """Per-step CUDA events on the current stream, L2 flushed (untimed) between steps."""
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            ms = float(t)
+        return ms
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    for _ in range(W):
+        step(devin)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.launches
+    ops.enable_timing(True)
+    ms = timed(lambda: step(devin), K)
+    kern = ops.kernel_ms()
+    ops.enable_timing(False)
+    launches = (ops.launches - l0) // K
+    clocks = sampler.summary()
+
+    # ---- end to end: pinned host -> device, loss -> host -------------------------------------
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+
+    def e2e_step():
+        x = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        loss, _ = step(x)
+        return float(loss)                                                     # D2H read of the result
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, max(3, K // 2))
+
+    # ---- roofline of the dominant kernel (word-region backward) -------------------------------
+    pk = peaks()
+    Bg, R = B * world, R_SIDE * R_SIDE
+    flops_bwd = 8.0 * B * Bg * T_WORDS * R * D_WORD          # dA, dV(x2 operands), dQ: 4 GEMMs x 2*Bq*Bk*T*R*D
+    flops_fwd = 4.0 * B * Bg * T_WORDS * R * D_WORD
+    n_bwd, ms_bwd = kern.get("wordregion_bwd", (0, float("nan")))
+    n_fwd, ms_fwd = kern.get("wordregion_fwd", (0, float("nan")))
+    ach = flops_bwd / (ms_bwd * 1e-3) / 1e12
+    roofline = {
+        "kernel": "wordregion_backward (%s path)" % ("tcgen05 bf16" if precision == "bf16" else "fp32 SIMT"),
+        "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
+        "traffic": None, "peak_source": pk["src"] + ", bf16 sustained",
+        "algorithmic_flops_per_launch": flops_bwd, "ms_per_launch": ms_bwd, "launches_timed": n_bwd,
+        "forward": {"ms_per_launch": ms_fwd, "achieved": flops_fwd / (ms_fwd * 1e-3) / 1e12,
+                    "frac": flops_fwd / (ms_fwd * 1e-3) / 1e12 / pk["tensor"]},
+        "kernels_ms": {k: round(v[1], 4) for k, v in kern.items()},
+    }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": "contrastive-loss fwd+bwd samples/sec", "value": Bg / (ms * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+        "config": {
+            "workload": ("COCO-256 (BASELINE config %d): sent_loss D=256 + img_loss D=512 + word_loss T=18 R=289 D=256, "
+                         "fwd+bwd, batch 256/GPU, %s" % (2 if world == 1 else 3,
+                                                       "bf16-in/fp32-accumulate" if precision == "bf16" else "fp32")),
+            "global_batch": Bg, "pairs_per_s": B * Bg * world / (ms * 1e-3), "rho": RHO,
+            "parallelism": "single GPU" if world == 1 else f"rows local, columns all-gathered over NCCL x{world}",
+            "l2": "256 MiB buffer written between timed steps (untimed) to flush the 126 MB L2",
+        },
+        "clocks": clocks,
+        "e2e": {"value": Bg / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sps, dt = time_oracle(2, 1, B)
+        line["cpu_baseline"] = {
+            "value": sps, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "full COCO-256 batch, 2 timed + 1 warm-up fwd+bwd steps of the CPU oracle (fp32, all host threads)",
+            "ms_per_step": dt * 1e3}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,23 @@ def _f32c(t):
     return None if t is None else t.to(torch.float32).contiguous()
 
 
+class _Timed:
+    def __init__(self, ops, name):
+        self.ops, self.name = ops, name
+
+    def __enter__(self):
+        if self.ops.events is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.ops.events is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.ops.events.setdefault(self.name, []).append((self.a, b))
+        return False
+
+
 class CudaOps:
     """Calls into libxmcloss.so.  Stateless; safe from the autograd worker thread."""
 
@@ -49,6 +66,19 @@ class CudaOps:
     def __init__(self):
         self.L = _lib.lib()
         self.launches = 0      # kernels launched through this backend (bench.py's gpu_launches)
+        self.events = None     # name -> [(start, stop)] CUDA events when kernel timing is on
+
+    def enable_timing(self, on=True):
+        """Record CUDA events (current stream) around the named hot kernels; see kernel_ms()."""
+        self.events = {} if on else None
+
+    def kernel_ms(self):
+        """name -> (launches, mean ms) over everything recorded since enable_timing()."""
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v) / len(v)) for k, v in self.events.items()}
+
+    def _timed(self, name):
+        return _Timed(self, name)
 
     # -- similarity losses ------------------------------------------------------------------
     def cosine_scores(self, a, b):
@@ -72,7 +102,7 @@ class CudaOps:
         inv_b = torch.empty(Bk, device=dev, dtype=torch.float32)
         row_stats = torch.empty(3, Bq, device=dev, dtype=torch.float32)
         col_stats = torch.empty(3, Bk, device=dev, dtype=torch.float32)
-        with torch.cuda.device_of(a):
+        with torch.cuda.device_of(a), self._timed("simloss_fwd"):
             _lib.check(self.L.xmc_simloss_forward(_p(a), _p(b), Bq, Bk, D, _dt(a), _p(labels), diag, scale,
                                                   _p(scores), _p(inv_a), _p(inv_b), _p(row_stats), _p(col_stats),
                                                   _stream()))
@@ -88,7 +118,7 @@ class CudaOps:
         db = torch.empty_like(b) if need_b else None
         if not (need_a or need_b):
             return None, None
-        with torch.cuda.device_of(a):
+        with torch.cuda.device_of(a), self._timed("simloss_bwd"):
             _lib.check(self.L.xmc_simloss_backward(
                 _p(a), _p(b), Bq, Bk, D, _dt(a), _p(scores), _p(inv_a), _p(inv_b), _p(labels), diag, scale,
                 _p(row_stats), _p(col_stats), _p(row_div), _p(col_div), float(num_pos), rows_total, cols_total,
@@ -178,7 +208,7 @@ class CudaOps:
         cnorm = torch.empty_like(lsum)
         rel = torch.empty_like(lsum)
         ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
-        with torch.cuda.device_of(qn):
+        with torch.cuda.device_of(qn), self._timed("wordregion_fwd"):
             _lib.check(self.L.xmc_wordregion_forward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
                                                      _p(lsum), _p(cnorm), _p(rel), _p(ws), n, _stream()))
         self.launches += 1
@@ -193,7 +223,7 @@ class CudaOps:
         dkn = torch.zeros(Bi, Rpad, D, device=dev, dtype=torch.float32)
         drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if rnorm is not None else None
         ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
-        with torch.cuda.device_of(qn):
+        with torch.cuda.device_of(qn), self._timed("wordregion_bwd"):
             _lib.check(self.L.xmc_wordregion_backward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
                                                       _p(lsum), _p(cnorm), _p(rel), _p(grel), _p(dqn), _p(dkn),
                                                       _p(drnorm), _p(ws), n, _stream()))
