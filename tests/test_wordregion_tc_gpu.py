@@ -1,0 +1,97 @@
+"""GPU tests of the tcgen05/TMEM/TMA word-region kernels (bf16 operands, fp32 accumulate).
+
+Level 1: raw tensor-core plumbing — the TMEM debug dump of tile 0 (S = Q Khat^T of chunk 0 and the
+context accumulator C) against torch matmuls on the same bf16 operands: this isolates descriptor /
+swizzle / TMEM-layout mistakes from the loss maths.
+Level 2: kernel statistics (lsum, cnorm, rel) against the fp32 CUDA-core kernel on the same operands.
+Level 3: word_loss(precision='bf16') against the CPU oracle fed the bf16-rounded inputs, rel 2e-2."""
+import ctypes
+
+import pytest
+import torch
+
+import oracle
+from util import TOL_BF16, lerr, nerr, word_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from xmc_gan_b200.ops import default_ops
+    return default_ops()
+
+
+def _operands(ops, B, D, T_, R, seed):
+    words, regions, mask = word_inputs(B, D, T_, R, seed)
+    Rpad = (R + 15) // 16 * 16
+    qn, _ = ops.normalize_transpose(words.cuda(), T_, torch.bfloat16)
+    kn, rnorm = ops.normalize_transpose(regions.cuda(), Rpad, torch.bfloat16)
+    return qn.view(B * T_, D), kn, rnorm, mask
+
+
+def _err_word(ops):
+    torch.cuda.synchronize()
+    return int(ops.last_workspace[:4].view(torch.int32)[0])
+
+
+@pytest.mark.parametrize("D", [256, 128, 64])
+def test_tmem_dump_matches_matmul(ops, D):
+    from xmc_gan_b200 import _lib
+    B, T_, R = 8, 18, 100
+    qn, kn, rnorm, _ = _operands(ops, B, D, T_, R, seed=D)
+    hook = _lib.lib().xmc_internal_set_debug_dump
+    hook.argtypes, hook.restype = [ctypes.c_int], None
+    hook(1)
+    try:
+        lsum, cnorm, rel = ops.wordregion_forward(_lib.PATH_BF16_TCGEN05, qn, kn, rnorm, R, 5.0)
+        assert _err_word(ops) == 0, "mbarrier wait timed out inside the kernel"
+        dump = ops.last_workspace[64:].view(torch.float32)
+    finally:
+        hook(0)
+    q = qn[:128].float()                                   # tile 0 (zero rows beyond NQ)
+    if q.shape[0] < 128:
+        q = torch.cat([q, torch.zeros(128 - q.shape[0], D, device="cuda")])
+    k0 = kn[0].float()                                     # image 0, [Rpad, D]
+    S_ref = q @ k0[:64].t()
+    S = dump[:128 * 64].view(128, 64)
+    assert torch.allclose(S, S_ref, atol=2e-3), float((S - S_ref).abs().max())
+    s_all = q @ k0.t()
+    valid = (torch.arange(k0.shape[0], device="cuda") < R).float()
+    p = torch.exp(5.0 * (s_all - 1.0)) * valid * rnorm[0]
+    C_ref = p.bfloat16().float() @ k0
+    C = dump[128 * 64:128 * 64 + 128 * D].view(128, D)
+    assert nerr(C, C_ref) < 5e-3, nerr(C, C_ref)
+
+
+@pytest.mark.parametrize("B,D,T_,R", [(8, 256, 18, 289), (32, 256, 18, 289), (5, 128, 7, 40), (16, 64, 32, 64),
+                                      (3, 256, 12, 17), (40, 256, 20, 256)])
+@pytest.mark.parametrize("raw_values", [True, False])
+def test_statistics_vs_fp32_kernel(ops, B, D, T_, R, raw_values):
+    from xmc_gan_b200 import _lib
+    qn, kn, rnorm, _ = _operands(ops, B, D, T_, R, seed=B + R)
+    rn = rnorm if raw_values else None
+    l1, c1, r1 = ops.wordregion_forward(_lib.PATH_BF16_TCGEN05, qn, kn, rn, R, 5.0)
+    assert _err_word(ops) == 0
+    l0, c0, r0 = ops.wordregion_forward(_lib.PATH_FP32_SIMT, qn.float(), kn.float(), rn, R, 5.0)
+    assert nerr(l1, l0) < 1e-3, nerr(l1, l0)
+    assert nerr(c1, c0) < 1e-2, nerr(c1, c0)
+    assert float((r1 - r0).abs().max()) < 2e-2, float((r1 - r0).abs().max())
+
+
+@pytest.mark.parametrize("B,D,T_,R", [(32, 256, 18, 289), (12, 128, 9, 64), (64, 256, 18, 289)])
+def test_word_loss_bf16_vs_oracle(B, D, T_, R):
+    from xmc_gan_b200 import train_gan as T
+    words, regions, mask = word_inputs(B, D, T_, R, seed=3 * B)
+    wb, rb = words.bfloat16(), regions.bfloat16()
+    labels = T.make_labels(B, None, False)
+    r = rb.clone().cuda().requires_grad_()
+    w = wb.clone().cuda().requires_grad_()
+    loss = T.word_loss(r, w, mask.cuda(), labels, False, precision="bf16")
+    loss.backward()
+    ro, wo = rb.double().requires_grad_(), wb.double().requires_grad_()
+    lo = oracle.word_loss(ro, wo, mask, torch.eye(B), False)
+    lo.backward()
+    assert lerr(loss, lo) <= TOL_BF16, (float(loss), float(lo))
+    assert nerr(r.grad, ro.grad) <= TOL_BF16, nerr(r.grad, ro.grad)
+    assert nerr(w.grad, wo.grad) <= TOL_BF16, nerr(w.grad, wo.grad)

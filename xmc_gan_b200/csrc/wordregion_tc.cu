@@ -1,14 +1,354 @@
-// wordregion_tc.cu — bf16 tcgen05/TMEM/TMA path of the word-region loss (placeholder until built).
+// wordregion_tc.cu — word–region attention statistics on the 5th-gen tensor cores (sm_100a):
+// bf16 operands, fp32 accumulation in TMEM, region tiles streamed by TMA.
+//
+// Tile = (128 consecutive word rows of the flattened [Bc*T, D] unit-word matrix) x (one image).
+// A CTA keeps its 128 word rows resident in TMEM as the A operand (bf16, D/2 columns) and walks
+// over a contiguous range of images; the regions of an image arrive in chunks of 64 rows
+// ([64 x D] bf16, four 128B-swizzled TMA boxes) through an NS-stage mbarrier ring.
+//
+//   GEMM1 (TS)  S[128 x 64]  = Q(tmem) . Khat_chunk^T        B = K-major  smem descriptor
+//   softmax warps: P' = exp2(c1 (S-1)) * ||v_r||  -> bf16, written over S in TMEM;  l += P, a += P' S
+//   GEMM2 (TS)  C[128 x D] += P'(tmem) . Khat_chunk           B = MN-major smem descriptor (same bytes)
+//   epilogue: ||C|| from TMEM  ->  lsum, cnorm, rel  (per image, per word row)
+//
+// The key and the value of the attention are the SAME smem tile (raw values are folded into P' as a
+// per-column scale), cosines are bounded so the softmax uses the constant shift rho1 (no running
+// max, no rescale of C), and the [Bi,Bc,T,R] score tensor lives only in TMEM.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
+// allocator, warps 4-7 = softmax/epilogue warpgroup (thread = TMEM lane = word row).
+// TMEM map (512 columns): C [0,D) | Q [D, D+D/2) | S0 | S1 (64 columns each, P' aliases S).
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "wordregion.h"
+
 namespace xmc {
-size_t wordregion_tc_workspace_bytes(int, int, int, int, int) { return 0; }
-int wordregion_tc_forward(const WrParams&, int, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 word-region forward not built yet");
+
+using namespace tc;
+
+constexpr int TM = 128;            // word rows per tile (UMMA M)
+constexpr int CH = 64;             // region rows per chunk
+constexpr int kTcThreads = 256;
+constexpr float kLog2eTc = 1.4426950408889634f;
+
+template <int D>
+struct FwdCfg {
+  static constexpr int kStageBytes = CH * D * 2;
+  static constexpr int kBlockBytes = CH * 128;                    // one [64 rows x 64 bf16] swizzled box
+  static constexpr int kStages = (D == 256) ? 6 : 8;
+  static constexpr int kColC = 0, kColQ = D, kColS0 = D + D / 2, kColS1 = kColS0 + CH;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kColS1 + CH <= 512, "TMEM budget");
+};
+
+struct TcFwdParams {
+  const __nv_bfloat16* qn;     // [NQ, D]
+  const float* rnorm;          // [Bi, Rpad] or null
+  int NQ, Bi, R, Rpad;
+  float rho1;
+  float* lsum; float* cnorm; float* rel;
+  int imgs_per_cta;
+  int* err;
+  float* dbg;                  // optional: S chunk 0 and C of the first tile/image (tests)
+};
+
+template <int D>
+__global__ void __launch_bounds__(kTcThreads, 1)
+wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
+  using Cfg = FwdCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* kv = smem;                                               // kStages x kStageBytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* kv_full = bars;                       // [kStages]
+  uint64_t* kv_empty = bars + Cfg::kStages;       // [kStages]
+  uint64_t* s_full = kv_empty + Cfg::kStages;     // [2]
+  uint64_t* p_full = s_full + 2;                  // [2]
+  uint64_t* c_full = p_full + 2;
+  uint64_t* c_empty = c_full + 1;
+  uint64_t* q_ready = c_empty + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
+  int* abort_flag = reinterpret_cast<int*>(tmem_slot + 1);
+  const WaitCtx wc{abort_flag, p.err};
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TM;
+  const int img0 = blockIdx.y * p.imgs_per_cta;
+  const int img1 = min(p.Bi, img0 + p.imgs_per_cta);
+  const int nimg = img1 - img0;
+  const int nch = (p.Rpad + CH - 1) / CH;
+  const int G = nimg * nch;
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(p_full + s, 128); }
+    mbar_init(c_full, 1); mbar_init(c_empty, 128); mbar_init(q_ready, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_k);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (G > 0) {
+    if (warp == 0) {
+      // ===== TMA producer =====
+      if (lane == 0) {
+        for (int g = 0; g < G; ++g) {
+          const int st = g % Cfg::kStages, it = g / Cfg::kStages;
+          const int img = img0 + g / nch, c = g % nch;
+          mbar_wait(kv_empty + st, (it & 1) ^ 1, wc, 1);
+          mbar_expect_tx(kv_full + st, Cfg::kStageBytes);
+          uint8_t* dst = kv + st * Cfg::kStageBytes;
+#pragma unroll
+          for (int kb = 0; kb < D / 64; ++kb)
+            tma_load_3d(dst + kb * Cfg::kBlockBytes, &tm_k, kb * 64, c * CH, img, kv_full + st);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ===== MMA issuer =====
+      if (lane == 0) {
+        const uint32_t kv_addr = smem_u32(kv);
+        constexpr uint32_t idesc2 = idesc_bf16(TM, D, false, true);
+        auto issue_g1 = [&](int g) {
+          const int st = g % Cfg::kStages, c = g % nch;
+          const int n = min(CH, p.Rpad - c * CH);
+          const uint32_t idesc1 = idesc_bf16(TM, n, false, false);
+          const uint32_t base = kv_addr + st * Cfg::kStageBytes;
+          const uint32_t d_tmem = tmem + ((g & 1) ? Cfg::kColS1 : Cfg::kColS0);
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k) {
+            const uint64_t bd = smem_desc(base + (k >> 2) * Cfg::kBlockBytes + (k & 3) * 32, 16, 1024);
+            mma_ts(d_tmem, tmem + Cfg::kColQ + k * 8, bd, idesc1, k > 0);
+          }
+        };
+        mbar_wait(q_ready, 0, wc, 2);
+        tc_fence_after();
+        mbar_wait(kv_full + 0, 0, wc, 3);
+        tc_fence_after();
+        issue_g1(0);
+        mma_commit(s_full + 0);
+        for (int g = 0; g < G; ++g) {
+          const int c = g % nch, ii = g / nch;
+          if (g + 1 < G) {
+            const int st1 = (g + 1) % Cfg::kStages, it1 = (g + 1) / Cfg::kStages;
+            mbar_wait(kv_full + st1, it1 & 1, wc, 4);
+            tc_fence_after();
+            issue_g1(g + 1);
+            mma_commit(s_full + ((g + 1) & 1));
+          }
+          mbar_wait(p_full + (g & 1), (g >> 1) & 1, wc, 5);
+          tc_fence_after();
+          if (c == 0 && ii > 0) {
+            mbar_wait(c_empty, (ii - 1) & 1, wc, 6);
+            tc_fence_after();
+          }
+          const int st = g % Cfg::kStages;
+          const int n = min(CH, p.Rpad - c * CH);
+          const uint32_t base = kv_addr + st * Cfg::kStageBytes;
+          const uint32_t a_tmem = tmem + ((g & 1) ? Cfg::kColS1 : Cfg::kColS0);
+          for (int ks = 0; ks < n / 16; ++ks) {
+            const uint64_t bd = smem_desc(base + ks * 2048, Cfg::kBlockBytes, 1024);
+            mma_ts(tmem + Cfg::kColC, a_tmem + ks * 8, bd, idesc2, (c > 0) || (ks > 0));
+          }
+          mma_commit(kv_empty + st);
+          if (c == nch - 1) mma_commit(c_full);
+        }
+      }
+      __syncwarp();
+    } else if (warp >= 4) {
+      // ===== softmax / epilogue warpgroup: thread = TMEM lane = word row =====
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int grow = m0 + row;
+      const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
+      // Q row -> TMEM (A operand: column c holds elements 2c, 2c+1)
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(p.qn + (size_t)grow * D);
+#pragma unroll
+        for (int blk = 0; blk < D / 32; ++blk) {          // 32 bf16 = 16 columns per store
+          uint32_t v[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 w = (grow < p.NQ) ? __ldg(src + blk * 4 + u) : make_uint4(0, 0, 0, 0);
+            v[4 * u + 0] = w.x; v[4 * u + 1] = w.y; v[4 * u + 2] = w.z; v[4 * u + 3] = w.w;
+          }
+          tmem_st16(lane_base + Cfg::kColQ + blk * 16, v);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(q_ready);
+      }
+      const float c1 = p.rho1 * kLog2eTc;
+      for (int ii = 0; ii < nimg; ++ii) {
+        const int img = img0 + ii;
+        const float* rn = p.rnorm ? p.rnorm + (size_t)img * p.Rpad : nullptr;
+        float l = 0.f, a = 0.f;
+        for (int c = 0; c < nch; ++c) {
+          const int g = ii * nch + c;
+          const int n = min(CH, p.Rpad - c * CH);
+          const uint32_t s_col = (g & 1) ? Cfg::kColS1 : Cfg::kColS0;
+          mbar_wait(s_full + (g & 1), (g >> 1) & 1, wc, 7);
+          tc_fence_after();
+          for (int h = 0; h * 32 < n; ++h) {
+            uint32_t sv[32];
+            tmem_ld32(lane_base + s_col + h * 32, sv);
+            tmem_wait_ld();
+            if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && g == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) p.dbg[row * CH + h * 32 + j] = __uint_as_float(sv[j]);
+            }
+            uint32_t pk[16];
+            const int r0 = c * CH + h * 32;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (rn && r0 + j4 * 4 < p.Rpad) mr = __ldg(reinterpret_cast<const float4*>(rn + r0 + j4 * 4));
+              const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
+              float pw[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = j4 * 4 + u;
+                const bool valid = (r0 + j) < p.R;
+                const float s = valid ? __uint_as_float(sv[j]) : 0.f;
+                const float pv = valid ? exp2f(c1 * (s - 1.f)) : 0.f;
+                l += pv;
+                pw[u] = pv * mrv[u];
+                a = fmaf(pw[u], s, a);
+              }
+              pk[j4 * 2 + 0] = pack_bf16(pw[0], pw[1]);
+              pk[j4 * 2 + 1] = pack_bf16(pw[2], pw[3]);
+            }
+            tmem_st16(lane_base + s_col + h * 16, pk);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(p_full + (g & 1));
+        }
+        // ---- epilogue of this image: ||C|| ----
+        mbar_wait(c_full, ii & 1, wc, 8);
+        tc_fence_after();
+        float c2 = 0.f;
+#pragma unroll 1
+        for (int blk = 0; blk < D / 32; ++blk) {
+          uint32_t cv[32];
+          tmem_ld32(lane_base + Cfg::kColC + blk * 32, cv);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(cv[j]);
+            c2 = fmaf(v, v, c2);
+          }
+          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ii == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) p.dbg[TM * CH + row * D + blk * 32 + j] = __uint_as_float(cv[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(c_empty);
+        if (grow < p.NQ) {
+          const float cn = sqrtf(c2) / l;
+          const size_t o = (size_t)img * p.NQ + grow;
+          p.lsum[o] = l;
+          p.cnorm[o] = cn;
+          p.rel[o] = (a / l) / fmaxf(cn, kEps);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+static int g_debug_dump = 0;   // tests only: dump S chunk 0 and C of tile 0 / image 0 into the workspace
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// kn [Bi, Rpad, D] bf16 as a 3-D tensor (d, r, image); box = 64 d x 64 rows x 1 image, 128B swizzle.
+static int make_region_map(CUtensorMap* m, const void* kn, int Bi, int Rpad, int D) {
+  PFN_encodeTiled enc = get_encode();
+  XMC_REQUIRE(enc != nullptr, XMC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)Rpad, (cuuint64_t)Bi};
+  cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)Rpad * D * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)CH, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(kn), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XMC_REQUIRE(r == CUDA_SUCCESS, XMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return XMC_OK;
+}
+
+static int num_sms() {
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
+}
+
+template <int D>
+static int launch_fwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using Cfg = FwdCfg<D>;
+  XMC_REQUIRE(ws && ws_bytes >= 64, XMC_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  CUtensorMap tm;
+  if (int rc = make_region_map(&tm, w.kn, w.Bi, w.Rpad, D)) return rc;
+  TcFwdParams p{};
+  p.qn = static_cast<const __nv_bfloat16*>(w.qn);
+  p.rnorm = w.rnorm; p.NQ = w.NQ; p.Bi = w.Bi; p.R = w.R; p.Rpad = w.Rpad; p.rho1 = w.rho1;
+  p.lsum = w.lsum; p.cnorm = w.cnorm; p.rel = w.rel;
+  p.err = static_cast<int*>(ws);
+  p.dbg = (g_debug_dump && ws_bytes >= 64 + sizeof(float) * (size_t)(TM * CH + TM * D))
+              ? reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
+  const int tiles = (w.NQ + TM - 1) / TM;
+  int splits = num_sms() / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > w.Bi) splits = w.Bi;
+  p.imgs_per_cta = (w.Bi + splits - 1) / splits;
+  splits = (w.Bi + p.imgs_per_cta - 1) / p.imgs_per_cta;
+  XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  wr_fwd_tc_kernel<D><<<dim3(tiles, splits), kTcThreads, Cfg::kSmemBytes, st>>>(tm, p);
+  return cuda_fail(cudaGetLastError(), "wr_fwd_tc_kernel launch");
+}
+
+size_t wordregion_tc_workspace_bytes(int, int, int, int, int D) {
+  return 64 + sizeof(float) * (size_t)(TM * CH + TM * D);   // error word + optional debug dump
+}
+
+int wordregion_tc_forward(const WrParams& p, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+  switch (D) {
+    case 64: return launch_fwd_tc<64>(p, ws, ws_bytes, st);
+    case 128: return launch_fwd_tc<128>(p, ws, ws_bytes, st);
+    case 256: return launch_fwd_tc<256>(p, ws, ws_bytes, st);
+  }
+  set_error("word-region D=%d unsupported (64, 128, 256)", D);
   return XMC_ERR_UNSUPPORTED;
 }
+
 int wordregion_tc_backward(const WrParams&, int, void*, size_t, cudaStream_t) {
   set_error("tcgen05 word-region backward not built yet");
   return XMC_ERR_UNSUPPORTED;
 }
+
 }  // namespace xmc
+
+// Not part of the public ABI (not in include/xmc_loss.h): test hook for the TMEM debug dump.
+extern "C" void xmc_internal_set_debug_dump(int on) { xmc::g_debug_dump = on; }

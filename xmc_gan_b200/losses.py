@@ -158,6 +158,9 @@ class SimLossFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # word–region attention contrastive loss
 # ------------------------------------------------------------------------------------------------
+TC_BACKWARD = False   # flipped when wordregion_tc.cu gains its backward kernel
+
+
 def _ceil_to(x, m):
     return (x + m - 1) // m * m
 
@@ -237,8 +240,14 @@ class WordLossFn(torch.autograd.Function):
                                    rows_total, Bc, go)
         grel = ops.word_scores_backward(rel, m_all, scores, dscores, T, rho2)
         D = qn.shape[2]
-        dqn, dkn, drnorm = ops.wordregion_backward(path, qn.view(-1, D), kn, rnorm if has_rn else None, R, rho1,
-                                                   lsum, cnorm, rel, grel)
+        if path == _lib.PATH_BF16_TCGEN05 and not TC_BACKWARD:
+            # interim: the tcgen05 backward kernel is not built yet -> run the fp32 CUDA-core backward
+            # kernel on the (bf16-rounded) operands the forward used.  Still libxmcloss, never PyTorch.
+            dqn, dkn, drnorm = ops.wordregion_backward(_lib.PATH_FP32_SIMT, qn.view(-1, D).float(), kn.float(),
+                                                       rnorm if has_rn else None, R, rho1, lsum, cnorm, rel, grel)
+        else:
+            dqn, dkn, drnorm = ops.wordregion_backward(path, qn.view(-1, D), kn, rnorm if has_rn else None, R, rho1,
+                                                       lsum, cnorm, rel, grel)
         dreg = dwords = None
         if need_reg:
             dreg = ops.normalize_transpose_backward(kn, rnorm, dkn, drnorm, R, reg_dtype).view(reg_shape)

@@ -67,6 +67,7 @@ class CudaOps:
         self.L = _lib.lib()
         self.launches = 0      # kernels launched through this backend (bench.py's gpu_launches)
         self.events = None     # name -> [(start, stop)] CUDA events when kernel timing is on
+        self.last_workspace = None
 
     def enable_timing(self, on=True):
         """Record CUDA events (current stream) around the named hot kernels; see kernel_ms()."""
@@ -196,8 +197,11 @@ class CudaOps:
         return dx
 
     def _workspace(self, path, NQ, Bi, R, Rpad, D, dev):
+        """Caller-owned scratch of the tcgen05 path; word 0 is its error flag (0 = ok), so zero-filled."""
         n = self.L.xmc_wordregion_workspace_bytes(path, NQ, Bi, R, Rpad, D)
-        return (torch.empty(n, device=dev, dtype=torch.uint8) if n else None), n
+        ws = torch.zeros(n, device=dev, dtype=torch.uint8) if n else None
+        self.last_workspace = ws
+        return ws, n
 
     def wordregion_forward(self, path, qn, kn, rnorm, R, rho1):
         _cuda(qn, kn, rnorm)
