@@ -18,8 +18,8 @@
  *  - Return 0 (XMC_OK) on success, otherwise an xmc_status; xmc_last_error() returns a
  *    thread-local message.  No exceptions, no exit(), no stdout.  There is NO CPU fallback.
  *  - Matrices are row-major and contiguous unless a leading dimension is given.  Base pointers
- *    must be 16-byte aligned.  D must be a multiple of 128 for the similarity losses (256, 512
- *    and 768 in the reference) and one of 64/128/256 for the word-region kernels.
+ *    must be 16-byte aligned.  D must be a multiple of 4 and <= 768 for the similarity losses
+ *    (256, 512, 768 in the reference) and one of 64/128/256 for the word-region kernels.
  *  - dtype: XMC_F32 or XMC_BF16 is the STORAGE type of embedding operands; all arithmetic and
  *    all statistics / gradients of statistics are fp32.
  */
@@ -156,17 +156,20 @@ size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad,
  *   lsum  = sum_r exp(rho1*(s_qr - 1))     (softmax denominator, constant shift rho1)
  *   cnorm = || c_q ||                       (norm of the attended context)
  *   rel   = cos(e_q, c_q)
+ * chat[Bi,NQ,D] bf16 (tcgen05 path only, nullable): the unit attended contexts c_q/||c_q||, saved
+ * for the backward pass when gradients are needed (the fp32 path recomputes them and ignores it).
  * Rpad must be a multiple of 16 and >= R. */
 int xmc_wordregion_forward(int path, const void* qn, const void* kn, const float* rnorm,
                            int NQ, int Bi, int R, int Rpad, int D, float rho1,
-                           float* lsum, float* cnorm, float* rel,
+                           float* lsum, float* cnorm, float* rel, void* chat,
                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* grel[Bi,NQ] = d loss / d rel.  dqn[NQ,D], dkn[Bi,Rpad,D], drnorm[Bi,Rpad] (nullable iff rnorm
- * is NULL) are fp32 and are ACCUMULATED into: the caller zero-fills them first. */
+ * is NULL) are fp32 and are ACCUMULATED into: the caller zero-fills them first.
+ * chat: what the forward saved (required by the tcgen05 path, ignored by the fp32 path). */
 int xmc_wordregion_backward(int path, const void* qn, const void* kn, const float* rnorm,
                             int NQ, int Bi, int R, int Rpad, int D, float rho1,
-                            const float* lsum, const float* cnorm, const float* rel,
+                            const float* lsum, const float* cnorm, const float* rel, const void* chat,
                             const float* grel, float* dqn, float* dkn, float* drnorm,
                             void* workspace, size_t workspace_bytes, void* stream);
 

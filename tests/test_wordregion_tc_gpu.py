@@ -44,7 +44,7 @@ def test_tmem_dump_matches_matmul(ops, D):
     hook.argtypes, hook.restype = [ctypes.c_int], None
     hook(1)
     try:
-        lsum, cnorm, rel = ops.wordregion_forward(_lib.PATH_BF16_TCGEN05, qn, kn, rnorm, R, 5.0)
+        lsum, cnorm, rel, _ = ops.wordregion_forward(_lib.PATH_BF16_TCGEN05, qn, kn, rnorm, R, 5.0)
         assert _err_word(ops) == 0, "mbarrier wait timed out inside the kernel"
         dump = ops.last_workspace[64:].view(torch.float32)
     finally:
@@ -71,15 +71,44 @@ def test_statistics_vs_fp32_kernel(ops, B, D, T_, R, raw_values):
     from xmc_gan_b200 import _lib
     qn, kn, rnorm, _ = _operands(ops, B, D, T_, R, seed=B + R)
     rn = rnorm if raw_values else None
-    l1, c1, r1 = ops.wordregion_forward(_lib.PATH_BF16_TCGEN05, qn, kn, rn, R, 5.0)
+    l1, c1, r1, _ = ops.wordregion_forward(_lib.PATH_BF16_TCGEN05, qn, kn, rn, R, 5.0)
     assert _err_word(ops) == 0
-    l0, c0, r0 = ops.wordregion_forward(_lib.PATH_FP32_SIMT, qn.float(), kn.float(), rn, R, 5.0)
+    l0, c0, r0, _ = ops.wordregion_forward(_lib.PATH_FP32_SIMT, qn.float(), kn.float(), rn, R, 5.0)
     assert nerr(l1, l0) < 1e-3, nerr(l1, l0)
     assert nerr(c1, c0) < 1e-2, nerr(c1, c0)
     assert float((r1 - r0).abs().max()) < 2e-2, float((r1 - r0).abs().max())
 
 
-@pytest.mark.parametrize("B,D,T_,R", [(32, 256, 18, 289), (12, 128, 9, 64), (64, 256, 18, 289)])
+@pytest.mark.parametrize("B,D,T_,R", [(8, 256, 18, 289), (32, 256, 18, 289), (5, 128, 7, 40), (3, 256, 12, 17),
+                                      (40, 256, 20, 256), (20, 128, 32, 100)])
+@pytest.mark.parametrize("raw_values", [True, False])
+def test_backward_vs_fp32_kernel(ops, B, D, T_, R, raw_values):
+    """tcgen05 backward (dQ, dKhat, d rnorm) against the fp32 CUDA-core backward on the same operands,
+    statistics and upstream gradient."""
+    from xmc_gan_b200 import _lib
+    qn, kn, rnorm, _ = _operands(ops, B, D, T_, R, seed=7 * B + R)
+    rn = rnorm if raw_values else None
+    l1, c1, r1, chat = ops.wordregion_forward(_lib.PATH_BF16_TCGEN05, qn, kn, rn, R, 5.0, save_context=True)
+    assert _err_word(ops) == 0
+    g = torch.Generator().manual_seed(B)
+    grel = torch.randn(l1.shape, generator=g).cuda() * 0.1
+    dq1, dk1, dr1 = ops.wordregion_backward(_lib.PATH_BF16_TCGEN05, qn, kn, rn, R, 5.0, l1, c1, r1, grel, chat)
+    assert _err_word(ops) == 0, "mbarrier wait timed out inside the backward kernel"
+    dq0, dk0, dr0 = ops.wordregion_backward(_lib.PATH_FP32_SIMT, qn.float(), kn.float(), rn, R, 5.0, l1, c1, r1, grel)
+    # unit contexts saved by the forward
+    s_all = torch.einsum('qd,ird->iqr', qn.float(), kn.float())
+    valid = (torch.arange(kn.shape[1], device="cuda") < R).float()
+    pw = torch.exp(5.0 * (s_all - 1.0)) * valid * (rnorm.unsqueeze(1) if raw_values else 1.0)
+    ctx = torch.einsum('iqr,ird->iqd', pw, kn.float())
+    chat_ref = ctx / ctx.norm(dim=-1, keepdim=True).clamp_min(1e-30)
+    assert nerr(chat, chat_ref) < 1e-2, nerr(chat, chat_ref)
+    assert nerr(dq1, dq0) < 1.5e-2, nerr(dq1, dq0)
+    assert nerr(dk1, dk0) < 1.5e-2, nerr(dk1, dk0)
+    if raw_values:
+        assert nerr(dr1, dr0) < 1.5e-2, nerr(dr1, dr0)
+
+
+@pytest.mark.parametrize("B,D,T_,R", [(32, 256, 18, 289), (12, 128, 9, 64), (64, 256, 18, 289), (9, 64, 5, 30)])
 def test_word_loss_bf16_vs_oracle(B, D, T_, R):
     from xmc_gan_b200 import train_gan as T
     words, regions, mask = word_inputs(B, D, T_, R, seed=3 * B)

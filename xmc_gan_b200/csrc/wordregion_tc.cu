@@ -47,6 +47,7 @@ struct TcFwdParams {
   int NQ, Bi, R, Rpad;
   float rho1;
   float* lsum; float* cnorm; float* rel;
+  __nv_bfloat16* chat;         // [Bi, NQ, D] unit contexts saved for backward, or null
   int imgs_per_cta;
   int* err;
   float* dbg;                  // optional: S chunk 0 and C of the first tile/image (tests)
@@ -248,6 +249,28 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
             for (int j = 0; j < 32; ++j) p.dbg[TM * CH + row * D + blk * 32 + j] = __uint_as_float(cv[j]);
           }
         }
+        if (p.chat) {
+          // second TMEM pass: unit context rows -> bf16 -> global (saved for the backward kernel)
+          const float inv_c = 1.f / fmaxf(sqrtf(c2), kEps * l);
+          uint4* dst = reinterpret_cast<uint4*>(p.chat + ((size_t)img * p.NQ + grow) * D);
+#pragma unroll 1
+          for (int blk = 0; blk < D / 32; ++blk) {
+            uint32_t cv[32];
+            tmem_ld32(lane_base + Cfg::kColC + blk * 32, cv);
+            tmem_wait_ld();
+            if (grow < p.NQ) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint4 o;
+                o.x = pack_bf16(__uint_as_float(cv[8 * u + 0]) * inv_c, __uint_as_float(cv[8 * u + 1]) * inv_c);
+                o.y = pack_bf16(__uint_as_float(cv[8 * u + 2]) * inv_c, __uint_as_float(cv[8 * u + 3]) * inv_c);
+                o.z = pack_bf16(__uint_as_float(cv[8 * u + 4]) * inv_c, __uint_as_float(cv[8 * u + 5]) * inv_c);
+                o.w = pack_bf16(__uint_as_float(cv[8 * u + 6]) * inv_c, __uint_as_float(cv[8 * u + 7]) * inv_c);
+                dst[blk * 4 + u] = o;
+              }
+            }
+          }
+        }
         tc_fence_before();
         mbar_arrive(c_empty);
         if (grow < p.NQ) {
@@ -315,6 +338,7 @@ static int launch_fwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
   p.qn = static_cast<const __nv_bfloat16*>(w.qn);
   p.rnorm = w.rnorm; p.NQ = w.NQ; p.Bi = w.Bi; p.R = w.R; p.Rpad = w.Rpad; p.rho1 = w.rho1;
   p.lsum = w.lsum; p.cnorm = w.cnorm; p.rel = w.rel;
+  p.chat = static_cast<__nv_bfloat16*>(w.chat);
   p.err = static_cast<int*>(ws);
   p.dbg = (g_debug_dump && ws_bytes >= 64 + sizeof(float) * (size_t)(TM * CH + TM * D))
               ? reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
@@ -343,8 +367,361 @@ int wordregion_tc_forward(const WrParams& p, int D, void* ws, size_t ws_bytes, c
   return XMC_ERR_UNSUPPORTED;
 }
 
-int wordregion_tc_backward(const WrParams&, int, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 word-region backward not built yet");
+// =====================================================================================================
+// Backward.  Tile = (128 word rows) x (one image); the CTA keeps its word tile Q in smem and the
+// gradient dQ [128 x D] in TMEM across ALL the images it visits; per image the saved unit contexts
+// Chat arrive by TMA, the regions in 64-row chunks through a 2-stage ring.  Per chunk:
+//   S = Q Khat^T, W = Chat Khat^T                     (SS MMAs, K-major operands)          -> TMEM
+//   X = dS + gamma*alpha', Y = -gamma*rel*alpha'      (2 warpgroups, bf16, 128B-swizzled smem tiles)
+//   dQ   += X Khat_chunk                              (A = X K-major, B = Khat MN-major)   -> TMEM, persistent
+//   dK^T  = Q^T X + Chat^T Y   [D x 64]               (A = Q / Chat as MN-major, B = X / Y MN-major) -> TMEM
+//   dK^T -> red.global.add into dkn (coalesced along d);  column sums of alpha*d alpha' -> drnorm
+// The same smem bytes serve as K-major and as MN-major operands; nothing of size Bi x Bc x T x R
+// ever reaches global memory.
+// Warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 elementwise WG0 (chunk cols 0-31, dK^T rows d<128),
+// 8-11 elementwise WG1 (cols 32-63, d>=128).
+// =====================================================================================================
+constexpr int kBwdThreads = 384;
+
+template <int D>
+struct BwdCfg {
+  static constexpr int kQBytes = TM * D * 2;       // Q / Chat tile: D/64 blocks of [128 rows x 128 B]
+  static constexpr int kQBlock = TM * 128;
+  static constexpr int kKvStage = CH * D * 2;      // region chunk: D/64 blocks of [64 rows x 128 B]
+  static constexpr int kKvBlock = CH * 128;
+  static constexpr int kXBytes = TM * 128;         // X / Y tile: [128 t x 64 r] bf16
+  static constexpr int kOffQ = 0, kOffC = kQBytes, kOffKv = 2 * kQBytes, kOffX = kOffKv + 2 * kKvStage,
+                       kOffY = kOffX + kXBytes, kOffBar = kOffY + kXBytes;
+  static constexpr int kSmemBytes = kOffBar + 256 + 1024;
+  static constexpr int kTilesD = D / 128;          // M-tiles of dK^T
+  static constexpr int kColDQ = 0, kColS = D, kColW = D + CH, kColDK = D + 2 * CH;
+  static_assert(kColDK + kTilesD * CH <= 512, "TMEM budget");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+struct TcBwdParams {
+  const float* rnorm;
+  int NQ, Bi, R, Rpad;
+  float rho1;
+  const float* lsum; const float* cnorm; const float* rel; const float* grel;
+  float* dqn; float* dkn; float* drnorm;
+  int imgs_per_cta;
+  int* err;
+};
+
+// lane L returns sum over the warp of v[L] (31 shuffles instead of 160)
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float keep = hi ? v[k + off] : v[k];
+      const float send = hi ? v[k] : v[k + off];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_c,
+                 const __grid_constant__ CUtensorMap tm_k, TcBwdParams p) {
+  using Cfg = BwdCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem + Cfg::kOffQ;
+  uint8_t* Cs = smem + Cfg::kOffC;
+  uint8_t* kv = smem + Cfg::kOffKv;
+  uint8_t* Xs = smem + Cfg::kOffX;
+  uint8_t* Ys = smem + Cfg::kOffY;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* ch_full = bars + 1;
+  uint64_t* ch_empty = bars + 2;
+  uint64_t* kv_full = bars + 3;    // [2]
+  uint64_t* kv_empty = bars + 5;   // [2]
+  uint64_t* sw_full = bars + 7;
+  uint64_t* xy_full = bars + 8;
+  uint64_t* dk_full = bars + 9;
+  uint64_t* dk_empty = bars + 10;
+  uint64_t* dq_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  int* abort_flag = reinterpret_cast<int*>(tmem_slot + 1);
+  const WaitCtx wc{abort_flag, p.err};
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TM;
+  const int img0 = blockIdx.y * p.imgs_per_cta;
+  const int nimg = min(p.Bi, img0 + p.imgs_per_cta) - img0;
+  const int nch = (p.Rpad + CH - 1) / CH;
+  const int G = nimg * nch;
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    mbar_init(q_full, 1); mbar_init(ch_full, 1); mbar_init(ch_empty, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
+    mbar_init(sw_full, 1); mbar_init(xy_full, 256); mbar_init(dk_full, 1); mbar_init(dk_empty, 256);
+    mbar_init(dq_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_c); tma_prefetch_desc(&tm_k); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (G > 0) {
+    if (warp == 0) {
+      // ===== TMA producer =====
+      if (lane == 0) {
+        mbar_expect_tx(q_full, Cfg::kQBytes);
+#pragma unroll
+        for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(Qs + kb * Cfg::kQBlock, &tm_q, kb * 64, m0, q_full);
+        for (int g = 0; g < G; ++g) {
+          const int st = g & 1, ii = g / nch, c = g % nch;
+          mbar_wait(kv_empty + st, ((g >> 1) & 1) ^ 1, wc, 11);
+          mbar_expect_tx(kv_full + st, Cfg::kKvStage);
+#pragma unroll
+          for (int kb = 0; kb < D / 64; ++kb)
+            tma_load_3d(kv + st * Cfg::kKvStage + kb * Cfg::kKvBlock, &tm_k, kb * 64, c * CH, img0 + ii, kv_full + st);
+          if (c == 0) {
+            mbar_wait(ch_empty, (ii & 1) ^ 1, wc, 12);
+            mbar_expect_tx(ch_full, Cfg::kQBytes);
+#pragma unroll
+            for (int kb = 0; kb < D / 64; ++kb)
+              tma_load_3d(Cs + kb * Cfg::kQBlock, &tm_c, kb * 64, m0, img0 + ii, ch_full);
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ===== MMA issuer =====
+      if (lane == 0) {
+        const uint32_t q_addr = smem_u32(Qs), c_addr = smem_u32(Cs), kv_addr = smem_u32(kv);
+        const uint32_t x_addr = smem_u32(Xs), y_addr = smem_u32(Ys);
+        constexpr uint32_t idesc_dq = idesc_bf16(TM, D, false, true);
+        auto chunk_n = [&](int g) { return min(CH, p.Rpad - (g % nch) * CH); };
+        auto issue_scores = [&](int g, uint32_t a_addr, uint32_t d_col) {   // [128 x n] = A[128 x D] . Khat_chunk^T
+          const uint32_t idesc = idesc_bf16(TM, chunk_n(g), false, false);
+          const uint32_t b_addr = kv_addr + (g & 1) * Cfg::kKvStage;
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k) {
+            const uint64_t ad = smem_desc(a_addr + (k >> 2) * Cfg::kQBlock + (k & 3) * 32, 16, 1024);
+            const uint64_t bd = smem_desc(b_addr + (k >> 2) * Cfg::kKvBlock + (k & 3) * 32, 16, 1024);
+            mma_ss(tmem + d_col, ad, bd, idesc, k > 0);
+          }
+        };
+        mbar_wait(q_full, 0, wc, 13);
+        mbar_wait(kv_full + 0, 0, wc, 14);
+        tc_fence_after();
+        issue_scores(0, q_addr, Cfg::kColS);
+        mbar_wait(ch_full, 0, wc, 15);
+        tc_fence_after();
+        issue_scores(0, c_addr, Cfg::kColW);
+        mma_commit(sw_full);
+        for (int g = 0; g < G; ++g) {
+          const int c = g % nch, st = g & 1, n = chunk_n(g);
+          mbar_wait(xy_full, g & 1, wc, 16);
+          if (g > 0) mbar_wait(dk_empty, (g - 1) & 1, wc, 17);
+          tc_fence_after();
+          // dK^T tiles: [128 d x n] = Q^T X + Chat^T Y   (contraction over the 128 word rows)
+          const uint32_t idesc_dk = idesc_bf16(TM, n, true, true);
+#pragma unroll
+          for (int h = 0; h < Cfg::kTilesD; ++h) {
+#pragma unroll
+            for (int kt = 0; kt < TM / 16; ++kt) {
+              const uint64_t ad = smem_desc(q_addr + 2 * h * Cfg::kQBlock + kt * 2048, Cfg::kQBlock, 1024);
+              const uint64_t bd = smem_desc(x_addr + kt * 2048, Cfg::kXBytes, 1024);
+              mma_ss(tmem + Cfg::kColDK + h * CH, ad, bd, idesc_dk, kt > 0);
+            }
+#pragma unroll
+            for (int kt = 0; kt < TM / 16; ++kt) {
+              const uint64_t ad = smem_desc(c_addr + 2 * h * Cfg::kQBlock + kt * 2048, Cfg::kQBlock, 1024);
+              const uint64_t bd = smem_desc(y_addr + kt * 2048, Cfg::kXBytes, 1024);
+              mma_ss(tmem + Cfg::kColDK + h * CH, ad, bd, idesc_dk, true);
+            }
+          }
+          mma_commit(dk_full);
+          if (c == nch - 1) mma_commit(ch_empty);
+          // dQ += X Khat_chunk
+          for (int ks = 0; ks < n / 16; ++ks) {
+            const uint64_t ad = smem_desc(x_addr + ks * 32, 16, 1024);
+            const uint64_t bd = smem_desc(kv_addr + st * Cfg::kKvStage + ks * 2048, Cfg::kKvBlock, 1024);
+            mma_ss(tmem + Cfg::kColDQ, ad, bd, idesc_dq, (g > 0) || (ks > 0));
+          }
+          mma_commit(kv_empty + st);
+          if (g + 1 < G) {
+            mbar_wait(kv_full + ((g + 1) & 1), ((g + 1) >> 1) & 1, wc, 18);
+            tc_fence_after();
+            issue_scores(g + 1, q_addr, Cfg::kColS);
+            if ((g + 1) % nch == 0) {
+              mbar_wait(ch_full, ((g + 1) / nch) & 1, wc, 19);
+              tc_fence_after();
+            }
+            issue_scores(g + 1, c_addr, Cfg::kColW);
+            mma_commit(sw_full);
+          }
+        }
+        mma_commit(dq_full);
+      }
+      __syncwarp();
+    } else if (warp >= 4) {
+      // ===== elementwise warpgroups: thread = TMEM lane = word row (S/W) or feature d (dK^T) =====
+      const int h = (warp - 4) >> 2;              // 0: chunk cols 0-31, 1: cols 32-63
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int grow = m0 + row;
+      const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
+      const float c1 = p.rho1 * kLog2eTc;
+      const int col0 = h * 32;
+      for (int ii = 0; ii < nimg; ++ii) {
+        const int img = img0 + ii;
+        const float* rn = p.rnorm ? p.rnorm + (size_t)img * p.Rpad : nullptr;
+        float inv_l = 1.f, gam = 0.f, relv = 0.f;
+        if (grow < p.NQ) {
+          const size_t o = (size_t)img * p.NQ + grow;
+          inv_l = 1.f / __ldg(p.lsum + o);
+          gam = __ldg(p.grel + o) / fmaxf(__ldg(p.cnorm + o), kEps);
+          relv = __ldg(p.rel + o);
+        }
+        for (int c = 0; c < nch; ++c) {
+          const int g = ii * nch + c;
+          const int n = min(CH, p.Rpad - c * CH);
+          mbar_wait(sw_full, g & 1, wc, 20);
+          tc_fence_after();
+          if (col0 < n) {
+            uint32_t sv[32], wv[32];
+            tmem_ld32(lane_base + Cfg::kColS + col0, sv);
+            tmem_ld32(lane_base + Cfg::kColW + col0, wv);
+            tmem_wait_ld();
+            const int r0 = c * CH + col0;
+            float z[32];
+            uint32_t xp[16], yp[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (rn && r0 + j4 * 4 < p.Rpad) mr = __ldg(reinterpret_cast<const float4*>(rn + r0 + j4 * 4));
+              const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
+              float xv[4], yv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = j4 * 4 + u;
+                const bool valid = (r0 + j) < p.R;
+                const float s = valid ? __uint_as_float(sv[j]) : 0.f;
+                const float w = valid ? __uint_as_float(wv[j]) : 0.f;
+                const float al = valid ? exp2f(c1 * (s - 1.f)) * inv_l : 0.f;    // alpha
+                const float alp = al * mrv[u];                                   // alpha' = alpha * ||v_r||
+                const float dap = gam * (s - relv * w);                          // d loss / d alpha'
+                xv[u] = fmaf(p.rho1 * alp, dap, gam * alp);                      // dS + gamma*alpha'
+                yv[u] = -gam * relv * alp;
+                z[j] = al * dap;
+              }
+              xp[j4 * 2 + 0] = pack_bf16(xv[0], xv[1]); xp[j4 * 2 + 1] = pack_bf16(xv[2], xv[3]);
+              yp[j4 * 2 + 0] = pack_bf16(yv[0], yv[1]); yp[j4 * 2 + 1] = pack_bf16(yv[2], yv[3]);
+            }
+            // row `row` of the [128 x 64] bf16 tiles, 16-byte chunks XOR-swizzled by (row & 7)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int phys = ((col0 >> 3) + u) ^ (row & 7);
+              *reinterpret_cast<uint4*>(Xs + row * 128 + phys * 16) = make_uint4(xp[4 * u], xp[4 * u + 1], xp[4 * u + 2], xp[4 * u + 3]);
+              *reinterpret_cast<uint4*>(Ys + row * 128 + phys * 16) = make_uint4(yp[4 * u], yp[4 * u + 1], yp[4 * u + 2], yp[4 * u + 3]);
+            }
+            if (rn) {
+              const float colsum = warp_transpose_sum32(z, lane);      // column (r0 + lane) over this warp's 32 rows
+              if (r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(xy_full);
+          // drain dK^T tile h of this chunk
+          mbar_wait(dk_full, g & 1, wc, 21);
+          tc_fence_after();
+          if (h < Cfg::kTilesD) {
+            float* dst = p.dkn + ((size_t)img * p.Rpad + c * CH) * D + h * 128 + row;
+            for (int jb = 0; jb < n; jb += 32) {
+              uint32_t dv[32];
+              tmem_ld32(lane_base + Cfg::kColDK + h * CH + jb, dv);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (jb + j < n && c * CH + jb + j < p.R) atomicAdd(dst + (size_t)(jb + j) * D, __uint_as_float(dv[j]));
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(dk_empty);
+        }
+      }
+      // ---- dQ of this CTA's word tile (summed over its images) ----
+      mbar_wait(dq_full, 0, wc, 22);
+      tc_fence_after();
+      if (grow < p.NQ) {
+        float* dst = p.dqn + (size_t)grow * D + h * (D / 2);
+#pragma unroll 1
+        for (int blk = 0; blk < D / 64; ++blk) {
+          uint32_t dv[32];
+          tmem_ld32(lane_base + Cfg::kColDQ + h * (D / 2) + blk * 32, dv);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + blk * 32 + j, __uint_as_float(dv[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// 2-D [rows, D] / 3-D [outer, rows, D] bf16 tensor maps, box = 64 d x box_rows (x 1), 128B swizzle
+static int make_rows_map(CUtensorMap* m, const void* base, int outer, int rows, int D, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  XMC_REQUIRE(enc != nullptr, XMC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)rows, (cuuint64_t)outer};
+  cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)rows * D * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, outer > 0 ? 3 : 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XMC_REQUIRE(r == CUDA_SUCCESS, XMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return XMC_OK;
+}
+
+template <int D>
+static int launch_bwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using Cfg = BwdCfg<D>;
+  XMC_REQUIRE(ws && ws_bytes >= 64, XMC_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
+  XMC_REQUIRE(w.chat != nullptr, XMC_ERR_INVALID_ARG, "the tcgen05 backward needs the unit contexts saved by the forward (chat)");
+  CUtensorMap tq, tcm, tk;
+  if (int rc = make_rows_map(&tq, w.qn, 0, w.NQ, D, TM)) return rc;
+  if (int rc = make_rows_map(&tcm, w.chat, w.Bi, w.NQ, D, TM)) return rc;
+  if (int rc = make_region_map(&tk, w.kn, w.Bi, w.Rpad, D)) return rc;
+  TcBwdParams p{};
+  p.rnorm = w.rnorm; p.NQ = w.NQ; p.Bi = w.Bi; p.R = w.R; p.Rpad = w.Rpad; p.rho1 = w.rho1;
+  p.lsum = w.lsum; p.cnorm = w.cnorm; p.rel = w.rel; p.grel = w.grel;
+  p.dqn = w.dqn; p.dkn = w.dkn; p.drnorm = w.drnorm;
+  p.err = static_cast<int*>(ws);
+  const int tiles = (w.NQ + TM - 1) / TM;
+  int splits = num_sms() / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > w.Bi) splits = w.Bi;
+  p.imgs_per_cta = (w.Bi + splits - 1) / splits;
+  splits = (w.Bi + p.imgs_per_cta - 1) / p.imgs_per_cta;
+  XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_bwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  wr_bwd_tc_kernel<D><<<dim3(tiles, splits), kBwdThreads, Cfg::kSmemBytes, st>>>(tq, tcm, tk, p);
+  return cuda_fail(cudaGetLastError(), "wr_bwd_tc_kernel launch");
+}
+
+int wordregion_tc_backward(const WrParams& p, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+  switch (D) {
+    case 128: return launch_bwd_tc<128>(p, ws, ws_bytes, st);
+    case 256: return launch_bwd_tc<256>(p, ws, ws_bytes, st);
+  }
+  set_error("tcgen05 word-region backward supports D = 128, 256 (got %d)", D);
   return XMC_ERR_UNSUPPORTED;
 }
 

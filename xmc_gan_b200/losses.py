@@ -158,7 +158,7 @@ class SimLossFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # word–region attention contrastive loss
 # ------------------------------------------------------------------------------------------------
-TC_BACKWARD = False   # flipped when wordregion_tc.cu gains its backward kernel
+TC_BACKWARD_DIMS = (128, 256)   # D handled by the tcgen05 backward kernel (others: fp32 kernel)
 
 
 def _ceil_to(x, m):
@@ -196,7 +196,10 @@ class WordLossFn(torch.autograd.Function):
         kn, rnorm = ops.normalize_transpose(reg, Rpad, op_dtype)   # [Bi, Rpad, D]
         qn2 = qn.view(Bc * T, D)
         rn = None if normalize_values else rnorm
-        lsum, cnorm, rel = ops.wordregion_forward(path, qn2, kn, rn, R, rho1)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        use_tc_bwd = path == _lib.PATH_BF16_TCGEN05 and D in TC_BACKWARD_DIMS
+        lsum, cnorm, rel, chat = ops.wordregion_forward(path, qn2, kn, rn, R, rho1,
+                                                        save_context=need_grad and use_tc_bwd)
         scores = ops.word_scores(rel, m_all, Bc, T, rho2)          # [Bi, Bc_g]
 
         lab, diag, rc = _label_args(labels, comm, Bi)
@@ -214,18 +217,20 @@ class WordLossFn(torch.autograd.Function):
         ctx.comm, ctx.ops = comm, ops
         ctx.meta = (path, R, T, float(rho1), float(rho2), float(rho3), diag, num_pos, rows_total, Bc,
                     tuple(regions.shape), regions.dtype, words.dtype)
-        ctx.has = (rn is not None, m_all is not None, lab is not None, row_div is not None, col_div is not None)
+        ctx.has = (rn is not None, m_all is not None, lab is not None, row_div is not None, col_div is not None,
+                   chat is not None)
         e = torch.empty(0)
         ctx.save_for_backward(qn, qnorm, kn, rnorm, lsum, cnorm, rel, scores, row_stats, col_stats,
                               m_all if m_all is not None else e, lab if lab is not None else e,
-                              row_div if row_div is not None else e, col_div if col_div is not None else e)
+                              row_div if row_div is not None else e, col_div if col_div is not None else e,
+                              chat if chat is not None else e)
         return loss3[0]
 
     @staticmethod
     def backward(ctx, grad_out):
         (qn, qnorm, kn, rnorm, lsum, cnorm, rel, scores, row_stats, col_stats,
-         m_all, lab, row_div, col_div) = ctx.saved_tensors
-        has_rn, has_m, has_lab, has_rd, has_cd = ctx.has
+         m_all, lab, row_div, col_div, chat) = ctx.saved_tensors
+        has_rn, has_m, has_lab, has_rd, has_cd, has_chat = ctx.has
         m_all = m_all if has_m else None
         lab = lab if has_lab else None
         row_div = row_div if has_rd else None
@@ -240,14 +245,14 @@ class WordLossFn(torch.autograd.Function):
                                    rows_total, Bc, go)
         grel = ops.word_scores_backward(rel, m_all, scores, dscores, T, rho2)
         D = qn.shape[2]
-        if path == _lib.PATH_BF16_TCGEN05 and not TC_BACKWARD:
-            # interim: the tcgen05 backward kernel is not built yet -> run the fp32 CUDA-core backward
-            # kernel on the (bf16-rounded) operands the forward used.  Still libxmcloss, never PyTorch.
+        if path == _lib.PATH_BF16_TCGEN05 and not has_chat:
+            # D outside the tcgen05 backward kernel's set: run the fp32 CUDA-core backward kernel on the
+            # (bf16-rounded) operands the forward used.  Still libxmcloss, never PyTorch.
             dqn, dkn, drnorm = ops.wordregion_backward(_lib.PATH_FP32_SIMT, qn.view(-1, D).float(), kn.float(),
                                                        rnorm if has_rn else None, R, rho1, lsum, cnorm, rel, grel)
         else:
             dqn, dkn, drnorm = ops.wordregion_backward(path, qn.view(-1, D), kn, rnorm if has_rn else None, R, rho1,
-                                                       lsum, cnorm, rel, grel)
+                                                       lsum, cnorm, rel, grel, chat if has_chat else None)
         dreg = dwords = None
         if need_reg:
             dreg = ops.normalize_transpose_backward(kn, rnorm, dkn, drnorm, R, reg_dtype).view(reg_shape)

@@ -203,7 +203,8 @@ class CudaOps:
         self.last_workspace = ws
         return ws, n
 
-    def wordregion_forward(self, path, qn, kn, rnorm, R, rho1):
+    def wordregion_forward(self, path, qn, kn, rnorm, R, rho1, save_context=False):
+        """-> lsum, cnorm, rel [Bi, NQ] (+ chat [Bi, NQ, D] bf16 on the tcgen05 path when asked)."""
         _cuda(qn, kn, rnorm)
         NQ, D = qn.shape
         Bi, Rpad, _ = kn.shape
@@ -211,14 +212,17 @@ class CudaOps:
         lsum = torch.empty(Bi, NQ, device=dev, dtype=torch.float32)
         cnorm = torch.empty_like(lsum)
         rel = torch.empty_like(lsum)
+        chat = None
+        if save_context and path == _lib.PATH_BF16_TCGEN05:
+            chat = torch.empty(Bi, NQ, D, device=dev, dtype=torch.bfloat16)
         ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
         with torch.cuda.device_of(qn), self._timed("wordregion_fwd"):
             _lib.check(self.L.xmc_wordregion_forward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
-                                                     _p(lsum), _p(cnorm), _p(rel), _p(ws), n, _stream()))
+                                                     _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(ws), n, _stream()))
         self.launches += 1
-        return lsum, cnorm, rel
+        return lsum, cnorm, rel, chat
 
-    def wordregion_backward(self, path, qn, kn, rnorm, R, rho1, lsum, cnorm, rel, grel):
+    def wordregion_backward(self, path, qn, kn, rnorm, R, rho1, lsum, cnorm, rel, grel, chat=None):
         _cuda(qn, kn, grel)
         NQ, D = qn.shape
         Bi, Rpad, _ = kn.shape
@@ -229,7 +233,7 @@ class CudaOps:
         ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
         with torch.cuda.device_of(qn), self._timed("wordregion_bwd"):
             _lib.check(self.L.xmc_wordregion_backward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
-                                                      _p(lsum), _p(cnorm), _p(rel), _p(grel), _p(dqn), _p(dkn),
+                                                      _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(grel), _p(dqn), _p(dkn),
                                                       _p(drnorm), _p(ws), n, _stream()))
         self.launches += 1
         return dqn, dkn, drnorm
