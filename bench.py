@@ -166,7 +166,7 @@ def main():
         group = dist.group.WORLD
     dev = torch.device("cuda", local_rank)
     ops = default_ops()
-    precision = args.precision or os.environ.get("XMC_BENCH_PRECISION", "fp32")
+    precision = args.precision or os.environ.get("XMC_BENCH_PRECISION", "bf16")
     in_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
     B = args.batch
     W = max(args.warmup, 3)

@@ -47,13 +47,20 @@ struct WaitCtx {
   volatile int* abort_flag;   // shared memory
   int* err;                   // global (workspace)
 };
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// try_wait itself may suspend the thread for an implementation-defined time, so the bound is on
+// elapsed wall time (0.5 s), not on the number of polls.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const WaitCtx& w, int code) {
   if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_ns();
   for (uint32_t spin = 0;; ++spin) {
     if (*w.abort_flag) return;
     if (mbar_try_wait(bar, parity)) return;
-    if (spin > 2048) __nanosleep(64);
-    if (spin > (1u << 22)) {
+    if ((spin & 63) == 63 && global_ns() - t0 > 500000000ull) {
       *w.abort_flag = 1;
       if (w.err) atomicExch(w.err, code + 1000 * (int)blockIdx.x);
       return;

@@ -658,15 +658,17 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // ---- dQ of this CTA's word tile (summed over its images) ----
       mbar_wait(dq_full, 0, wc, 22);
       tc_fence_after();
-      if (grow < p.NQ) {
+      {
         float* dst = p.dqn + (size_t)grow * D + h * (D / 2);
 #pragma unroll 1
         for (int blk = 0; blk < D / 64; ++blk) {
           uint32_t dv[32];
-          tmem_ld32(lane_base + Cfg::kColDQ + h * (D / 2) + blk * 32, dv);
+          tmem_ld32(lane_base + Cfg::kColDQ + h * (D / 2) + blk * 32, dv);   // warp-collective: never predicate
           tmem_wait_ld();
+          if (grow < p.NQ) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + blk * 32 + j, __uint_as_float(dv[j]));
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + blk * 32 + j, __uint_as_float(dv[j]));
+          }
         }
       }
     }
