@@ -1,0 +1,99 @@
+"""world_size-2 gloo tests (CPU) of the multi-rank host logic: all-gather of the column operand,
+rank-offset identity labels, column-statistics exchange, reduce-scatter of gradients, global
+soft-positive labels.  The compute kernels are replaced by the CPU checker backend
+(tests/cpu_ops.py) — the product backend needs a GPU; its own parity is tested with -m gpu.
+
+Definition of correct: each rank's loss equals the single-process oracle on the
+concatenated global batch, and its gradients equal the oracle's gradient rows of that rank."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+WORLD = 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _data(seed, Bg, D, Dw, T_, R):
+    g = torch.Generator().manual_seed(seed)
+    d = dict(
+        img=torch.randn(Bg, D, generator=g, dtype=torch.float64),
+        sent=torch.randn(Bg, D, generator=g, dtype=torch.float64),
+        words=torch.randn(Bg, Dw, T_, generator=g, dtype=torch.float64),
+        regions=torch.randn(Bg, Dw, R, generator=g, dtype=torch.float64),
+    )
+    d["sent"][3] = d["sent"][Bg - 2] + 0.05 * torch.randn(D, generator=g, dtype=torch.float64)   # cross-rank positives
+    d["sent"][1] = d["sent"][2] + 0.05 * torch.randn(D, generator=g, dtype=torch.float64)
+    lens = torch.randint(1, T_ + 1, (Bg,), generator=g)
+    d["mask"] = torch.arange(T_).unsqueeze(0) >= lens.unsqueeze(1)
+    return d
+
+
+def _worker(rank, port, b_global, smooth, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        from cpu_ops import CpuOps
+        from xmc_gan_b200 import train_gan as T
+        torch.set_num_threads(1)
+        T.cfg.TRAIN.SMOOTH.GLOBAL = smooth
+        ops = CpuOps()
+        B, D, Dw, T_, R = 6, 16, 8, 5, 7
+        d = _data(0, B * WORLD, D, Dw, T_, R)
+        sl = slice(rank * B, (rank + 1) * B)
+        leaf = lambda x: x[sl].clone().requires_grad_()
+        img, sent, words, regions = leaf(d["img"]), leaf(d["sent"]), leaf(d["words"]), leaf(d["regions"])
+        group = dist.group.WORLD
+        labels = T.make_labels(B, d["sent"][sl].float(), b_global, group=group, _ops=ops)
+        loss = (T.sent_loss(img, sent, labels, b_global, group=group, _ops=ops)
+                + T.img_loss(sent.detach(), img, labels, b_global, tau=0.5, group=group, _ops=ops)
+                + T.word_loss(regions, words, d["mask"][sl], labels, b_global, rho1=4.0, rho2=5.0, rho3=6.0,
+                              group=group, _ops=ops))
+        loss.backward()
+        out[rank] = dict(loss=loss.detach(), labels=labels.detach().clone(),
+                         grads=[t.grad.clone() for t in (img, sent, words, regions)])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("b_global,smooth", [(False, 0.5), (True, 0.5), (True, 0.0)])
+def test_two_rank_global_negatives_match_single_process_oracle(b_global, smooth):
+    import oracle
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(_free_port(), b_global, smooth, out), nprocs=WORLD, join=True)
+
+    B, D, Dw, T_, R = 6, 16, 8, 5, 7
+    Bg = B * WORLD
+    d = _data(0, Bg, D, Dw, T_, R)
+    leaf = lambda x: x.clone().requires_grad_()
+    img, sent, words, regions = leaf(d["img"]), leaf(d["sent"]), leaf(d["words"]), leaf(d["regions"])
+    labels = oracle.make_labels(Bg, d["sent"].float(), b_global, smooth_global=smooth)
+    num_pos = oracle.num_pos_of(labels, b_global, smooth)
+    loss = (oracle.sent_loss(img, sent, labels, b_global, smooth)
+            + oracle.infonce_tail(oracle.cosine_scores(sent.detach(), img) / 0.5, labels, num_pos)
+            + oracle.word_loss(regions, words, d["mask"], labels, b_global, smooth, 4.0, 5.0, 6.0))
+    loss.backward()
+    if b_global:
+        assert (labels - torch.eye(Bg)).abs().sum() > 0, "test data must contain soft positives"
+    for rank in range(WORLD):
+        sl = slice(rank * B, (rank + 1) * B)
+        r = out[rank]
+        assert torch.equal(r["labels"], labels[sl]), f"rank {rank} label rows"
+        assert abs(float(r["loss"]) - float(loss)) < 1e-6 * abs(float(loss)), (float(r["loss"]), float(loss))
+        for got, ref in zip(r["grads"], (img.grad, sent.grad, words.grad, regions.grad)):
+            err = float((got - ref[sl]).norm() / ref[sl].norm())
+            assert err < 1e-6, (rank, err)

@@ -24,7 +24,7 @@ from .ops import default_ops
 __all__ = ["cfg", "make_labels", "cosine_scores", "sent_loss", "img_loss", "word_loss"]
 
 
-def make_labels(batch_size, sent_embs, b_global, p=0.6, *, group=None, device=None):
+def make_labels(batch_size, sent_embs, b_global, p=0.6, *, group=None, device=None, _ops=None):
     """Label matrix of the contrastive losses — ``xmc_gan/train_gan.py:72-83``.
 
     ``b_global=False``: identity ``[B, B]`` (``:74``).  The returned dense tensor is tagged so the
@@ -33,10 +33,10 @@ def make_labels(batch_size, sent_embs, b_global, p=0.6, *, group=None, device=No
     ``xmc_make_labels``; the row counts ``(labels > 0).sum(1)`` come back with it (``:99``).
     With ``group``, returns the rank's rows ``[B, B_global]`` of the global label matrix.
     """
-    ops = default_ops()
+    ops = _ops or default_ops()            # _ops: test hook (CPU checker backend under gloo), never set by users
     comm = _L.Comm(group)
     if device is None:
-        device = sent_embs.device if (sent_embs is not None and sent_embs.is_cuda) else torch.device("cuda")
+        device = sent_embs.device if sent_embs is not None and (sent_embs.is_cuda or _ops) else torch.device("cuda")
     if not b_global:
         B_all = batch_size * comm.world
         labels = torch.zeros(batch_size, B_all, device=device, dtype=torch.float32)
@@ -58,23 +58,23 @@ def make_labels(batch_size, sent_embs, b_global, p=0.6, *, group=None, device=No
     return labels
 
 
-def cosine_scores(emb0, emb1):
+def cosine_scores(emb0, emb1, *, _ops=None):
     """``normalize(emb0) @ normalize(emb1).T`` — ``xmc_gan/train_gan.py:85-91`` (no autograd)."""
-    return default_ops().cosine_scores(emb0.detach(), emb1.detach())
+    return (_ops or default_ops()).cosine_scores(emb0.detach(), emb1.detach())
 
 
-def sent_loss(imgs, txts, labels, b_global, *, tau=1.0, group=None):
+def sent_loss(imgs, txts, labels, b_global, *, tau=1.0, group=None, _ops=None):
     """Sentence–image InfoNCE, rows = images, cols = texts — ``xmc_gan/train_gan.py:93-115``."""
-    return _L.SimLossFn.apply(imgs, txts, labels, bool(b_global), 1.0 / tau, group, default_ops())
+    return _L.SimLossFn.apply(imgs, txts, labels, bool(b_global), 1.0 / tau, group, _ops or default_ops())
 
 
-def img_loss(real_imgs, fake_imgs, labels, b_global, *, tau=1.0, group=None):
+def img_loss(real_imgs, fake_imgs, labels, b_global, *, tau=1.0, group=None, _ops=None):
     """Real–fake image InfoNCE, rows = real, cols = fake — ``xmc_gan/train_gan.py:117-139``."""
-    return _L.SimLossFn.apply(real_imgs, fake_imgs, labels, bool(b_global), 1.0 / tau, group, default_ops())
+    return _L.SimLossFn.apply(real_imgs, fake_imgs, labels, bool(b_global), 1.0 / tau, group, _ops or default_ops())
 
 
 def word_loss(imgs, words, mask, labels, b_global, *, rho1=5.0, rho2=5.0, rho3=10.0,
-              normalize_values=False, precision=None, group=None):
+              normalize_values=False, precision=None, group=None, _ops=None):
     """Word–region attention contrastive loss (name pinned by ``train_gan.py:222, 269``).
 
     imgs: region features ``[B, D, H, W]`` (or ``[B, D, R]``); words ``[B, D, T]`` and
@@ -84,4 +84,4 @@ def word_loss(imgs, words, mask, labels, b_global, *, rho1=5.0, rho2=5.0, rho3=1
     fp32 accumulate, rel 2e-2); default follows the input dtype.
     """
     return _L.WordLossFn.apply(imgs, words, mask, labels, bool(b_global), float(rho1), float(rho2), float(rho3),
-                               bool(normalize_values), precision, group, default_ops())
+                               bool(normalize_values), precision, group, _ops or default_ops())
