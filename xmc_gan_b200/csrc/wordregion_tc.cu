@@ -28,16 +28,20 @@ using namespace tc;
 
 constexpr int TM = 128;            // word rows per tile (UMMA M)
 constexpr int CH = 64;             // region rows per chunk
-constexpr int kTcThreads = 256;
 constexpr float kLog2eTc = 1.4426950408889634f;
+
+constexpr int kFwdThreads = 384;     // 4 role warps + 2 softmax warpgroups
 
 template <int D>
 struct FwdCfg {
   static constexpr int kStageBytes = CH * D * 2;
   static constexpr int kBlockBytes = CH * 128;                    // one [64 rows x 64 bf16] swizzled box
   static constexpr int kStages = (D == 256) ? 6 : 8;
+  static constexpr int kOffRn = kStages * kStageBytes;            // [kStages][64] fp32 region norms of the chunk
+  static constexpr int kOffEx = kOffRn + kStages * CH * 4;        // [2 parity][2 wg][3][128] fp32 partials
+  static constexpr int kOffBar = kOffEx + 2 * 2 * 3 * TM * 4;
+  static constexpr int kSmemBytes = kOffBar + 256 + 1024 /*align*/;
   static constexpr int kColC = 0, kColQ = D, kColS0 = D + D / 2, kColS1 = kColS0 + CH;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kColS1 + CH <= 512, "TMEM budget");
 };
 
@@ -53,14 +57,29 @@ struct TcFwdParams {
   float* dbg;                  // optional: S chunk 0 and C of the first tile/image (tests)
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 template <int D>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
   using Cfg = FwdCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* kv = smem;                                               // kStages x kStageBytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  float* rn_s = reinterpret_cast<float*>(smem + Cfg::kOffRn);
+  float* ex_s = reinterpret_cast<float*>(smem + Cfg::kOffEx);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* kv_full = bars;                       // [kStages]
   uint64_t* kv_empty = bars + Cfg::kStages;       // [kStages]
   uint64_t* s_full = kv_empty + Cfg::kStages;     // [2]
@@ -79,12 +98,13 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
   const int nimg = img1 - img0;
   const int nch = (p.Rpad + CH - 1) / CH;
   const int G = nimg * nch;
+  const bool has_rn = p.rnorm != nullptr;
 
   if (threadIdx.x == 0) {
     *abort_flag = 0;
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(p_full + s, 128); }
-    mbar_init(c_full, 1); mbar_init(c_empty, 128); mbar_init(q_ready, 128);
+    for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(p_full + s, 256); }
+    mbar_init(c_full, 1); mbar_init(c_empty, 256); mbar_init(q_ready, 256);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -98,15 +118,18 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
     if (warp == 0) {
       // ===== TMA producer =====
       if (lane == 0) {
+        int st = 0, ph = 1, c = 0, img = img0;       // ph: parity to wait on kv_empty (first pass free)
         for (int g = 0; g < G; ++g) {
-          const int st = g % Cfg::kStages, it = g / Cfg::kStages;
-          const int img = img0 + g / nch, c = g % nch;
-          mbar_wait(kv_empty + st, (it & 1) ^ 1, wc, 1);
-          mbar_expect_tx(kv_full + st, Cfg::kStageBytes);
+          const int n = min(CH, p.Rpad - c * CH);
+          mbar_wait(kv_empty + st, ph, wc, 1);
+          mbar_expect_tx(kv_full + st, Cfg::kStageBytes + (has_rn ? n * 4 : 0));
           uint8_t* dst = kv + st * Cfg::kStageBytes;
 #pragma unroll
           for (int kb = 0; kb < D / 64; ++kb)
             tma_load_3d(dst + kb * Cfg::kBlockBytes, &tm_k, kb * 64, c * CH, img, kv_full + st);
+          if (has_rn) bulk_load_1d(rn_s + st * CH, p.rnorm + (size_t)img * p.Rpad + c * CH, n * 4, kv_full + st);
+          if (++st == Cfg::kStages) { st = 0; ph ^= 1; }
+          if (++c == nch) { c = 0; ++img; }
         }
       }
       __syncwarp();
@@ -115,12 +138,10 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
       if (lane == 0) {
         const uint32_t kv_addr = smem_u32(kv);
         constexpr uint32_t idesc2 = idesc_bf16(TM, D, false, true);
-        auto issue_g1 = [&](int g) {
-          const int st = g % Cfg::kStages, c = g % nch;
-          const int n = min(CH, p.Rpad - c * CH);
+        auto issue_g1 = [&](int st, int n, int sb) {
           const uint32_t idesc1 = idesc_bf16(TM, n, false, false);
           const uint32_t base = kv_addr + st * Cfg::kStageBytes;
-          const uint32_t d_tmem = tmem + ((g & 1) ? Cfg::kColS1 : Cfg::kColS0);
+          const uint32_t d_tmem = tmem + (sb ? Cfg::kColS1 : Cfg::kColS0);
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
             const uint64_t bd = smem_desc(base + (k >> 2) * Cfg::kBlockBytes + (k & 3) * 32, 16, 1024);
@@ -128,50 +149,55 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
           }
         };
         mbar_wait(q_ready, 0, wc, 2);
-        tc_fence_after();
         mbar_wait(kv_full + 0, 0, wc, 3);
         tc_fence_after();
-        issue_g1(0);
+        issue_g1(0, min(CH, p.Rpad), 0);
         mma_commit(s_full + 0);
+        // state of chunk g (st, c, ii) and of chunk g+1 (st1, ph1, c1)
+        int st = 0, c = 0, ii = 0;
+        int st1 = (Cfg::kStages > 1) ? 1 : 0, ph1 = 0, c1 = (nch > 1) ? 1 : 0;
         for (int g = 0; g < G; ++g) {
-          const int c = g % nch, ii = g / nch;
+          const int sb = g & 1;
           if (g + 1 < G) {
-            const int st1 = (g + 1) % Cfg::kStages, it1 = (g + 1) / Cfg::kStages;
-            mbar_wait(kv_full + st1, it1 & 1, wc, 4);
+            mbar_wait(kv_full + st1, ph1, wc, 4);
             tc_fence_after();
-            issue_g1(g + 1);
-            mma_commit(s_full + ((g + 1) & 1));
+            issue_g1(st1, min(CH, p.Rpad - c1 * CH), sb ^ 1);
+            mma_commit(s_full + (sb ^ 1));
           }
-          mbar_wait(p_full + (g & 1), (g >> 1) & 1, wc, 5);
+          mbar_wait(p_full + sb, (g >> 1) & 1, wc, 5);
+          if (c == 0 && ii > 0) mbar_wait(c_empty, (ii - 1) & 1, wc, 6);
           tc_fence_after();
-          if (c == 0 && ii > 0) {
-            mbar_wait(c_empty, (ii - 1) & 1, wc, 6);
-            tc_fence_after();
-          }
-          const int st = g % Cfg::kStages;
           const int n = min(CH, p.Rpad - c * CH);
           const uint32_t base = kv_addr + st * Cfg::kStageBytes;
-          const uint32_t a_tmem = tmem + ((g & 1) ? Cfg::kColS1 : Cfg::kColS0);
+          const uint32_t a_tmem = tmem + (sb ? Cfg::kColS1 : Cfg::kColS0);
           for (int ks = 0; ks < n / 16; ++ks) {
+            // P' of region cols [0,32) sits at S cols [0,16), of [32,64) at S cols [32,48)
             const uint64_t bd = smem_desc(base + ks * 2048, Cfg::kBlockBytes, 1024);
-            mma_ts(tmem + Cfg::kColC, a_tmem + ks * 8, bd, idesc2, (c > 0) || (ks > 0));
+            mma_ts(tmem + Cfg::kColC, a_tmem + (ks >> 1) * 32 + (ks & 1) * 8, bd, idesc2, (c > 0) || (ks > 0));
           }
           mma_commit(kv_empty + st);
           if (c == nch - 1) mma_commit(c_full);
+          // advance
+          st = st1; c = c1;
+          if (c == 0) ++ii;
+          if (++st1 == Cfg::kStages) { st1 = 0; ph1 ^= 1; }
+          if (++c1 == nch) c1 = 0;
         }
       }
       __syncwarp();
     } else if (warp >= 4) {
-      // ===== softmax / epilogue warpgroup: thread = TMEM lane = word row =====
+      // ===== softmax / epilogue warpgroups: thread = TMEM lane = word row; WG h owns chunk cols [32h, 32h+32)
+      const int h = (warp - 4) >> 2;
       const int q = warp & 3;
       const int row = q * 32 + lane;
       const int grow = m0 + row;
       const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
-      // Q row -> TMEM (A operand: column c holds elements 2c, 2c+1)
+      // Q row -> TMEM (A operand: 32-bit column c holds bf16 elements 2c, 2c+1); each WG writes half of D
       {
         const uint4* src = reinterpret_cast<const uint4*>(p.qn + (size_t)grow * D);
 #pragma unroll
-        for (int blk = 0; blk < D / 32; ++blk) {          // 32 bf16 = 16 columns per store
+        for (int b = 0; b < D / 64; ++b) {                 // 32 bf16 = 16 columns per store
+          const int blk = h * (D / 64) + b;
           uint32_t v[16];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -185,59 +211,80 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
         mbar_arrive(q_ready);
       }
       const float c1 = p.rho1 * kLog2eTc;
+      const int col0 = h * 32;
+      int st = 0, g = 0;
       for (int ii = 0; ii < nimg; ++ii) {
         const int img = img0 + ii;
-        const float* rn = p.rnorm ? p.rnorm + (size_t)img * p.Rpad : nullptr;
         float l = 0.f, a = 0.f;
-        for (int c = 0; c < nch; ++c) {
-          const int g = ii * nch + c;
+        for (int c = 0; c < nch; ++c, ++g) {
           const int n = min(CH, p.Rpad - c * CH);
           const uint32_t s_col = (g & 1) ? Cfg::kColS1 : Cfg::kColS0;
           mbar_wait(s_full + (g & 1), (g >> 1) & 1, wc, 7);
           tc_fence_after();
-          for (int h = 0; h * 32 < n; ++h) {
+          if (col0 < n) {
             uint32_t sv[32];
-            tmem_ld32(lane_base + s_col + h * 32, sv);
+            tmem_ld32(lane_base + s_col + col0, sv);
             tmem_wait_ld();
             if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && g == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) p.dbg[row * CH + h * 32 + j] = __uint_as_float(sv[j]);
+              for (int j = 0; j < 32; ++j) p.dbg[row * CH + col0 + j] = __uint_as_float(sv[j]);
             }
             uint32_t pk[16];
-            const int r0 = c * CH + h * 32;
+            const int r0 = c * CH + col0;
+            const float* wsm = rn_s + st * CH + col0;
+            if (r0 + 32 <= p.R) {                           // every column is a real region: no predicates
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (rn && r0 + j4 * 4 < p.Rpad) mr = __ldg(reinterpret_cast<const float4*>(rn + r0 + j4 * 4));
-              const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
-              float pw[4];
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + j4 * 4);
+                const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
+                float pw[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int j = j4 * 4 + u;
-                const bool valid = (r0 + j) < p.R;
-                const float s = valid ? __uint_as_float(sv[j]) : 0.f;
-                const float pv = valid ? exp2f(c1 * (s - 1.f)) : 0.f;
-                l += pv;
-                pw[u] = pv * mrv[u];
-                a = fmaf(pw[u], s, a);
+                for (int u = 0; u < 4; ++u) {
+                  const float s = __uint_as_float(sv[j4 * 4 + u]);
+                  const float pv = ex2_approx(fmaf(c1, s, -c1));
+                  l += pv;
+                  pw[u] = pv * mrv[u];
+                  a = fmaf(pw[u], s, a);
+                }
+                pk[j4 * 2 + 0] = pack_bf16(pw[0], pw[1]);
+                pk[j4 * 2 + 1] = pack_bf16(pw[2], pw[3]);
               }
-              pk[j4 * 2 + 0] = pack_bf16(pw[0], pw[1]);
-              pk[j4 * 2 + 1] = pack_bf16(pw[2], pw[3]);
+            } else {                                        // ragged tail of the image
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float pw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int j = j4 * 4 + u;
+                  const bool valid = (r0 + j) < p.R;
+                  const float s = valid ? __uint_as_float(sv[j]) : 0.f;
+                  const float pv = valid ? ex2_approx(fmaf(c1, s, -c1)) : 0.f;
+                  const float mr = (has_rn && valid) ? wsm[j] : 1.f;
+                  l += pv;
+                  pw[u] = pv * mr;
+                  a = fmaf(pw[u], s, a);
+                }
+                pk[j4 * 2 + 0] = pack_bf16(pw[0], pw[1]);
+                pk[j4 * 2 + 1] = pack_bf16(pw[2], pw[3]);
+              }
             }
-            tmem_st16(lane_base + s_col + h * 16, pk);
+            tmem_st16(lane_base + s_col + col0, pk);        // WG0 -> S cols [0,16), WG1 -> [32,48)
+            tmem_wait_st();
           }
-          tmem_wait_st();
           tc_fence_before();
           mbar_arrive(p_full + (g & 1));
+          if (++st == Cfg::kStages) st = 0;
         }
-        // ---- epilogue of this image: ||C|| ----
+        // ---- epilogue of this image: ||C||, statistics, unit contexts ----
         mbar_wait(c_full, ii & 1, wc, 8);
         tc_fence_after();
         float c2 = 0.f;
+        constexpr int kHalf = D / 2;
 #pragma unroll 1
-        for (int blk = 0; blk < D / 32; ++blk) {
+        for (int blk = 0; blk < kHalf / 32; ++blk) {
           uint32_t cv[32];
-          tmem_ld32(lane_base + Cfg::kColC + blk * 32, cv);
+          tmem_ld32(lane_base + Cfg::kColC + h * kHalf + blk * 32, cv);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -246,39 +293,49 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
           }
           if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ii == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) p.dbg[TM * CH + row * D + blk * 32 + j] = __uint_as_float(cv[j]);
+            for (int j = 0; j < 32; ++j) p.dbg[TM * CH + row * D + h * kHalf + blk * 32 + j] = __uint_as_float(cv[j]);
           }
         }
+        // combine the two warpgroups' partial l, a, ||C||^2 (double-buffered by image parity)
+        float* ex = ex_s + (ii & 1) * (2 * 3 * TM);
+        ex[(h * 3 + 0) * TM + row] = l;
+        ex[(h * 3 + 1) * TM + row] = a;
+        ex[(h * 3 + 2) * TM + row] = c2;
+        named_bar_sync(1, 256);
+        const int o = 1 - h;
+        l += ex[(o * 3 + 0) * TM + row];
+        a += ex[(o * 3 + 1) * TM + row];
+        c2 += ex[(o * 3 + 2) * TM + row];
         if (p.chat) {
           // second TMEM pass: unit context rows -> bf16 -> global (saved for the backward kernel)
           const float inv_c = 1.f / fmaxf(sqrtf(c2), kEps * l);
-          uint4* dst = reinterpret_cast<uint4*>(p.chat + ((size_t)img * p.NQ + grow) * D);
+          uint4* dst = reinterpret_cast<uint4*>(p.chat + ((size_t)img * p.NQ + grow) * D + h * kHalf);
 #pragma unroll 1
-          for (int blk = 0; blk < D / 32; ++blk) {
+          for (int blk = 0; blk < kHalf / 32; ++blk) {
             uint32_t cv[32];
-            tmem_ld32(lane_base + Cfg::kColC + blk * 32, cv);
+            tmem_ld32(lane_base + Cfg::kColC + h * kHalf + blk * 32, cv);
             tmem_wait_ld();
             if (grow < p.NQ) {
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                uint4 o;
-                o.x = pack_bf16(__uint_as_float(cv[8 * u + 0]) * inv_c, __uint_as_float(cv[8 * u + 1]) * inv_c);
-                o.y = pack_bf16(__uint_as_float(cv[8 * u + 2]) * inv_c, __uint_as_float(cv[8 * u + 3]) * inv_c);
-                o.z = pack_bf16(__uint_as_float(cv[8 * u + 4]) * inv_c, __uint_as_float(cv[8 * u + 5]) * inv_c);
-                o.w = pack_bf16(__uint_as_float(cv[8 * u + 6]) * inv_c, __uint_as_float(cv[8 * u + 7]) * inv_c);
-                dst[blk * 4 + u] = o;
+                uint4 ov;
+                ov.x = pack_bf16(__uint_as_float(cv[8 * u + 0]) * inv_c, __uint_as_float(cv[8 * u + 1]) * inv_c);
+                ov.y = pack_bf16(__uint_as_float(cv[8 * u + 2]) * inv_c, __uint_as_float(cv[8 * u + 3]) * inv_c);
+                ov.z = pack_bf16(__uint_as_float(cv[8 * u + 4]) * inv_c, __uint_as_float(cv[8 * u + 5]) * inv_c);
+                ov.w = pack_bf16(__uint_as_float(cv[8 * u + 6]) * inv_c, __uint_as_float(cv[8 * u + 7]) * inv_c);
+                dst[blk * 4 + u] = ov;
               }
             }
           }
         }
         tc_fence_before();
         mbar_arrive(c_empty);
-        if (grow < p.NQ) {
+        if (h == 0 && grow < p.NQ) {
           const float cn = sqrtf(c2) / l;
-          const size_t o = (size_t)img * p.NQ + grow;
-          p.lsum[o] = l;
-          p.cnorm[o] = cn;
-          p.rel[o] = (a / l) / fmaxf(cn, kEps);
+          const size_t o2 = (size_t)img * p.NQ + grow;
+          p.lsum[o2] = l;
+          p.cnorm[o2] = cn;
+          p.rel[o2] = (a / l) / fmaxf(cn, kEps);
         }
       }
     }
@@ -349,7 +406,7 @@ static int launch_fwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
   p.imgs_per_cta = (w.Bi + splits - 1) / splits;
   splits = (w.Bi + p.imgs_per_cta - 1) / p.imgs_per_cta;
   XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  wr_fwd_tc_kernel<D><<<dim3(tiles, splits), kTcThreads, Cfg::kSmemBytes, st>>>(tm, p);
+  wr_fwd_tc_kernel<D><<<dim3(tiles, splits), kFwdThreads, Cfg::kSmemBytes, st>>>(tm, p);
   return cuda_fail(cudaGetLastError(), "wr_fwd_tc_kernel launch");
 }
 
@@ -375,7 +432,8 @@ int wordregion_tc_forward(const WrParams& p, int D, void* ws, size_t ws_bytes, c
 //   X = dS + gamma*alpha', Y = -gamma*rel*alpha'      (2 warpgroups, bf16, 128B-swizzled smem tiles)
 //   dQ   += X Khat_chunk                              (A = X K-major, B = Khat MN-major)   -> TMEM, persistent
 //   dK^T  = Q^T X + Chat^T Y   [D x 64]               (A = Q / Chat as MN-major, B = X / Y MN-major) -> TMEM
-//   dK^T -> red.global.add into dkn (coalesced along d);  column sums of alpha*d alpha' -> drnorm
+//   dK^T -> fp32 rows staged in smem (the dead X|Y bytes) -> cp.reduce.async.bulk add into dkn;
+//           column sums of alpha*d alpha' -> drnorm
 // The same smem bytes serve as K-major and as MN-major operands; nothing of size Bi x Bc x T x R
 // ever reaches global memory.
 // Warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 elementwise WG0 (chunk cols 0-31, dK^T rows d<128),
@@ -391,12 +449,14 @@ struct BwdCfg {
   static constexpr int kKvBlock = CH * 128;
   static constexpr int kXBytes = TM * 128;         // X / Y tile: [128 t x 64 r] bf16
   static constexpr int kOffQ = 0, kOffC = kQBytes, kOffKv = 2 * kQBytes, kOffX = kOffKv + 2 * kKvStage,
-                       kOffY = kOffX + kXBytes, kOffBar = kOffY + kXBytes;
-  static constexpr int kSmemBytes = kOffBar + 256 + 1024;
+                       kOffY = kOffX + kXBytes, kOffBar = kOffY + kXBytes, kOffRn = kOffBar + 256;
+  static constexpr int kSmemBytes = kOffRn + 2 * CH * 4 + 1024;
   static constexpr int kTilesD = D / 128;          // M-tiles of dK^T
   static constexpr int kColDQ = 0, kColS = D, kColW = D + CH, kColDK = D + 2 * CH;
+  static constexpr int kDrainRows = (2 * kXBytes) / (D * 4);   // region rows of fp32 dK staged per bulk reduce
   static_assert(kColDK + kTilesD * CH <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
+  static_assert(kDrainRows >= 32, "staging buffer holds at least one TMEM load of rows");
 };
 
 struct TcBwdParams {
@@ -436,6 +496,8 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint8_t* kv = smem + Cfg::kOffKv;
   uint8_t* Xs = smem + Cfg::kOffX;
   uint8_t* Ys = smem + Cfg::kOffY;
+  float* stage = reinterpret_cast<float*>(Xs);      // X|Y bytes double as the fp32 dK staging buffer
+  float* rn_s = reinterpret_cast<float*>(smem + Cfg::kOffRn);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* q_full = bars + 0;
   uint64_t* ch_full = bars + 1;
@@ -457,6 +519,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int nimg = min(p.Bi, img0 + p.imgs_per_cta) - img0;
   const int nch = (p.Rpad + CH - 1) / CH;
   const int G = nimg * nch;
+  const bool has_rn = p.rnorm != nullptr;
 
   if (threadIdx.x == 0) {
     *abort_flag = 0;
@@ -480,13 +543,16 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_expect_tx(q_full, Cfg::kQBytes);
 #pragma unroll
         for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(Qs + kb * Cfg::kQBlock, &tm_q, kb * 64, m0, q_full);
+        int c = 0, ii = 0;
         for (int g = 0; g < G; ++g) {
-          const int st = g & 1, ii = g / nch, c = g % nch;
+          const int st = g & 1;
+          const int n = min(CH, p.Rpad - c * CH);
           mbar_wait(kv_empty + st, ((g >> 1) & 1) ^ 1, wc, 11);
-          mbar_expect_tx(kv_full + st, Cfg::kKvStage);
+          mbar_expect_tx(kv_full + st, Cfg::kKvStage + (has_rn ? n * 4 : 0));
 #pragma unroll
           for (int kb = 0; kb < D / 64; ++kb)
             tma_load_3d(kv + st * Cfg::kKvStage + kb * Cfg::kKvBlock, &tm_k, kb * 64, c * CH, img0 + ii, kv_full + st);
+          if (has_rn) bulk_load_1d(rn_s + st * CH, p.rnorm + (size_t)(img0 + ii) * p.Rpad + c * CH, n * 4, kv_full + st);
           if (c == 0) {
             mbar_wait(ch_empty, (ii & 1) ^ 1, wc, 12);
             mbar_expect_tx(ch_full, Cfg::kQBytes);
@@ -494,6 +560,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             for (int kb = 0; kb < D / 64; ++kb)
               tma_load_3d(Cs + kb * Cfg::kQBlock, &tm_c, kb * 64, m0, img0 + ii, ch_full);
           }
+          if (++c == nch) { c = 0; ++ii; }
         }
       }
       __syncwarp();
@@ -503,10 +570,9 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const uint32_t q_addr = smem_u32(Qs), c_addr = smem_u32(Cs), kv_addr = smem_u32(kv);
         const uint32_t x_addr = smem_u32(Xs), y_addr = smem_u32(Ys);
         constexpr uint32_t idesc_dq = idesc_bf16(TM, D, false, true);
-        auto chunk_n = [&](int g) { return min(CH, p.Rpad - (g % nch) * CH); };
-        auto issue_scores = [&](int g, uint32_t a_addr, uint32_t d_col) {   // [128 x n] = A[128 x D] . Khat_chunk^T
-          const uint32_t idesc = idesc_bf16(TM, chunk_n(g), false, false);
-          const uint32_t b_addr = kv_addr + (g & 1) * Cfg::kKvStage;
+        auto issue_scores = [&](int st, int n, uint32_t a_addr, uint32_t d_col) {   // [128 x n] = A[128 x D] . Khat_chunk^T
+          const uint32_t idesc = idesc_bf16(TM, n, false, false);
+          const uint32_t b_addr = kv_addr + st * Cfg::kKvStage;
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
             const uint64_t ad = smem_desc(a_addr + (k >> 2) * Cfg::kQBlock + (k & 3) * 32, 16, 1024);
@@ -517,13 +583,14 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_wait(q_full, 0, wc, 13);
         mbar_wait(kv_full + 0, 0, wc, 14);
         tc_fence_after();
-        issue_scores(0, q_addr, Cfg::kColS);
+        issue_scores(0, min(CH, p.Rpad), q_addr, Cfg::kColS);
         mbar_wait(ch_full, 0, wc, 15);
         tc_fence_after();
-        issue_scores(0, c_addr, Cfg::kColW);
+        issue_scores(0, min(CH, p.Rpad), c_addr, Cfg::kColW);
         mma_commit(sw_full);
+        int c = 0, ii = 0;
         for (int g = 0; g < G; ++g) {
-          const int c = g % nch, st = g & 1, n = chunk_n(g);
+          const int st = g & 1, n = min(CH, p.Rpad - c * CH);
           mbar_wait(xy_full, g & 1, wc, 16);
           if (g > 0) mbar_wait(dk_empty, (g - 1) & 1, wc, 17);
           tc_fence_after();
@@ -544,8 +611,8 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               mma_ss(tmem + Cfg::kColDK + h * CH, ad, bd, idesc_dk, true);
             }
           }
-          mma_commit(dk_full);
-          if (c == nch - 1) mma_commit(ch_empty);
+          const bool last_chunk = (c == nch - 1);
+          if (last_chunk) mma_commit(ch_empty);
           // dQ += X Khat_chunk
           for (int ks = 0; ks < n / 16; ++ks) {
             const uint64_t ad = smem_desc(x_addr + ks * 32, 16, 1024);
@@ -553,15 +620,18 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             mma_ss(tmem + Cfg::kColDQ, ad, bd, idesc_dq, (g > 0) || (ks > 0));
           }
           mma_commit(kv_empty + st);
+          mma_commit(dk_full);          // X / Y are dead once this fires: the drain may reuse their bytes
+          if (++c == nch) { c = 0; ++ii; }
           if (g + 1 < G) {
-            mbar_wait(kv_full + ((g + 1) & 1), ((g + 1) >> 1) & 1, wc, 18);
+            const int n1 = min(CH, p.Rpad - c * CH);
+            mbar_wait(kv_full + (st ^ 1), ((g + 1) >> 1) & 1, wc, 18);
             tc_fence_after();
-            issue_scores(g + 1, q_addr, Cfg::kColS);
-            if ((g + 1) % nch == 0) {
-              mbar_wait(ch_full, ((g + 1) / nch) & 1, wc, 19);
+            issue_scores(st ^ 1, n1, q_addr, Cfg::kColS);
+            if (c == 0) {
+              mbar_wait(ch_full, ii & 1, wc, 19);
               tc_fence_after();
             }
-            issue_scores(g + 1, c_addr, Cfg::kColW);
+            issue_scores(st ^ 1, n1, c_addr, Cfg::kColW);
             mma_commit(sw_full);
           }
         }
@@ -577,9 +647,9 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
       const float c1 = p.rho1 * kLog2eTc;
       const int col0 = h * 32;
+      int g = 0;
       for (int ii = 0; ii < nimg; ++ii) {
         const int img = img0 + ii;
-        const float* rn = p.rnorm ? p.rnorm + (size_t)img * p.Rpad : nullptr;
         float inv_l = 1.f, gam = 0.f, relv = 0.f;
         if (grow < p.NQ) {
           const size_t o = (size_t)img * p.NQ + grow;
@@ -587,8 +657,8 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           gam = __ldg(p.grel + o) / fmaxf(__ldg(p.cnorm + o), kEps);
           relv = __ldg(p.rel + o);
         }
-        for (int c = 0; c < nch; ++c) {
-          const int g = ii * nch + c;
+        const float grl = gam * relv;
+        for (int c = 0; c < nch; ++c, ++g) {
           const int n = min(CH, p.Rpad - c * CH);
           mbar_wait(sw_full, g & 1, wc, 20);
           tc_fence_after();
@@ -598,25 +668,27 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             tmem_ld32(lane_base + Cfg::kColW + col0, wv);
             tmem_wait_ld();
             const int r0 = c * CH + col0;
+            const float* wsm = rn_s + (g & 1) * CH + col0;
+            const bool full = (r0 + 32 <= p.R);
             float z[32];
             uint32_t xp[16], yp[16];
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (rn && r0 + j4 * 4 < p.Rpad) mr = __ldg(reinterpret_cast<const float4*>(rn + r0 + j4 * 4));
+              if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + j4 * 4);
               const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
               float xv[4], yv[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const int j = j4 * 4 + u;
-                const bool valid = (r0 + j) < p.R;
+                const bool valid = full || (r0 + j) < p.R;
                 const float s = valid ? __uint_as_float(sv[j]) : 0.f;
                 const float w = valid ? __uint_as_float(wv[j]) : 0.f;
-                const float al = valid ? exp2f(c1 * (s - 1.f)) * inv_l : 0.f;    // alpha
-                const float alp = al * mrv[u];                                   // alpha' = alpha * ||v_r||
-                const float dap = gam * (s - relv * w);                          // d loss / d alpha'
-                xv[u] = fmaf(p.rho1 * alp, dap, gam * alp);                      // dS + gamma*alpha'
-                yv[u] = -gam * relv * alp;
+                const float al = valid ? ex2_approx(fmaf(c1, s, -c1)) * inv_l : 0.f;   // alpha
+                const float alp = al * mrv[u];                                         // alpha' = alpha * ||v_r||
+                const float dap = fmaf(-grl, w, gam * s);                              // d loss / d alpha'
+                xv[u] = fmaf(p.rho1 * alp, dap, gam * alp);                            // dS + gamma*alpha'
+                yv[u] = -grl * alp;
                 z[j] = al * dap;
               }
               xp[j4 * 2 + 0] = pack_bf16(xv[0], xv[1]); xp[j4 * 2 + 1] = pack_bf16(xv[2], xv[3]);
@@ -629,7 +701,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               *reinterpret_cast<uint4*>(Xs + row * 128 + phys * 16) = make_uint4(xp[4 * u], xp[4 * u + 1], xp[4 * u + 2], xp[4 * u + 3]);
               *reinterpret_cast<uint4*>(Ys + row * 128 + phys * 16) = make_uint4(yp[4 * u], yp[4 * u + 1], yp[4 * u + 2], yp[4 * u + 3]);
             }
-            if (rn) {
+            if (has_rn) {
               const float colsum = warp_transpose_sum32(z, lane);      // column (r0 + lane) over this warp's 32 rows
               if (r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
             }
@@ -637,24 +709,33 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(xy_full);
-          // drain dK^T tile h of this chunk
+          // ---- drain dK^T of this chunk: TMEM -> fp32 rows in smem (X|Y bytes) -> bulk reduce-add ----
           mbar_wait(dk_full, g & 1, wc, 21);
           tc_fence_after();
-          if (h < Cfg::kTilesD) {
-            float* dst = p.dkn + ((size_t)img * p.Rpad + c * CH) * D + h * 128 + row;
-            for (int jb = 0; jb < n; jb += 32) {
+          for (int jb = 0; jb < n; jb += 32) {
+            const int rows = min(32, n - jb);
+            if (h < Cfg::kTilesD) {
               uint32_t dv[32];
               tmem_ld32(lane_base + Cfg::kColDK + h * CH + jb, dv);
               tmem_wait_ld();
+              float* dst = stage + h * 128 + row;                // column d = 128h + row of the [rows x D] block
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (jb + j < n && c * CH + jb + j < p.R) atomicAdd(dst + (size_t)(jb + j) * D, __uint_as_float(dv[j]));
+              for (int j = 0; j < 32; ++j) dst[j * D] = __uint_as_float(dv[j]);
             }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 256);
+            if (warp == 4 && lane == 0) {
+              bulk_reduce_add_f32(p.dkn + ((size_t)img * p.Rpad + c * CH + jb) * D, stage, rows * D * 4);
+              bulk_commit();
+              bulk_wait_read<0>();                               // smem may be overwritten after this
+            }
+            named_bar_sync(1, 256);
           }
           tc_fence_before();
           mbar_arrive(dk_empty);
         }
       }
+      if (warp == 4 && lane == 0) bulk_wait<0>();                // all reductions performed before exit
       // ---- dQ of this CTA's word tile (summed over its images) ----
       mbar_wait(dq_full, 0, wc, 22);
       tc_fence_after();
