@@ -18,6 +18,8 @@
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
 // allocator, warps 4-7 = softmax/epilogue warpgroup (thread = TMEM lane = word row).
 // TMEM map (512 columns): C [0,D) | Q [D, D+D/2) | S0 | S1 (64 columns each, P' aliases S).
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "wordregion.h"
@@ -112,7 +114,11 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  // The allocation is the whole tensor memory (512 columns, one CTA per SM), so its base is lane 0 /
+  // column 0; using the literal keeps every TMEM address an immediate for the MMA issue path.
+  constexpr uint32_t tmem = 0;
+  if (threadIdx.x == 0 && *tmem_slot != 0) { *abort_flag = 1; if (p.err) atomicExch(p.err, 999); }
+  __syncthreads();
 
   if (G > 0) {
     if (warp == 0) {
@@ -134,19 +140,20 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
       }
       __syncwarp();
     } else if (warp == 1) {
-      // ===== MMA issuer =====
-      if (lane == 0) {
+      // ===== MMA issuer: whole warp converged, one elected lane issues =====
+      {
         const uint32_t kv_addr = smem_u32(kv);
         constexpr uint32_t idesc2 = idesc_bf16(TM, D, false, true);
+        // descriptor of stage 0; stages / k-steps are reached by adding (byte offset >> 4) to the low word
+        const Desc kdesc0 = make_desc(kv_addr, 16, 1024);                    // K-major   (GEMM1 B)
+        const Desc vdesc0 = make_desc(kv_addr, Cfg::kBlockBytes, 1024);      // MN-major  (GEMM2 B)
         auto issue_g1 = [&](int st, int n, int sb) {
           const uint32_t idesc1 = idesc_bf16(TM, n, false, false);
-          const uint32_t base = kv_addr + st * Cfg::kStageBytes;
+          const Desc base = kdesc0 + ((uint32_t)(st * Cfg::kStageBytes) >> 4);
           const uint32_t d_tmem = tmem + (sb ? Cfg::kColS1 : Cfg::kColS0);
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint64_t bd = smem_desc(base + (k >> 2) * Cfg::kBlockBytes + (k & 3) * 32, 16, 1024);
-            mma_ts(d_tmem, tmem + Cfg::kColQ + k * 8, bd, idesc1, k > 0);
-          }
+          for (int k = 0; k < D / 16; ++k)
+            mma_ts(d_tmem, tmem + Cfg::kColQ + k * 8, base + (((k >> 2) * Cfg::kBlockBytes + (k & 3) * 32) >> 4), idesc1, k > 0);
         };
         mbar_wait(q_ready, 0, wc, 2);
         mbar_wait(kv_full + 0, 0, wc, 3);
@@ -168,13 +175,13 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
           if (c == 0 && ii > 0) mbar_wait(c_empty, (ii - 1) & 1, wc, 6);
           tc_fence_after();
           const int n = min(CH, p.Rpad - c * CH);
-          const uint32_t base = kv_addr + st * Cfg::kStageBytes;
+          const Desc vbase = vdesc0 + ((uint32_t)(st * Cfg::kStageBytes) >> 4);
           const uint32_t a_tmem = tmem + (sb ? Cfg::kColS1 : Cfg::kColS0);
-          for (int ks = 0; ks < n / 16; ++ks) {
-            // P' of region cols [0,32) sits at S cols [0,16), of [32,64) at S cols [32,48)
-            const uint64_t bd = smem_desc(base + ks * 2048, Cfg::kBlockBytes, 1024);
-            mma_ts(tmem + Cfg::kColC, a_tmem + (ks >> 1) * 32 + (ks & 1) * 8, bd, idesc2, (c > 0) || (ks > 0));
-          }
+          // P' of region cols [0,32) sits at S cols [0,16), of [32,64) at S cols [32,48)
+#pragma unroll
+          for (int ks = 0; ks < CH / 16; ++ks)
+            if (ks * 16 < n)
+              mma_ts(tmem + Cfg::kColC, a_tmem + (ks >> 1) * 32 + (ks & 1) * 8, vbase + ((ks * 2048) >> 4), idesc2, (c > 0) || (ks > 0));
           mma_commit(kv_empty + st);
           if (c == nch - 1) mma_commit(c_full);
           // advance
@@ -342,7 +349,7 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 2) tmem_dealloc(*tmem_slot, 512);
 }
 
 static int g_debug_dump = 0;   // tests only: dump S chunk 0 and C of tile 0 / image 0 into the workspace
@@ -397,7 +404,7 @@ static int launch_fwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
   p.lsum = w.lsum; p.cnorm = w.cnorm; p.rel = w.rel;
   p.chat = static_cast<__nv_bfloat16*>(w.chat);
   p.err = static_cast<int*>(ws);
-  p.dbg = (g_debug_dump && ws_bytes >= 64 + sizeof(float) * (size_t)(TM * CH + TM * D))
+  p.dbg = ((g_debug_dump & 1) && ws_bytes >= 64 + sizeof(float) * (size_t)(TM * CH + TM * D))
               ? reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
   const int tiles = (w.NQ + TM - 1) / TM;
   int splits = num_sms() / tiles;
@@ -467,6 +474,8 @@ struct TcBwdParams {
   float* dqn; float* dkn; float* drnorm;
   int imgs_per_cta;
   int* err;
+  int dbg_flags;               // perf experiments only (xmc_internal_set_debug_dump): 2 = skip the dK reduce
+  long long* trace;            // perf experiments only (flag 4): clock64 timeline of CTA (0,0), [4 roles][64 chunks][4]
 };
 
 // lane L returns sum over the warp of v[L] (31 shuffles instead of 160)
@@ -483,6 +492,12 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
   }
   return v[0];
 }
+
+#define XMC_TRACE(role, g, k)                                                             \
+  do {                                                                                   \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (g) < 64)                      \
+      p.trace[((role) * 64 + (g)) * 4 + (k)] = clock64();                               \
+  } while (0)
 
 template <int D>
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -534,7 +549,11 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  // The allocation is the whole tensor memory (512 columns, one CTA per SM), so its base is lane 0 /
+  // column 0; using the literal keeps every TMEM address an immediate for the MMA issue path.
+  constexpr uint32_t tmem = 0;
+  if (threadIdx.x == 0 && *tmem_slot != 0) { *abort_flag = 1; if (p.err) atomicExch(p.err, 999); }
+  __syncthreads();
 
   if (G > 0) {
     if (warp == 0) {
@@ -565,28 +584,30 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
       __syncwarp();
     } else if (warp == 1) {
-      // ===== MMA issuer =====
-      if (lane == 0) {
-        const uint32_t q_addr = smem_u32(Qs), c_addr = smem_u32(Cs), kv_addr = smem_u32(kv);
-        const uint32_t x_addr = smem_u32(Xs), y_addr = smem_u32(Ys);
+      // ===== MMA issuer: whole warp converged, one elected lane issues =====
+      {
         constexpr uint32_t idesc_dq = idesc_bf16(TM, D, false, true);
-        auto issue_scores = [&](int st, int n, uint32_t a_addr, uint32_t d_col) {   // [128 x n] = A[128 x D] . Khat_chunk^T
+        // base descriptors; k-steps / blocks / stages are reached by adding (byte offset >> 4)
+        const Desc q_k = make_desc(smem_u32(Qs), 16, 1024), q_mn = make_desc(smem_u32(Qs), Cfg::kQBlock, 1024);
+        const Desc c_k = make_desc(smem_u32(Cs), 16, 1024), c_mn = make_desc(smem_u32(Cs), Cfg::kQBlock, 1024);
+        const Desc kv_k = make_desc(smem_u32(kv), 16, 1024), kv_mn = make_desc(smem_u32(kv), Cfg::kKvBlock, 1024);
+        const Desc x_k = make_desc(smem_u32(Xs), 16, 1024), x_mn = make_desc(smem_u32(Xs), Cfg::kXBytes, 1024);
+        const Desc y_mn = make_desc(smem_u32(Ys), Cfg::kXBytes, 1024);
+        auto issue_scores = [&](int st, int n, Desc a_k, uint32_t d_col) {   // [128 x n] = A[128 x D] . Khat_chunk^T
           const uint32_t idesc = idesc_bf16(TM, n, false, false);
-          const uint32_t b_addr = kv_addr + st * Cfg::kKvStage;
+          const Desc b_k = kv_k + ((uint32_t)(st * Cfg::kKvStage) >> 4);
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint64_t ad = smem_desc(a_addr + (k >> 2) * Cfg::kQBlock + (k & 3) * 32, 16, 1024);
-            const uint64_t bd = smem_desc(b_addr + (k >> 2) * Cfg::kKvBlock + (k & 3) * 32, 16, 1024);
-            mma_ss(tmem + d_col, ad, bd, idesc, k > 0);
-          }
+          for (int k = 0; k < D / 16; ++k)
+            mma_ss(tmem + d_col, a_k + (((k >> 2) * Cfg::kQBlock + (k & 3) * 32) >> 4),
+                   b_k + (((k >> 2) * Cfg::kKvBlock + (k & 3) * 32) >> 4), idesc, k > 0);
         };
         mbar_wait(q_full, 0, wc, 13);
         mbar_wait(kv_full + 0, 0, wc, 14);
         tc_fence_after();
-        issue_scores(0, min(CH, p.Rpad), q_addr, Cfg::kColS);
+        issue_scores(0, min(CH, p.Rpad), q_k, Cfg::kColS);
         mbar_wait(ch_full, 0, wc, 15);
         tc_fence_after();
-        issue_scores(0, min(CH, p.Rpad), c_addr, Cfg::kColW);
+        issue_scores(0, min(CH, p.Rpad), c_k, Cfg::kColW);
         mma_commit(sw_full);
         int c = 0, ii = 0;
         for (int g = 0; g < G; ++g) {
@@ -594,45 +615,44 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           mbar_wait(xy_full, g & 1, wc, 16);
           if (g > 0) mbar_wait(dk_empty, (g - 1) & 1, wc, 17);
           tc_fence_after();
+          XMC_TRACE(0, g, 0);
           // dK^T tiles: [128 d x n] = Q^T X + Chat^T Y   (contraction over the 128 word rows)
           const uint32_t idesc_dk = idesc_bf16(TM, n, true, true);
 #pragma unroll
           for (int h = 0; h < Cfg::kTilesD; ++h) {
 #pragma unroll
-            for (int kt = 0; kt < TM / 16; ++kt) {
-              const uint64_t ad = smem_desc(q_addr + 2 * h * Cfg::kQBlock + kt * 2048, Cfg::kQBlock, 1024);
-              const uint64_t bd = smem_desc(x_addr + kt * 2048, Cfg::kXBytes, 1024);
-              mma_ss(tmem + Cfg::kColDK + h * CH, ad, bd, idesc_dk, kt > 0);
-            }
+            for (int kt = 0; kt < TM / 16; ++kt)
+              mma_ss(tmem + Cfg::kColDK + h * CH, q_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), x_mn + ((kt * 2048) >> 4), idesc_dk, kt > 0);
 #pragma unroll
-            for (int kt = 0; kt < TM / 16; ++kt) {
-              const uint64_t ad = smem_desc(c_addr + 2 * h * Cfg::kQBlock + kt * 2048, Cfg::kQBlock, 1024);
-              const uint64_t bd = smem_desc(y_addr + kt * 2048, Cfg::kXBytes, 1024);
-              mma_ss(tmem + Cfg::kColDK + h * CH, ad, bd, idesc_dk, true);
-            }
+            for (int kt = 0; kt < TM / 16; ++kt)
+              mma_ss(tmem + Cfg::kColDK + h * CH, c_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), y_mn + ((kt * 2048) >> 4), idesc_dk, true);
           }
           const bool last_chunk = (c == nch - 1);
           if (last_chunk) mma_commit(ch_empty);
           // dQ += X Khat_chunk
-          for (int ks = 0; ks < n / 16; ++ks) {
-            const uint64_t ad = smem_desc(x_addr + ks * 32, 16, 1024);
-            const uint64_t bd = smem_desc(kv_addr + st * Cfg::kKvStage + ks * 2048, Cfg::kKvBlock, 1024);
-            mma_ss(tmem + Cfg::kColDQ, ad, bd, idesc_dq, (g > 0) || (ks > 0));
+          {
+            const Desc b_mn = kv_mn + ((uint32_t)(st * Cfg::kKvStage) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < CH / 16; ++ks)
+              if (ks * 16 < n) mma_ss(tmem + Cfg::kColDQ, x_k + ((ks * 32) >> 4), b_mn + ((ks * 2048) >> 4), idesc_dq, (g > 0) || (ks > 0));
           }
           mma_commit(kv_empty + st);
           mma_commit(dk_full);          // X / Y are dead once this fires: the drain may reuse their bytes
+          XMC_TRACE(0, g, 1);
           if (++c == nch) { c = 0; ++ii; }
           if (g + 1 < G) {
             const int n1 = min(CH, p.Rpad - c * CH);
             mbar_wait(kv_full + (st ^ 1), ((g + 1) >> 1) & 1, wc, 18);
             tc_fence_after();
-            issue_scores(st ^ 1, n1, q_addr, Cfg::kColS);
+            XMC_TRACE(0, g, 2);
+            issue_scores(st ^ 1, n1, q_k, Cfg::kColS);
             if (c == 0) {
               mbar_wait(ch_full, ii & 1, wc, 19);
               tc_fence_after();
             }
-            issue_scores(st ^ 1, n1, c_addr, Cfg::kColW);
+            issue_scores(st ^ 1, n1, c_k, Cfg::kColW);
             mma_commit(sw_full);
+            XMC_TRACE(0, g, 3);
           }
         }
         mma_commit(dq_full);
@@ -657,43 +677,56 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           gam = __ldg(p.grel + o) / fmaxf(__ldg(p.cnorm + o), kEps);
           relv = __ldg(p.rel + o);
         }
-        const float grl = gam * relv;
+        const float ngrl = -gam * relv;
         for (int c = 0; c < nch; ++c, ++g) {
           const int n = min(CH, p.Rpad - c * CH);
           mbar_wait(sw_full, g & 1, wc, 20);
           tc_fence_after();
-          if (col0 < n) {
+          if (threadIdx.x == 128) XMC_TRACE(1, g, 0);
+          const bool active = col0 < n;              // warp-uniform: this warpgroup has columns in the chunk
+          const int r0 = c * CH + col0;
+          float z[32];
+          uint32_t xp[16], yp[16];
+          if (active) {
             uint32_t sv[32], wv[32];
             tmem_ld32(lane_base + Cfg::kColS + col0, sv);
             tmem_ld32(lane_base + Cfg::kColW + col0, wv);
             tmem_wait_ld();
-            const int r0 = c * CH + col0;
+            if (threadIdx.x == 128) XMC_TRACE(2, g, 0);
             const float* wsm = rn_s + (g & 1) * CH + col0;
-            const bool full = (r0 + 32 <= p.R);
-            float z[32];
-            uint32_t xp[16], yp[16];
+            auto elementwise = [&](auto full_tag) {
+              constexpr bool kFull = decltype(full_tag)::value;   // every column is a real region: no predicates
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + j4 * 4);
-              const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
-              float xv[4], yv[4];
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + j4 * 4);
+                const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
+                float xv[4], yv[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int j = j4 * 4 + u;
-                const bool valid = full || (r0 + j) < p.R;
-                const float s = valid ? __uint_as_float(sv[j]) : 0.f;
-                const float w = valid ? __uint_as_float(wv[j]) : 0.f;
-                const float al = valid ? ex2_approx(fmaf(c1, s, -c1)) * inv_l : 0.f;   // alpha
-                const float alp = al * mrv[u];                                         // alpha' = alpha * ||v_r||
-                const float dap = fmaf(-grl, w, gam * s);                              // d loss / d alpha'
-                xv[u] = fmaf(p.rho1 * alp, dap, gam * alp);                            // dS + gamma*alpha'
-                yv[u] = -grl * alp;
-                z[j] = al * dap;
+                for (int u = 0; u < 4; ++u) {
+                  const int j = j4 * 4 + u;
+                  const bool valid = kFull || (r0 + j) < p.R;
+                  const float s = valid ? __uint_as_float(sv[j]) : 0.f;
+                  const float w = valid ? __uint_as_float(wv[j]) : 0.f;
+                  const float al = valid ? ex2_approx(fmaf(c1, s, -c1)) * inv_l : 0.f;   // alpha
+                  const float alp = al * mrv[u];                                         // alpha' = alpha * ||v_r||
+                  const float dap = fmaf(ngrl, w, gam * s);                              // d loss / d alpha'
+                  xv[u] = alp * fmaf(p.rho1, dap, gam);                                  // dS + gamma*alpha'
+                  yv[u] = ngrl * alp;
+                  z[j] = al * dap;
+                }
+                xp[j4 * 2 + 0] = pack_bf16(xv[0], xv[1]); xp[j4 * 2 + 1] = pack_bf16(xv[2], xv[3]);
+                yp[j4 * 2 + 0] = pack_bf16(yv[0], yv[1]); yp[j4 * 2 + 1] = pack_bf16(yv[2], yv[3]);
               }
-              xp[j4 * 2 + 0] = pack_bf16(xv[0], xv[1]); xp[j4 * 2 + 1] = pack_bf16(xv[2], xv[3]);
-              yp[j4 * 2 + 0] = pack_bf16(yv[0], yv[1]); yp[j4 * 2 + 1] = pack_bf16(yv[2], yv[3]);
-            }
+            };
+            if (r0 + 32 <= p.R) elementwise(std::true_type{}); else elementwise(std::false_type{});
+          }
+          if (threadIdx.x == 128) XMC_TRACE(2, g, 1);
+          // the previous chunk's dK reductions must have finished reading the X|Y bytes
+          if (warp == 4 && lane == 0) bulk_wait_read<0>();
+          named_bar_sync(1, 256);
+          if (threadIdx.x == 128) XMC_TRACE(2, g, 2);
+          if (active) {
             // row `row` of the [128 x 64] bf16 tiles, 16-byte chunks XOR-swizzled by (row & 7)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -706,31 +739,42 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               if (r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
             }
           }
+          if (threadIdx.x == 128) XMC_TRACE(2, g, 3);
           fence_proxy_async_smem();
           tc_fence_before();
+          if (threadIdx.x == 128) XMC_TRACE(1, g, 1);
           mbar_arrive(xy_full);
-          // ---- drain dK^T of this chunk: TMEM -> fp32 rows in smem (X|Y bytes) -> bulk reduce-add ----
+          // ---- drain dK^T of this chunk: TMEM -> fp32 rows in smem (the dead X|Y bytes, two 16-row
+          //      buffers) -> cp.reduce.async.bulk add into dkn, overlapped with the next TMEM read ----
           mbar_wait(dk_full, g & 1, wc, 21);
           tc_fence_after();
-          for (int jb = 0; jb < n; jb += 32) {
-            const int rows = min(32, n - jb);
+          if (threadIdx.x == 128) XMC_TRACE(1, g, 2);
+          for (int qt = 0; qt * 16 < n; ++qt) {
+            float* buf = stage + (qt & 1) * 16 * D;
+            if (threadIdx.x == 128 && qt == 2) XMC_TRACE(3, g, 0);
+            if (qt >= 2) {
+              if (warp == 4 && lane == 0) bulk_wait_read<1>();     // the reduce issued from this buffer has read it
+              named_bar_sync(1, 256);
+            }
+            if (threadIdx.x == 128 && qt == 2) XMC_TRACE(3, g, 1);
             if (h < Cfg::kTilesD) {
-              uint32_t dv[32];
-              tmem_ld32(lane_base + Cfg::kColDK + h * CH + jb, dv);
+              uint32_t dv[16];
+              tmem_ld16(lane_base + Cfg::kColDK + h * CH + qt * 16, dv);
               tmem_wait_ld();
-              float* dst = stage + h * 128 + row;                // column d = 128h + row of the [rows x D] block
+              float* dst = buf + h * 128 + row;                    // column d = 128h + row of the [16 x D] block
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dst[j * D] = __uint_as_float(dv[j]);
+              for (int j = 0; j < 16; ++j) dst[j * D] = __uint_as_float(dv[j]);
             }
             fence_proxy_async_smem();
+            if (threadIdx.x == 128 && qt == 2) XMC_TRACE(3, g, 2);
             named_bar_sync(1, 256);
-            if (warp == 4 && lane == 0) {
-              bulk_reduce_add_f32(p.dkn + ((size_t)img * p.Rpad + c * CH + jb) * D, stage, rows * D * 4);
+            if (threadIdx.x == 128 && qt == 2) XMC_TRACE(3, g, 3);
+            if (warp == 4 && lane == 0 && !(p.dbg_flags & 2)) {
+              bulk_reduce_add_f32(p.dkn + ((size_t)img * p.Rpad + c * CH + qt * 16) * D, buf, 16 * D * 4);
               bulk_commit();
-              bulk_wait_read<0>();                               // smem may be overwritten after this
             }
-            named_bar_sync(1, 256);
           }
+          if (threadIdx.x == 128) XMC_TRACE(1, g, 3);
           tc_fence_before();
           mbar_arrive(dk_empty);
         }
@@ -756,7 +800,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if (warp == 2) tmem_dealloc(*tmem_slot, 512);
 }
 
 // 2-D [rows, D] / 3-D [outer, rows, D] bf16 tensor maps, box = 64 d x box_rows (x 1), 128B swizzle
@@ -788,6 +832,8 @@ static int launch_bwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
   p.lsum = w.lsum; p.cnorm = w.cnorm; p.rel = w.rel; p.grel = w.grel;
   p.dqn = w.dqn; p.dkn = w.dkn; p.drnorm = w.drnorm;
   p.err = static_cast<int*>(ws);
+  p.dbg_flags = g_debug_dump;
+  p.trace = ((g_debug_dump & 4) && ws_bytes >= 64 + 4 * 64 * 4 * 8) ? reinterpret_cast<long long*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
   const int tiles = (w.NQ + TM - 1) / TM;
   int splits = num_sms() / tiles;
   if (splits < 1) splits = 1;
