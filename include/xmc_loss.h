@@ -156,8 +156,9 @@ size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad,
  *   lsum  = sum_r exp(rho1*(s_qr - 1))     (softmax denominator, constant shift rho1)
  *   cnorm = || c_q ||                       (norm of the attended context)
  *   rel   = cos(e_q, c_q)
- * chat[Bi,NQ,D] bf16 (tcgen05 path only, nullable): the unit attended contexts c_q/||c_q||, saved
- * for the backward pass when gradients are needed (the fp32 path recomputes them and ignores it).
+ * chat[Bi,NQ,D] bf16 (tcgen05 path only, nullable): the attended context sums lsum * c_q
+ * (= sum_r exp(rho1*(s_qr - 1)) v_r), saved for the backward pass when gradients are needed (the
+ * fp32 path recomputes them and ignores it).
  * Rpad must be a multiple of 16 and >= R. */
 int xmc_wordregion_forward(int path, const void* qn, const void* kn, const float* rnorm,
                            int NQ, int Bi, int R, int Rpad, int D, float rho1,

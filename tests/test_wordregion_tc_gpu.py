@@ -95,12 +95,12 @@ def test_backward_vs_fp32_kernel(ops, B, D, T_, R, raw_values):
     dq1, dk1, dr1 = ops.wordregion_backward(_lib.PATH_BF16_TCGEN05, qn, kn, rn, R, 5.0, l1, c1, r1, grel, chat)
     assert _err_word(ops) == 0, "mbarrier wait timed out inside the backward kernel"
     dq0, dk0, dr0 = ops.wordregion_backward(_lib.PATH_FP32_SIMT, qn.float(), kn.float(), rn, R, 5.0, l1, c1, r1, grel)
-    # unit contexts saved by the forward
+    # context sums (unscaled softmax numerators times values) saved by the forward
     s_all = torch.einsum('qd,ird->iqr', qn.float(), kn.float())
     valid = (torch.arange(kn.shape[1], device="cuda") < R).float()
     pw = torch.exp(5.0 * (s_all - 1.0)) * valid * (rnorm.unsqueeze(1) if raw_values else 1.0)
     ctx = torch.einsum('iqr,ird->iqd', pw, kn.float())
-    chat_ref = ctx / ctx.norm(dim=-1, keepdim=True).clamp_min(1e-30)
+    chat_ref = ctx
     assert nerr(chat, chat_ref) < 1e-2, nerr(chat, chat_ref)
     assert nerr(dq1, dq0) < 1.5e-2, nerr(dq1, dq0)
     assert nerr(dk1, dk0) < 1.5e-2, nerr(dk1, dk0)

@@ -84,6 +84,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// smem box -> global tile (bulk async-group completion); out-of-bounds rows of the box are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / TMA reading smem)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -161,44 +166,45 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major,
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-// A descriptor is kept as its two 32-bit halves: only the low word (start address, bits [0,14))
-// changes between k-steps / blocks / stages, so stepping it is one 32-bit add of (byte offset >> 4).
-struct Desc {
-  uint32_t lo, hi;
-  __device__ __forceinline__ Desc operator+(uint32_t units16) const { return Desc{lo + units16, hi}; }
-};
+// A descriptor is a plain 64-bit value: only its low 14 bits (start address >> 4) change between
+// k-steps / blocks / stages, so stepping it is an add of (byte offset >> 4).
+typedef uint64_t Desc;
 __device__ __forceinline__ Desc make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  const uint64_t d = smem_desc(saddr, lbo_bytes, sbo_bytes);
-  return Desc{static_cast<uint32_t>(d), static_cast<uint32_t>(d >> 32)};
+  return smem_desc(saddr, lbo_bytes, sbo_bytes);
 }
 
-// The MMA-issuing warp runs CONVERGED (all 32 lanes execute the same code, so descriptors and
-// addresses stay in uniform registers); elect.sync picks the one lane that actually issues.
-// D[tmem] (+)= A[tmem] * B[smem]
+// The whole MMA-issuing (and TMA-producing) role runs inside ONE `if (elect_one())` of a warp whose
+// index is provably uniform (warp_index() below).  ptxas then keeps descriptors, TMEM addresses and
+// barrier addresses in uniform registers and emits back-to-back UTCHMMA with ~2 uniform-datapath
+// instructions between them (per-call elect.sync cost ~18 SASS instructions per MMA and left the
+// tensor pipe waiting on the issuing warp).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
+
+// D[tmem] (+)= A[tmem] * B[smem]          (single issuing thread)
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, Desc b, uint32_t idesc, bool accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\telect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %5, 0;\n\tmov.b64 db, {%2, %3};\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "r"(b.lo), "r"(b.hi), "r"(idesc), "r"(accumulate ? 1u : 0u)
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "r"(accumulate ? 1u : 0u)
       : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]
+// D[tmem] (+)= A[smem] * B[smem]          (single issuing thread)
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, Desc a, Desc b, uint32_t idesc, bool accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\telect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-      ::"r"(d_tmem), "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi), "r"(idesc), "r"(accumulate ? 1u : 0u)
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate ? 1u : 0u)
       : "memory");
 }
-// All previously issued MMAs of the elected lane arrive on `bar` when complete (implies
-// fence::before_thread_sync).  Warp-collective like mma_*: elect.sync picks the same lane.
+// All previously issued MMAs of this thread arrive on `bar` when complete (implies
+// fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

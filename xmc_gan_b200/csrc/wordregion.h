@@ -11,7 +11,7 @@ struct WrParams {
   int NQ, Bi, R, Rpad;
   float rho1;
   float* lsum; float* cnorm; float* rel;   // forward outputs / backward inputs, [Bi, NQ]
-  void* chat;                              // [Bi, NQ, D] bf16 unit contexts (tcgen05 path), nullable
+  void* chat;                              // [Bi, NQ, D] bf16 context sums C = l c_t (tcgen05 path), nullable
   const float* grel;                       // [Bi, NQ]
   float* dqn; float* dkn; float* drnorm;   // fp32, accumulated into
 };

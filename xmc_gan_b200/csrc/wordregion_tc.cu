@@ -32,19 +32,23 @@ constexpr int TM = 128;            // word rows per tile (UMMA M)
 constexpr int CH = 64;             // region rows per chunk
 constexpr float kLog2eTc = 1.4426950408889634f;
 
-constexpr int kFwdThreads = 384;     // 4 role warps + 2 softmax warpgroups
+constexpr int kFwdThreads = 512;     // 4 role warps + 2 softmax warpgroups + 1 epilogue warpgroup
 
 template <int D>
 struct FwdCfg {
   static constexpr int kStageBytes = CH * D * 2;
   static constexpr int kBlockBytes = CH * 128;                    // one [64 rows x 64 bf16] swizzled box
-  static constexpr int kStages = (D == 256) ? 6 : 8;
-  static constexpr int kOffRn = kStages * kStageBytes;            // [kStages][64] fp32 region norms of the chunk
-  static constexpr int kOffEx = kOffRn + kStages * CH * 4;        // [2 parity][2 wg][3][128] fp32 partials
-  static constexpr int kOffBar = kOffEx + 2 * 2 * 3 * TM * 4;
+  static constexpr int kStages = (D == 256) ? 4 : 6;
+  static constexpr int kOutBytes = TM * 128;                      // context staging: [128 rows x 64 bf16] swizzled box
+  static constexpr int kOutBoxes = D / 64;                        // one box per 64 features: a whole image's contexts
+  static constexpr int kOffOut = kStages * kStageBytes;           // staging boxes (1024-aligned)
+  static constexpr int kOffRn = kOffOut + kOutBoxes * kOutBytes;  // [kStages][64] fp32 region norms of the chunk
+  static constexpr int kOffEx = kOffRn + kStages * CH * 4;        // [2 parity][2 wg][2][128] fp32 partial l, a
+  static constexpr int kOffBar = kOffEx + 2 * 2 * 2 * TM * 4;
   static constexpr int kSmemBytes = kOffBar + 256 + 1024 /*align*/;
   static constexpr int kColC = 0, kColQ = D, kColS0 = D + D / 2, kColS1 = kColS0 + CH;
   static_assert(kColS1 + CH <= 512, "TMEM budget");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 struct TcFwdParams {
@@ -53,11 +57,18 @@ struct TcFwdParams {
   int NQ, Bi, R, Rpad;
   float rho1;
   float* lsum; float* cnorm; float* rel;
-  __nv_bfloat16* chat;         // [Bi, NQ, D] unit contexts saved for backward, or null
+  int save_ctx;                // context sums C = l * c_t go out through tm_ctx (bf16 [Bi, NQ, D]) for the backward
   int imgs_per_cta;
   int* err;
   float* dbg;                  // optional: S chunk 0 and C of the first tile/image (tests)
+  long long* trace;            // perf experiments only (flag 4): clock64 timeline of CTA (0,0), [4 roles][64][4]
 };
+
+#define XMC_TRACE(role, g, k)                                                             \
+  do {                                                                                   \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (g) < 64)                      \
+      p.trace[((role) * 64 + (g)) * 4 + (k)] = clock64();                               \
+  } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -74,11 +85,12 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 
 template <int D>
 __global__ void __launch_bounds__(kFwdThreads, 1)
-wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
+wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_ctx, TcFwdParams p) {
   using Cfg = FwdCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* kv = smem;                                               // kStages x kStageBytes
+  uint8_t* out_s = smem + Cfg::kOffOut;                             // 2 x kOutBytes
   float* rn_s = reinterpret_cast<float*>(smem + Cfg::kOffRn);
   float* ex_s = reinterpret_cast<float*>(smem + Cfg::kOffEx);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
@@ -86,14 +98,16 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
   uint64_t* kv_empty = bars + Cfg::kStages;       // [kStages]
   uint64_t* s_full = kv_empty + Cfg::kStages;     // [2]
   uint64_t* p_full = s_full + 2;                  // [2]
-  uint64_t* c_full = p_full + 2;
+  uint64_t* la_full = p_full + 2;                 // [2]  softmax partials of an image are in ex_s
+  uint64_t* la_empty = la_full + 2;               // [2]
+  uint64_t* c_full = la_empty + 2;
   uint64_t* c_empty = c_full + 1;
   uint64_t* q_ready = c_empty + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
   int* abort_flag = reinterpret_cast<int*>(tmem_slot + 1);
   const WaitCtx wc{abort_flag, p.err};
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TM;
   const int img0 = blockIdx.y * p.imgs_per_cta;
   const int img1 = min(p.Bi, img0 + p.imgs_per_cta);
@@ -105,12 +119,15 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
   if (threadIdx.x == 0) {
     *abort_flag = 0;
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(p_full + s, 256); }
-    mbar_init(c_full, 1); mbar_init(c_empty, 256); mbar_init(q_ready, 256);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full + s, 1); mbar_init(p_full + s, 256);
+      mbar_init(la_full + s, 256); mbar_init(la_empty + s, 128);
+    }
+    mbar_init(c_full, 1); mbar_init(c_empty, 128); mbar_init(q_ready, 256);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_k);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_ctx); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -123,7 +140,7 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
   if (G > 0) {
     if (warp == 0) {
       // ===== TMA producer =====
-      if (lane == 0) {
+      if (elect_one()) {
         int st = 0, ph = 1, c = 0, img = img0;       // ph: parity to wait on kv_empty (first pass free)
         for (int g = 0; g < G; ++g) {
           const int n = min(CH, p.Rpad - c * CH);
@@ -140,8 +157,8 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
       }
       __syncwarp();
     } else if (warp == 1) {
-      // ===== MMA issuer: whole warp converged, one elected lane issues =====
-      {
+      // ===== MMA issuer: one elected thread runs the whole role =====
+      if (elect_one()) {
         const uint32_t kv_addr = smem_u32(kv);
         constexpr uint32_t idesc2 = idesc_bf16(TM, D, false, true);
         // descriptor of stage 0; stages / k-steps are reached by adding (byte offset >> 4) to the low word
@@ -155,25 +172,35 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
           for (int k = 0; k < D / 16; ++k)
             mma_ts(d_tmem, tmem + Cfg::kColQ + k * 8, base + (((k >> 2) * Cfg::kBlockBytes + (k & 3) * 32) >> 4), idesc1, k > 0);
         };
+        // Issue order on the (in-order) tensor pipe: G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ...
+        // One exposed synchronisation point per chunk: P(g) written (and, at the first chunk of an image,
+        // the previous image's C drained); region chunk g+2 has normally landed long before.
         mbar_wait(q_ready, 0, wc, 2);
         mbar_wait(kv_full + 0, 0, wc, 3);
         tc_fence_after();
         issue_g1(0, min(CH, p.Rpad), 0);
         mma_commit(s_full + 0);
-        // state of chunk g (st, c, ii) and of chunk g+1 (st1, ph1, c1)
+        // chunk g: stage st, chunk-in-image c, image ii.  chunk g+2: stage st2 (parity ph2), chunk-in-image c2
         int st = 0, c = 0, ii = 0;
-        int st1 = (Cfg::kStages > 1) ? 1 : 0, ph1 = 0, c1 = (nch > 1) ? 1 : 0;
+        int st2 = 0, ph2 = 0, c2 = 0;
+        auto advance2 = [&]() {
+          if (++st2 == Cfg::kStages) { st2 = 0; ph2 ^= 1; }
+          if (++c2 == nch) c2 = 0;
+        };
+        advance2();
+        if (G > 1) {
+          mbar_wait(kv_full + st2, ph2, wc, 4);
+          tc_fence_after();
+          issue_g1(st2, min(CH, p.Rpad - c2 * CH), 1);
+          mma_commit(s_full + 1);
+        }
+        advance2();
         for (int g = 0; g < G; ++g) {
           const int sb = g & 1;
-          if (g + 1 < G) {
-            mbar_wait(kv_full + st1, ph1, wc, 4);
-            tc_fence_after();
-            issue_g1(st1, min(CH, p.Rpad - c1 * CH), sb ^ 1);
-            mma_commit(s_full + (sb ^ 1));
-          }
           mbar_wait(p_full + sb, (g >> 1) & 1, wc, 5);
           if (c == 0 && ii > 0) mbar_wait(c_empty, (ii - 1) & 1, wc, 6);
           tc_fence_after();
+          XMC_TRACE(0, g, 0);
           const int n = min(CH, p.Rpad - c * CH);
           const Desc vbase = vdesc0 + ((uint32_t)(st * Cfg::kStageBytes) >> 4);
           const uint32_t a_tmem = tmem + (sb ? Cfg::kColS1 : Cfg::kColS0);
@@ -184,16 +211,23 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
               mma_ts(tmem + Cfg::kColC, a_tmem + (ks >> 1) * 32 + (ks & 1) * 8, vbase + ((ks * 2048) >> 4), idesc2, (c > 0) || (ks > 0));
           mma_commit(kv_empty + st);
           if (c == nch - 1) mma_commit(c_full);
+          XMC_TRACE(0, g, 1);
+          if (g + 2 < G) {
+            mbar_wait(kv_full + st2, ph2, wc, 4);               // its latency hides behind G2(g) on the pipe
+            tc_fence_after();
+            issue_g1(st2, min(CH, p.Rpad - c2 * CH), sb);       // overwrites P(g) after G2(g): same pipe, in order
+            mma_commit(s_full + sb);
+          }
+          XMC_TRACE(0, g, 2);
           // advance
-          st = st1; c = c1;
-          if (c == 0) ++ii;
-          if (++st1 == Cfg::kStages) { st1 = 0; ph1 ^= 1; }
-          if (++c1 == nch) c1 = 0;
+          if (++st == Cfg::kStages) st = 0;
+          if (++c == nch) { c = 0; ++ii; }
+          advance2();
         }
       }
       __syncwarp();
-    } else if (warp >= 4) {
-      // ===== softmax / epilogue warpgroups: thread = TMEM lane = word row; WG h owns chunk cols [32h, 32h+32)
+    } else if (warp >= 4 && warp < 12) {
+      // ===== softmax warpgroups: thread = TMEM lane = word row; WG h owns chunk cols [32h, 32h+32)
       const int h = (warp - 4) >> 2;
       const int q = warp & 3;
       const int row = q * 32 + lane;
@@ -221,17 +255,18 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
       const int col0 = h * 32;
       int st = 0, g = 0;
       for (int ii = 0; ii < nimg; ++ii) {
-        const int img = img0 + ii;
         float l = 0.f, a = 0.f;
         for (int c = 0; c < nch; ++c, ++g) {
           const int n = min(CH, p.Rpad - c * CH);
           const uint32_t s_col = (g & 1) ? Cfg::kColS1 : Cfg::kColS0;
           mbar_wait(s_full + (g & 1), (g >> 1) & 1, wc, 7);
           tc_fence_after();
+          if (threadIdx.x == 128) XMC_TRACE(1, g, 0);
           if (col0 < n) {
             uint32_t sv[32];
             tmem_ld32(lane_base + s_col + col0, sv);
             tmem_wait_ld();
+            if (threadIdx.x == 128) XMC_TRACE(1, g, 1);
             if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && g == 0) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) p.dbg[row * CH + col0 + j] = __uint_as_float(sv[j]);
@@ -239,112 +274,141 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, TcFwdParams p) {
             uint32_t pk[16];
             const int r0 = c * CH + col0;
             const float* wsm = rn_s + st * CH + col0;
-            if (r0 + 32 <= p.R) {                           // every column is a real region: no predicates
+            // phase 1: all exponentials back to back (packed fp32x2 FMAs feed the MUFU)
+            float pv[32];
+            {
+              const float2 cc = make_float2(c1, c1), ncc = make_float2(-c1, -c1);
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + j4 * 4);
-                const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
-                float pw[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float s = __uint_as_float(sv[j4 * 4 + u]);
-                  const float pv = ex2_approx(fmaf(c1, s, -c1));
-                  l += pv;
-                  pw[u] = pv * mrv[u];
-                  a = fmaf(pw[u], s, a);
-                }
-                pk[j4 * 2 + 0] = pack_bf16(pw[0], pw[1]);
-                pk[j4 * 2 + 1] = pack_bf16(pw[2], pw[3]);
-              }
-            } else {                                        // ragged tail of the image
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                float pw[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const int j = j4 * 4 + u;
-                  const bool valid = (r0 + j) < p.R;
-                  const float s = valid ? __uint_as_float(sv[j]) : 0.f;
-                  const float pv = valid ? ex2_approx(fmaf(c1, s, -c1)) : 0.f;
-                  const float mr = (has_rn && valid) ? wsm[j] : 1.f;
-                  l += pv;
-                  pw[u] = pv * mr;
-                  a = fmaf(pw[u], s, a);
-                }
-                pk[j4 * 2 + 0] = pack_bf16(pw[0], pw[1]);
-                pk[j4 * 2 + 1] = pack_bf16(pw[2], pw[3]);
+              for (int j2 = 0; j2 < 16; ++j2) {
+                const float2 arg = __ffma2_rn(make_float2(__uint_as_float(sv[2 * j2]), __uint_as_float(sv[2 * j2 + 1])), cc, ncc);
+                pv[2 * j2] = ex2_approx(arg.x);
+                pv[2 * j2 + 1] = ex2_approx(arg.y);
               }
             }
+            if (r0 + 32 > p.R) {                            // ragged tail of the image: padded columns weigh 0
+#pragma unroll
+              for (int j = 0; j < 32; ++j) pv[j] = (r0 + j) < p.R ? pv[j] : 0.f;
+            }
+            if (threadIdx.x == 128) XMC_TRACE(3, g, 0);
+            // phase 2: l += p, p' = p * ||v_r||, a += p' s, pack (packed fp32x2, two chains each)
+            float2 l2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + j4 * 4);   // rows past Rpad of the chunk: pv = 0
+              const float2 mr2[2] = {make_float2(mr.x, mr.y), make_float2(mr.z, mr.w)};
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int j = j4 * 4 + 2 * u;
+                const float2 p2 = make_float2(pv[j], pv[j + 1]);
+                const float2 s2 = make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
+                l2[u] = __fadd2_rn(l2[u], p2);
+                const float2 pw = has_rn ? __fmul2_rn(p2, mr2[u]) : p2;
+                a2[u] = __ffma2_rn(pw, s2, a2[u]);
+                pk[j4 * 2 + u] = pack_bf16(pw.x, pw.y);
+              }
+            }
+            l += (l2[0].x + l2[0].y) + (l2[1].x + l2[1].y);
+            a += (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
+            if (threadIdx.x == 128) XMC_TRACE(3, g, 1);
             tmem_st16(lane_base + s_col + col0, pk);        // WG0 -> S cols [0,16), WG1 -> [32,48)
             tmem_wait_st();
           }
+          if (threadIdx.x == 128) XMC_TRACE(1, g, 2);
           tc_fence_before();
           mbar_arrive(p_full + (g & 1));
+          if (threadIdx.x == 128) XMC_TRACE(1, g, 3);
           if (++st == Cfg::kStages) st = 0;
         }
-        // ---- epilogue of this image: ||C||, statistics, unit contexts ----
+        // hand this warpgroup's partial l, a of the image to the epilogue warpgroup
+        mbar_wait(la_empty + (ii & 1), ((ii >> 1) & 1) ^ 1, wc, 9);
+        float* ex = ex_s + (ii & 1) * (2 * 2 * TM);
+        ex[(h * 2 + 0) * TM + row] = l;
+        ex[(h * 2 + 1) * TM + row] = a;
+        mbar_arrive(la_full + (ii & 1));                    // release semantics: the stores above are visible
+      }
+    } else if (warp >= 12) {
+      // ===== epilogue warpgroup: thread = TMEM lane = word row.  One pass over C per image:
+      //       ||C|| -> statistics;  bf16 C -> swizzled smem boxes -> TMA store (saved for the backward)
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int grow = m0 + row;
+      const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
+      const bool issuer = (threadIdx.x == 384);
+      for (int ii = 0; ii < nimg; ++ii) {
+        const int img = img0 + ii;
+        mbar_wait(la_full + (ii & 1), (ii >> 1) & 1, wc, 10);
+        const float* ex = ex_s + (ii & 1) * (2 * 2 * TM);
+        const float l = ex[0 * TM + row] + ex[2 * TM + row];
+        const float a = ex[1 * TM + row] + ex[3 * TM + row];
+        mbar_arrive(la_empty + (ii & 1));
+        const float inv_l = 1.f / l;
+        if (p.save_ctx) {
+          if (issuer) bulk_wait_read<0>();                  // the previous image's stores have read the boxes
+          named_bar_sync(2, 128);
+        }
         mbar_wait(c_full, ii & 1, wc, 8);
         tc_fence_after();
-        float c2 = 0.f;
-        constexpr int kHalf = D / 2;
-#pragma unroll 1
-        for (int blk = 0; blk < kHalf / 32; ++blk) {
-          uint32_t cv[32];
-          tmem_ld32(lane_base + Cfg::kColC + h * kHalf + blk * 32, cv);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = __uint_as_float(cv[j]);
-            c2 = fmaf(v, v, c2);
-          }
+        if (issuer) XMC_TRACE(2, ii, 0);
+        float2 c2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        uint32_t cva[32], cvb[32];
+        // 32 columns -> square-sum (packed fp32x2), bf16 -> four 16-byte units of the row's 128-byte box line.
+        // The saved tile is the UNSCALED sum C = l * c; the backward folds 1/(l ||c||) into its coefficients.
+        auto consume = [&](const uint32_t (&cv)[32], int blk32) {
           if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ii == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) p.dbg[TM * CH + row * D + h * kHalf + blk * 32 + j] = __uint_as_float(cv[j]);
+            for (int j = 0; j < 32; ++j) p.dbg[TM * CH + row * D + blk32 * 32 + j] = __uint_as_float(cv[j]);
           }
-        }
-        // combine the two warpgroups' partial l, a, ||C||^2 (double-buffered by image parity)
-        float* ex = ex_s + (ii & 1) * (2 * 3 * TM);
-        ex[(h * 3 + 0) * TM + row] = l;
-        ex[(h * 3 + 1) * TM + row] = a;
-        ex[(h * 3 + 2) * TM + row] = c2;
-        named_bar_sync(1, 256);
-        const int o = 1 - h;
-        l += ex[(o * 3 + 0) * TM + row];
-        a += ex[(o * 3 + 1) * TM + row];
-        c2 += ex[(o * 3 + 2) * TM + row];
-        if (p.chat) {
-          // second TMEM pass: unit context rows -> bf16 -> global (saved for the backward kernel)
-          const float inv_c = 1.f / fmaxf(sqrtf(c2), kEps * l);
-          uint4* dst = reinterpret_cast<uint4*>(p.chat + ((size_t)img * p.NQ + grow) * D + h * kHalf);
-#pragma unroll 1
-          for (int blk = 0; blk < kHalf / 32; ++blk) {
-            uint32_t cv[32];
-            tmem_ld32(lane_base + Cfg::kColC + h * kHalf + blk * 32, cv);
-            tmem_wait_ld();
-            if (grow < p.NQ) {
+          uint8_t* line = out_s + (blk32 >> 1) * Cfg::kOutBytes + row * 128;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                uint4 ov;
-                ov.x = pack_bf16(__uint_as_float(cv[8 * u + 0]) * inv_c, __uint_as_float(cv[8 * u + 1]) * inv_c);
-                ov.y = pack_bf16(__uint_as_float(cv[8 * u + 2]) * inv_c, __uint_as_float(cv[8 * u + 3]) * inv_c);
-                ov.z = pack_bf16(__uint_as_float(cv[8 * u + 4]) * inv_c, __uint_as_float(cv[8 * u + 5]) * inv_c);
-                ov.w = pack_bf16(__uint_as_float(cv[8 * u + 6]) * inv_c, __uint_as_float(cv[8 * u + 7]) * inv_c);
-                dst[blk * 4 + u] = ov;
-              }
+          for (int u = 0; u < 4; ++u) {                     // 8 bf16 = one 16-byte unit
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 v = make_float2(__uint_as_float(cv[8 * u + 2 * e]), __uint_as_float(cv[8 * u + 2 * e + 1]));
+              c2[e & 1] = __ffma2_rn(v, v, c2[e & 1]);
+              w[e] = pack_bf16(v.x, v.y);
             }
+            if (p.save_ctx)
+              *reinterpret_cast<uint4*>(line + ((((blk32 & 1) * 4 + u) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        };
+        tmem_ld32(lane_base + Cfg::kColC, cva);
+#pragma unroll 1
+        for (int b2 = 0; b2 < D / 64; ++b2) {               // two 32-column loads in flight / being consumed
+          tmem_wait_ld();
+          tmem_ld32(lane_base + Cfg::kColC + b2 * 64 + 32, cvb);
+          consume(cva, 2 * b2);
+          tmem_wait_ld();
+          if (b2 + 1 < D / 64) {
+            tmem_ld32(lane_base + Cfg::kColC + b2 * 64 + 64, cva);
+          } else {                                          // C is in registers: the next image may overwrite it
+            tc_fence_before();
+            mbar_arrive(c_empty);
+            if (issuer) XMC_TRACE(2, ii, 1);
+          }
+          consume(cvb, 2 * b2 + 1);
+        }
+        if (p.save_ctx) {
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (issuer) {
+#pragma unroll
+            for (int b = 0; b < Cfg::kOutBoxes; ++b) tma_store_3d(&tm_ctx, out_s + b * Cfg::kOutBytes, b * 64, m0, img);
+            bulk_commit();
           }
         }
-        tc_fence_before();
-        mbar_arrive(c_empty);
-        if (h == 0 && grow < p.NQ) {
-          const float cn = sqrtf(c2) / l;
+        if (issuer) XMC_TRACE(2, ii, 3);
+        if (grow < p.NQ) {
+          const float cn = sqrtf((c2[0].x + c2[0].y) + (c2[1].x + c2[1].y)) * inv_l;
           const size_t o2 = (size_t)img * p.NQ + grow;
           p.lsum[o2] = l;
           p.cnorm[o2] = cn;
-          p.rel[o2] = (a / l) / fmaxf(cn, kEps);
+          p.rel[o2] = (a * inv_l) / fmaxf(cn, kEps);
         }
       }
+      if (issuer) bulk_wait<0>();                           // all context stores performed before exit
     }
   }
   tc_fence_before();
@@ -386,6 +450,21 @@ static int make_region_map(CUtensorMap* m, const void* kn, int Bi, int Rpad, int
   return XMC_OK;
 }
 
+// 2-D [rows, D] / 3-D [outer, rows, D] bf16 tensor maps, box = 64 d x box_rows (x 1), 128B swizzle
+static int make_rows_map(CUtensorMap* m, const void* base, int outer, int rows, int D, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  XMC_REQUIRE(enc != nullptr, XMC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)rows, (cuuint64_t)outer};
+  cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)rows * D * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, outer > 0 ? 3 : 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XMC_REQUIRE(r == CUDA_SUCCESS, XMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return XMC_OK;
+}
+
 static int num_sms() {
   int dev = 0, n = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -396,16 +475,19 @@ template <int D>
 static int launch_fwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStream_t st) {
   using Cfg = FwdCfg<D>;
   XMC_REQUIRE(ws && ws_bytes >= 64, XMC_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
-  CUtensorMap tm;
+  CUtensorMap tm, tctx;
   if (int rc = make_region_map(&tm, w.kn, w.Bi, w.Rpad, D)) return rc;
+  // without a context buffer the map is never used; point it at the words so that it encodes
+  if (int rc = make_rows_map(&tctx, w.chat ? w.chat : w.qn, w.chat ? w.Bi : 1, w.NQ, D, TM)) return rc;
   TcFwdParams p{};
   p.qn = static_cast<const __nv_bfloat16*>(w.qn);
   p.rnorm = w.rnorm; p.NQ = w.NQ; p.Bi = w.Bi; p.R = w.R; p.Rpad = w.Rpad; p.rho1 = w.rho1;
   p.lsum = w.lsum; p.cnorm = w.cnorm; p.rel = w.rel;
-  p.chat = static_cast<__nv_bfloat16*>(w.chat);
+  p.save_ctx = w.chat != nullptr;
   p.err = static_cast<int*>(ws);
   p.dbg = ((g_debug_dump & 1) && ws_bytes >= 64 + sizeof(float) * (size_t)(TM * CH + TM * D))
               ? reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
+  p.trace = ((g_debug_dump & 4) && ws_bytes >= 64 + 4 * 64 * 4 * 8) ? reinterpret_cast<long long*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
   const int tiles = (w.NQ + TM - 1) / TM;
   int splits = num_sms() / tiles;
   if (splits < 1) splits = 1;
@@ -413,7 +495,7 @@ static int launch_fwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
   p.imgs_per_cta = (w.Bi + splits - 1) / splits;
   splits = (w.Bi + p.imgs_per_cta - 1) / p.imgs_per_cta;
   XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  wr_fwd_tc_kernel<D><<<dim3(tiles, splits), kFwdThreads, Cfg::kSmemBytes, st>>>(tm, p);
+  wr_fwd_tc_kernel<D><<<dim3(tiles, splits), kFwdThreads, Cfg::kSmemBytes, st>>>(tm, tctx, p);
   return cuda_fail(cudaGetLastError(), "wr_fwd_tc_kernel launch");
 }
 
@@ -433,8 +515,8 @@ int wordregion_tc_forward(const WrParams& p, int D, void* ws, size_t ws_bytes, c
 
 // =====================================================================================================
 // Backward.  Tile = (128 word rows) x (one image); the CTA keeps its word tile Q in smem and the
-// gradient dQ [128 x D] in TMEM across ALL the images it visits; per image the saved unit contexts
-// Chat arrive by TMA, the regions in 64-row chunks through a 2-stage ring.  Per chunk:
+// gradient dQ [128 x D] in TMEM across ALL the images it visits; per image the saved contexts
+// Chat (C = l c_t, bf16; 1/(l ||c||) is folded into the elementwise coefficients) arrive by TMA, the regions in 64-row chunks through a 2-stage ring.  Per chunk:
 //   S = Q Khat^T, W = Chat Khat^T                     (SS MMAs, K-major operands)          -> TMEM
 //   X = dS + gamma*alpha', Y = -gamma*rel*alpha'      (2 warpgroups, bf16, 128B-swizzled smem tiles)
 //   dQ   += X Khat_chunk                              (A = X K-major, B = Khat MN-major)   -> TMEM, persistent
@@ -493,12 +575,6 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
   return v[0];
 }
 
-#define XMC_TRACE(role, g, k)                                                             \
-  do {                                                                                   \
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (g) < 64)                      \
-      p.trace[((role) * 64 + (g)) * 4 + (k)] = clock64();                               \
-  } while (0)
-
 template <int D>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_c,
@@ -528,7 +604,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   int* abort_flag = reinterpret_cast<int*>(tmem_slot + 1);
   const WaitCtx wc{abort_flag, p.err};
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TM;
   const int img0 = blockIdx.y * p.imgs_per_cta;
   const int nimg = min(p.Bi, img0 + p.imgs_per_cta) - img0;
@@ -558,7 +634,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (G > 0) {
     if (warp == 0) {
       // ===== TMA producer =====
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_expect_tx(q_full, Cfg::kQBytes);
 #pragma unroll
         for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(Qs + kb * Cfg::kQBlock, &tm_q, kb * 64, m0, q_full);
@@ -584,8 +660,8 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
       __syncwarp();
     } else if (warp == 1) {
-      // ===== MMA issuer: whole warp converged, one elected lane issues =====
-      {
+      // ===== MMA issuer: one elected thread runs the whole role =====
+      if (elect_one()) {
         constexpr uint32_t idesc_dq = idesc_bf16(TM, D, false, true);
         // base descriptors; k-steps / blocks / stages are reached by adding (byte offset >> 4)
         const Desc q_k = make_desc(smem_u32(Qs), 16, 1024), q_mn = make_desc(smem_u32(Qs), Cfg::kQBlock, 1024);
@@ -670,14 +746,16 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       int g = 0;
       for (int ii = 0; ii < nimg; ++ii) {
         const int img = img0 + ii;
-        float inv_l = 1.f, gam = 0.f, relv = 0.f;
+        float inv_l = 1.f, gam = 0.f, ngrl = 0.f;
         if (grow < p.NQ) {
           const size_t o = (size_t)img * p.NQ + grow;
+          const float inv_cn = 1.f / fmaxf(__ldg(p.cnorm + o), kEps);
           inv_l = 1.f / __ldg(p.lsum + o);
-          gam = __ldg(p.grel + o) / fmaxf(__ldg(p.cnorm + o), kEps);
-          relv = __ldg(p.rel + o);
+          gam = __ldg(p.grel + o) * inv_cn;
+          // the saved context is the unscaled sum C = l c (not the unit vector): W = C K^T and the
+          // Chat^T Y term both carry 1 / (l ||c||), folded into the coefficient that multiplies them
+          ngrl = -gam * __ldg(p.rel + o) * inv_cn * inv_l;
         }
-        const float ngrl = -gam * relv;
         for (int c = 0; c < nch; ++c, ++g) {
           const int n = min(CH, p.Rpad - c * CH);
           mbar_wait(sw_full, g & 1, wc, 20);
@@ -803,26 +881,11 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 2) tmem_dealloc(*tmem_slot, 512);
 }
 
-// 2-D [rows, D] / 3-D [outer, rows, D] bf16 tensor maps, box = 64 d x box_rows (x 1), 128B swizzle
-static int make_rows_map(CUtensorMap* m, const void* base, int outer, int rows, int D, int box_rows) {
-  PFN_encodeTiled enc = get_encode();
-  XMC_REQUIRE(enc != nullptr, XMC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)rows, (cuuint64_t)outer};
-  cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)rows * D * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, outer > 0 ? 3 : 2, const_cast<void*>(base), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  XMC_REQUIRE(r == CUDA_SUCCESS, XMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  return XMC_OK;
-}
-
 template <int D>
 static int launch_bwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStream_t st) {
   using Cfg = BwdCfg<D>;
   XMC_REQUIRE(ws && ws_bytes >= 64, XMC_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
-  XMC_REQUIRE(w.chat != nullptr, XMC_ERR_INVALID_ARG, "the tcgen05 backward needs the unit contexts saved by the forward (chat)");
+  XMC_REQUIRE(w.chat != nullptr, XMC_ERR_INVALID_ARG, "the tcgen05 backward needs the contexts saved by the forward (chat)");
   CUtensorMap tq, tcm, tk;
   if (int rc = make_rows_map(&tq, w.qn, 0, w.NQ, D, TM)) return rc;
   if (int rc = make_rows_map(&tcm, w.chat, w.Bi, w.NQ, D, TM)) return rc;
