@@ -22,12 +22,9 @@ torch.cuda.synchronize()
 hook(0)
 tr = ops.last_workspace[64:64 + 4 * 64 * 4 * 8].view(torch.int64).view(4, 64, 4).cpu()
 t0 = int(tr[1, 0, 0])
-print("chunk | MMA: xy-ready, B issued, kv-ready, A issued | EW: sw-ready, E done, dk-ready, drain done   (cycles since first sw-ready)")
-for g_ in range(5, 21):
+print("chunk | MMA: SW(g+1) issue start, XY(g) ready, dQ/dK(g) issued, end | arith(g): sw ready, consumed, done | loop(g): XY stored, arith(g+1) done, dk ready, drain done")
+for g_ in range(4, 24):
     m = [int(v) - t0 for v in tr[0, g_]]
-    e = [int(v) - t0 for v in tr[1, g_]]
-    x = [int(v) for v in tr[2, g_]]
-    y = [int(v) for v in tr[3, g_]]
-    print(f"      drain quarter 2: start@{y[0]-int(tr[1,g_,2])} after dk-ready; wait_read+bar={y[1]-y[0]} ld+sts+fence={y[2]-y[1]} bar={y[3]-y[2]}")
-    print(f"      E parts: ld={x[0]-int(tr[1,g_,0])} math={x[1]-x[0]} wait+bar={x[2]-x[1]} stores+colsum={x[3]-x[2]}")
-    print(f"{g_:3d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d} | {e[0]:7d} {e[1]:7d} {e[2]:7d} {e[3]:7d} | E={e[1]-e[0]:5d} waitdk={e[2]-e[1]:5d} drain={e[3]-e[2]:5d} period={int(tr[1,g_,0])-int(tr[1,g_-1,0]):6d}")
+    a = [int(v) - t0 for v in tr[1, g_]]
+    e = [int(v) - t0 for v in tr[2, g_]]
+    print(f"{g_:3d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d} | {a[0]:7d} {a[1]:7d} {a[2]:7d} (ld {a[1]-a[0]}, math {a[2]-a[1]}) | {e[0]:7d} {e[1]:7d} {e[2]:7d} {e[3]:7d} (wait dk {e[2]-e[1]}, drain {e[3]-e[2]}) period {e[0]-int(tr[2,g_-1,0])+t0}")

@@ -515,20 +515,34 @@ int wordregion_tc_forward(const WrParams& p, int D, void* ws, size_t ws_bytes, c
 
 // =====================================================================================================
 // Backward.  Tile = (128 word rows) x (one image); the CTA keeps its word tile Q in smem and the
-// gradient dQ [128 x D] in TMEM across ALL the images it visits; per image the saved contexts
-// Chat (C = l c_t, bf16; 1/(l ||c||) is folded into the elementwise coefficients) arrive by TMA, the regions in 64-row chunks through a 2-stage ring.  Per chunk:
+// gradient dQ [128 x D] in TMEM across ALL the images it visits; per image the saved context sums
+// Chat (C = l c_t, bf16; 1/(l ||c||) is folded into the elementwise coefficients) arrive by TMA, the
+// regions in 64-row chunks through a 2-stage ring.  Per chunk g:
 //   S = Q Khat^T, W = Chat Khat^T                     (SS MMAs, K-major operands)          -> TMEM
 //   X = dS + gamma*alpha', Y = -gamma*rel*alpha'      (2 warpgroups, bf16, 128B-swizzled smem tiles)
 //   dQ   += X Khat_chunk                              (A = X K-major, B = Khat MN-major)   -> TMEM, persistent
-//   dK^T  = Q^T X + Chat^T Y   [D x 64]               (A = Q / Chat as MN-major, B = X / Y MN-major) -> TMEM
-//   dK^T -> fp32 rows staged in smem (the dead X|Y bytes) -> cp.reduce.async.bulk add into dkn;
+//   dK^T  = Chat^T Y + Q^T X   [D x 64]               (A = Chat / Q as MN-major, B = Y / X MN-major) -> TMEM
+//   dK^T -> registers -> red.global.add.f32 into dkn (a warp adds 128 contiguous bytes per instruction);
 //           column sums of alpha*d alpha' -> drnorm
 // The same smem bytes serve as K-major and as MN-major operands; nothing of size Bi x Bc x T x R
 // ever reaches global memory.
-// Warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 elementwise WG0 (chunk cols 0-31, dK^T rows d<128),
-// 8-11 elementwise WG1 (cols 32-63, d>=128).
+//
+// Software pipeline (tensor pipe order):  S,W(g+1) | dQ(g) dK^T(g) | S,W(g+2) | dQ(g+1) dK^T(g+1) ...
+//   * S,W(g+1) is issued as soon as the elementwise warps hold S,W(g) in registers (sw_consumed), so it
+//     runs under their arithmetic;
+//   * the elementwise warps do the arithmetic of chunk g+1 while dQ(g), dK^T(g) execute, then drain dK^T(g);
+//   * at an image boundary W(g+1) needs the next image's Chat, which can only be fetched once the last
+//     dK^T of the current image has consumed the old one: there the order is S(g+1) | dQ dK^T(g) | W(g+1).
+//   * dK^T(g) is drained by a dedicated warpgroup: the adds into dkn run at the L2's atomic rate
+//     (~3000 clk per chunk with every SM active, measured) and would otherwise stall the arithmetic.
+// Warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 elementwise WG0 (chunk cols 0-31), 8-11 elementwise WG1
+// (cols 32-63), 12-15 drain WG (dK^T rows d<128, then d>=128).  Registers are re-partitioned with
+// setmaxnreg (the sum must stay within the CTA's launch allocation, 512 x 128): 168 per elementwise
+// thread, 88 per drain thread, 80 per role thread.
 // =====================================================================================================
-constexpr int kBwdThreads = 384;
+constexpr int kBwdThreads = 512;
+constexpr int kBwdRegsRole = 80, kBwdRegsEw = 168, kBwdRegsDrain = 88;
+static_assert(128 * kBwdRegsRole + 256 * kBwdRegsEw + 128 * kBwdRegsDrain <= 512 * 128, "register pool of the CTA");
 
 template <int D>
 struct BwdCfg {
@@ -542,10 +556,8 @@ struct BwdCfg {
   static constexpr int kSmemBytes = kOffRn + 2 * CH * 4 + 1024;
   static constexpr int kTilesD = D / 128;          // M-tiles of dK^T
   static constexpr int kColDQ = 0, kColS = D, kColW = D + CH, kColDK = D + 2 * CH;
-  static constexpr int kDrainRows = (2 * kXBytes) / (D * 4);   // region rows of fp32 dK staged per bulk reduce
   static_assert(kColDK + kTilesD * CH <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
-  static_assert(kDrainRows >= 32, "staging buffer holds at least one TMEM load of rows");
 };
 
 struct TcBwdParams {
@@ -574,6 +586,13 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
   }
   return v[0];
 }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
 
 template <int D>
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -587,7 +606,6 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint8_t* kv = smem + Cfg::kOffKv;
   uint8_t* Xs = smem + Cfg::kOffX;
   uint8_t* Ys = smem + Cfg::kOffY;
-  float* stage = reinterpret_cast<float*>(Xs);      // X|Y bytes double as the fp32 dK staging buffer
   float* rn_s = reinterpret_cast<float*>(smem + Cfg::kOffRn);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* q_full = bars + 0;
@@ -596,11 +614,12 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint64_t* kv_full = bars + 3;    // [2]
   uint64_t* kv_empty = bars + 5;   // [2]
   uint64_t* sw_full = bars + 7;
-  uint64_t* xy_full = bars + 8;
-  uint64_t* dk_full = bars + 9;
-  uint64_t* dk_empty = bars + 10;
-  uint64_t* dq_full = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* sw_consumed = bars + 8;
+  uint64_t* xy_full = bars + 9;
+  uint64_t* dk_full = bars + 10;
+  uint64_t* dk_empty = bars + 11;
+  uint64_t* dq_full = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   int* abort_flag = reinterpret_cast<int*>(tmem_slot + 1);
   const WaitCtx wc{abort_flag, p.err};
 
@@ -616,8 +635,8 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     *abort_flag = 0;
     mbar_init(q_full, 1); mbar_init(ch_full, 1); mbar_init(ch_empty, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
-    mbar_init(sw_full, 1); mbar_init(xy_full, 256); mbar_init(dk_full, 1); mbar_init(dk_empty, 256);
-    mbar_init(dq_full, 1);
+    mbar_init(sw_full, 1); mbar_init(sw_consumed, 256); mbar_init(xy_full, 256);
+    mbar_init(dk_full, 1); mbar_init(dk_empty, 128); mbar_init(dq_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -631,8 +650,11 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (threadIdx.x == 0 && *tmem_slot != 0) { *abort_flag = 1; if (p.err) atomicExch(p.err, 999); }
   __syncthreads();
 
-  if (G > 0) {
-    if (warp == 0) {
+  // setmaxnreg sits at the top of each role's branch so that it dominates the role's code (ptxas
+  // allocates registers per region only then)
+  if (warp < 4) {
+    setmaxnreg_dec<kBwdRegsRole>();
+    if (G > 0 && warp == 0) {
       // ===== TMA producer =====
       if (elect_one()) {
         mbar_expect_tx(q_full, Cfg::kQBytes);
@@ -655,11 +677,17 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             for (int kb = 0; kb < D / 64; ++kb)
               tma_load_3d(Cs + kb * Cfg::kQBlock, &tm_c, kb * 64, m0, img0 + ii, ch_full);
           }
+          // the next image's contexts come from HBM and are needed the moment this image ends (the single
+          // buffer cannot be refilled earlier): pull them into L2 shortly before
+          if (c == max(0, nch - 3) && ii + 1 < nimg) {
+#pragma unroll
+            for (int kb = 0; kb < D / 64; ++kb) tma_prefetch_l2_3d(&tm_c, kb * 64, m0, img0 + ii + 1);
+          }
           if (++c == nch) { c = 0; ++ii; }
         }
       }
       __syncwarp();
-    } else if (warp == 1) {
+    } else if (G > 0 && warp == 1) {
       // ===== MMA issuer: one elected thread runs the whole role =====
       if (elect_one()) {
         constexpr uint32_t idesc_dq = idesc_bf16(TM, D, false, true);
@@ -688,54 +716,76 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         int c = 0, ii = 0;
         for (int g = 0; g < G; ++g) {
           const int st = g & 1, n = min(CH, p.Rpad - c * CH);
-          mbar_wait(xy_full, g & 1, wc, 16);
-          if (g > 0) mbar_wait(dk_empty, (g - 1) & 1, wc, 17);
-          tc_fence_after();
-          XMC_TRACE(0, g, 0);
-          // dK^T tiles: [128 d x n] = Q^T X + Chat^T Y   (contraction over the 128 word rows)
-          const uint32_t idesc_dk = idesc_bf16(TM, n, true, true);
-#pragma unroll
-          for (int h = 0; h < Cfg::kTilesD; ++h) {
-#pragma unroll
-            for (int kt = 0; kt < TM / 16; ++kt)
-              mma_ss(tmem + Cfg::kColDK + h * CH, q_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), x_mn + ((kt * 2048) >> 4), idesc_dk, kt > 0);
-#pragma unroll
-            for (int kt = 0; kt < TM / 16; ++kt)
-              mma_ss(tmem + Cfg::kColDK + h * CH, c_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), y_mn + ((kt * 2048) >> 4), idesc_dk, true);
-          }
           const bool last_chunk = (c == nch - 1);
-          if (last_chunk) mma_commit(ch_empty);
-          // dQ += X Khat_chunk
-          {
+          const bool has_next = g + 1 < G;
+          const int n1 = last_chunk ? min(CH, p.Rpad) : min(CH, p.Rpad - (c + 1) * CH);
+          if (has_next) {
+            // S,W(g) are in the elementwise warps' registers: the next scores may overwrite them now
+            mbar_wait(sw_consumed, g & 1, wc, 16);
+            mbar_wait(kv_full + (st ^ 1), ((g + 1) >> 1) & 1, wc, 18);
+            tc_fence_after();
+            XMC_TRACE(0, g, 0);
+            issue_scores(st ^ 1, n1, q_k, Cfg::kColS);
+            if (!last_chunk) {
+              issue_scores(st ^ 1, n1, c_k, Cfg::kColW);
+              mma_commit(sw_full);
+            }
+          }
+          mbar_wait(xy_full, g & 1, wc, 17);
+          if (g > 0) mbar_wait(dk_empty, (g - 1) & 1, wc, 19);
+          tc_fence_after();
+          XMC_TRACE(0, g, 1);
+          const uint32_t idesc_dk = idesc_bf16(TM, n, true, true);
+          auto issue_dq = [&]() {                       // dQ += X Khat_chunk
             const Desc b_mn = kv_mn + ((uint32_t)(st * Cfg::kKvStage) >> 4);
 #pragma unroll
             for (int ks = 0; ks < CH / 16; ++ks)
               if (ks * 16 < n) mma_ss(tmem + Cfg::kColDQ, x_k + ((ks * 32) >> 4), b_mn + ((ks * 2048) >> 4), idesc_dq, (g > 0) || (ks > 0));
-          }
-          mma_commit(kv_empty + st);
-          mma_commit(dk_full);          // X / Y are dead once this fires: the drain may reuse their bytes
-          XMC_TRACE(0, g, 1);
-          if (++c == nch) { c = 0; ++ii; }
-          if (g + 1 < G) {
-            const int n1 = min(CH, p.Rpad - c * CH);
-            mbar_wait(kv_full + (st ^ 1), ((g + 1) >> 1) & 1, wc, 18);
-            tc_fence_after();
-            XMC_TRACE(0, g, 2);
-            issue_scores(st ^ 1, n1, q_k, Cfg::kColS);
-            if (c == 0) {
-              mbar_wait(ch_full, ii & 1, wc, 19);
-              tc_fence_after();
+            mma_commit(kv_empty + st);
+          };
+          auto issue_dk_c = [&]() {                     // dK^T = Chat^T Y   [128 d x n] per M-tile, contraction over the 128 word rows
+#pragma unroll
+            for (int h = 0; h < Cfg::kTilesD; ++h) {
+#pragma unroll
+              for (int kt = 0; kt < TM / 16; ++kt)
+                mma_ss(tmem + Cfg::kColDK + h * CH, c_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), y_mn + ((kt * 2048) >> 4), idesc_dk, kt > 0);
             }
+          };
+          if (last_chunk) {
+            // end of the image: release the context buffer first, the refill overlaps dQ and the Q part of dK^T
+            issue_dk_c();
+            mma_commit(ch_empty);
+            issue_dq();
+          } else {
+            // inside the image: release the region stage first, the next chunk's load overlaps dK^T
+            issue_dq();
+            issue_dk_c();
+          }
+#pragma unroll
+          for (int h = 0; h < Cfg::kTilesD; ++h) {      // dK^T += Q^T X
+#pragma unroll
+            for (int kt = 0; kt < TM / 16; ++kt)
+              mma_ss(tmem + Cfg::kColDK + h * CH, q_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), x_mn + ((kt * 2048) >> 4), idesc_dk, true);
+          }
+          mma_commit(dk_full);          // X / Y are dead once this fires
+          XMC_TRACE(0, g, 2);
+          if (has_next && last_chunk) {
+            mbar_wait(ch_full, (ii + 1) & 1, wc, 15);
+            tc_fence_after();
             issue_scores(st ^ 1, n1, c_k, Cfg::kColW);
             mma_commit(sw_full);
-            XMC_TRACE(0, g, 3);
           }
+          XMC_TRACE(0, g, 3);
+          if (++c == nch) { c = 0; ++ii; }
         }
         mma_commit(dq_full);
       }
       __syncwarp();
-    } else if (warp >= 4) {
-      // ===== elementwise warpgroups: thread = TMEM lane = word row (S/W) or feature d (dK^T) =====
+    }
+  } else if (warp < 12) {
+    setmaxnreg_inc<kBwdRegsEw>();
+    if (G > 0) {
+      // ===== elementwise warpgroups: thread = TMEM lane = word row =====
       const int h = (warp - 4) >> 2;              // 0: chunk cols 0-31, 1: cols 32-63
       const int q = warp & 3;
       const int row = q * 32 + lane;
@@ -743,121 +793,112 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
       const float c1 = p.rho1 * kLog2eTc;
       const int col0 = h * 32;
-      int g = 0;
-      for (int ii = 0; ii < nimg; ++ii) {
-        const int img = img0 + ii;
-        float inv_l = 1.f, gam = 0.f, ngrl = 0.f;
-        if (grow < p.NQ) {
-          const size_t o = (size_t)img * p.NQ + grow;
-          const float inv_cn = 1.f / fmaxf(__ldg(p.cnorm + o), kEps);
-          inv_l = 1.f / __ldg(p.lsum + o);
-          gam = __ldg(p.grel + o) * inv_cn;
-          // the saved context is the unscaled sum C = l c (not the unit vector): W = C K^T and the
-          // Chat^T Y term both carry 1 / (l ||c||), folded into the coefficient that multiplies them
-          ngrl = -gam * __ldg(p.rel + o) * inv_cn * inv_l;
+      const bool tracer = (threadIdx.x == 128);
+
+      // ---- arithmetic of one chunk (gm): S,W -> X,Y (packed bf16, registers) and the drnorm column sum ----
+      int gm = 0, cm = 0, iim = 0;
+      float inv_l = 1.f, gam = 0.f, ngrl = 0.f;
+      uint32_t xp[16], yp[16];
+      float colsum = 0.f;
+      auto arithmetic = [&]() {
+        if (cm == 0) {
+          inv_l = 1.f; gam = 0.f; ngrl = 0.f;
+          if (grow < p.NQ) {
+            const size_t o = (size_t)(img0 + iim) * p.NQ + grow;
+            const float inv_cn = 1.f / fmaxf(__ldg(p.cnorm + o), kEps);
+            inv_l = 1.f / __ldg(p.lsum + o);
+            gam = __ldg(p.grel + o) * inv_cn;
+            // the saved context is the unscaled sum C = l c (not the unit vector): W = C K^T and the
+            // Chat^T Y term both carry 1 / (l ||c||), folded into the coefficient that multiplies them
+            ngrl = -gam * __ldg(p.rel + o) * inv_cn * inv_l;
+          }
         }
-        for (int c = 0; c < nch; ++c, ++g) {
-          const int n = min(CH, p.Rpad - c * CH);
-          mbar_wait(sw_full, g & 1, wc, 20);
-          tc_fence_after();
-          if (threadIdx.x == 128) XMC_TRACE(1, g, 0);
-          const bool active = col0 < n;              // warp-uniform: this warpgroup has columns in the chunk
-          const int r0 = c * CH + col0;
+        const int n = min(CH, p.Rpad - cm * CH);
+        const int r0 = cm * CH + col0;
+        mbar_wait(sw_full, gm & 1, wc, 20);
+        tc_fence_after();
+        if (tracer) XMC_TRACE(1, gm, 0);
+        if (col0 < n) {                               // warp-uniform: this warpgroup has columns in the chunk
+          const float* wsm = rn_s + (gm & 1) * CH + col0;
           float z[32];
-          uint32_t xp[16], yp[16];
-          if (active) {
-            uint32_t sv[32], wv[32];
-            tmem_ld32(lane_base + Cfg::kColS + col0, sv);
-            tmem_ld32(lane_base + Cfg::kColW + col0, wv);
+          // two halves of 16 columns (register budget); S,W are released after the second load
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t sv[16], wv[16];
+            tmem_ld16(lane_base + Cfg::kColS + col0 + hf * 16, sv);
+            tmem_ld16(lane_base + Cfg::kColW + col0 + hf * 16, wv);
             tmem_wait_ld();
-            if (threadIdx.x == 128) XMC_TRACE(2, g, 0);
-            const float* wsm = rn_s + (g & 1) * CH + col0;
+            if (hf == 1) {
+              tc_fence_before();
+              mbar_arrive(sw_consumed);
+              if (tracer) XMC_TRACE(1, gm, 1);
+            }
             auto elementwise = [&](auto full_tag) {
               constexpr bool kFull = decltype(full_tag)::value;   // every column is a real region: no predicates
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
+              for (int j4 = 0; j4 < 4; ++j4) {
                 float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + j4 * 4);
+                if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + hf * 16 + j4 * 4);
                 const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
                 float xv[4], yv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const int j = j4 * 4 + u;
-                  const bool valid = kFull || (r0 + j) < p.R;
-                  const float s = valid ? __uint_as_float(sv[j]) : 0.f;
-                  const float w = valid ? __uint_as_float(wv[j]) : 0.f;
-                  const float al = valid ? ex2_approx(fmaf(c1, s, -c1)) * inv_l : 0.f;   // alpha
+                  const float s = __uint_as_float(sv[j]);
+                  const float w = __uint_as_float(wv[j]);
+                  float al = ex2_approx(fmaf(c1, s, -c1)) * inv_l;                       // alpha
+                  if (!kFull) al = (r0 + hf * 16 + j) < p.R ? al : 0.f;                  // padded region rows: alpha = 0 zeroes X, Y, z
                   const float alp = al * mrv[u];                                         // alpha' = alpha * ||v_r||
                   const float dap = fmaf(ngrl, w, gam * s);                              // d loss / d alpha'
                   xv[u] = alp * fmaf(p.rho1, dap, gam);                                  // dS + gamma*alpha'
                   yv[u] = ngrl * alp;
-                  z[j] = al * dap;
+                  z[hf * 16 + j] = al * dap;
                 }
-                xp[j4 * 2 + 0] = pack_bf16(xv[0], xv[1]); xp[j4 * 2 + 1] = pack_bf16(xv[2], xv[3]);
-                yp[j4 * 2 + 0] = pack_bf16(yv[0], yv[1]); yp[j4 * 2 + 1] = pack_bf16(yv[2], yv[3]);
+                xp[hf * 8 + j4 * 2 + 0] = pack_bf16(xv[0], xv[1]); xp[hf * 8 + j4 * 2 + 1] = pack_bf16(xv[2], xv[3]);
+                yp[hf * 8 + j4 * 2 + 0] = pack_bf16(yv[0], yv[1]); yp[hf * 8 + j4 * 2 + 1] = pack_bf16(yv[2], yv[3]);
               }
             };
             if (r0 + 32 <= p.R) elementwise(std::true_type{}); else elementwise(std::false_type{});
           }
-          if (threadIdx.x == 128) XMC_TRACE(2, g, 1);
-          // the previous chunk's dK reductions must have finished reading the X|Y bytes
-          if (warp == 4 && lane == 0) bulk_wait_read<0>();
-          named_bar_sync(1, 256);
-          if (threadIdx.x == 128) XMC_TRACE(2, g, 2);
-          if (active) {
-            // row `row` of the [128 x 64] bf16 tiles, 16-byte chunks XOR-swizzled by (row & 7)
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int phys = ((col0 >> 3) + u) ^ (row & 7);
-              *reinterpret_cast<uint4*>(Xs + row * 128 + phys * 16) = make_uint4(xp[4 * u], xp[4 * u + 1], xp[4 * u + 2], xp[4 * u + 3]);
-              *reinterpret_cast<uint4*>(Ys + row * 128 + phys * 16) = make_uint4(yp[4 * u], yp[4 * u + 1], yp[4 * u + 2], yp[4 * u + 3]);
-            }
-            if (has_rn) {
-              const float colsum = warp_transpose_sum32(z, lane);      // column (r0 + lane) over this warp's 32 rows
-              if (r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
-            }
-          }
-          if (threadIdx.x == 128) XMC_TRACE(2, g, 3);
-          fence_proxy_async_smem();
+          if (has_rn) colsum = warp_transpose_sum32(z, lane);      // column (r0 + lane) over this warp's 32 rows
+        } else {
           tc_fence_before();
-          if (threadIdx.x == 128) XMC_TRACE(1, g, 1);
-          mbar_arrive(xy_full);
-          // ---- drain dK^T of this chunk: TMEM -> fp32 rows in smem (the dead X|Y bytes, two 16-row
-          //      buffers) -> cp.reduce.async.bulk add into dkn, overlapped with the next TMEM read ----
-          mbar_wait(dk_full, g & 1, wc, 21);
-          tc_fence_after();
-          if (threadIdx.x == 128) XMC_TRACE(1, g, 2);
-          for (int qt = 0; qt * 16 < n; ++qt) {
-            float* buf = stage + (qt & 1) * 16 * D;
-            if (threadIdx.x == 128 && qt == 2) XMC_TRACE(3, g, 0);
-            if (qt >= 2) {
-              if (warp == 4 && lane == 0) bulk_wait_read<1>();     // the reduce issued from this buffer has read it
-              named_bar_sync(1, 256);
-            }
-            if (threadIdx.x == 128 && qt == 2) XMC_TRACE(3, g, 1);
-            if (h < Cfg::kTilesD) {
-              uint32_t dv[16];
-              tmem_ld16(lane_base + Cfg::kColDK + h * CH + qt * 16, dv);
-              tmem_wait_ld();
-              float* dst = buf + h * 128 + row;                    // column d = 128h + row of the [16 x D] block
-#pragma unroll
-              for (int j = 0; j < 16; ++j) dst[j * D] = __uint_as_float(dv[j]);
-            }
-            fence_proxy_async_smem();
-            if (threadIdx.x == 128 && qt == 2) XMC_TRACE(3, g, 2);
-            named_bar_sync(1, 256);
-            if (threadIdx.x == 128 && qt == 2) XMC_TRACE(3, g, 3);
-            if (warp == 4 && lane == 0 && !(p.dbg_flags & 2)) {
-              bulk_reduce_add_f32(p.dkn + ((size_t)img * p.Rpad + c * CH + qt * 16) * D, buf, 16 * D * 4);
-              bulk_commit();
-            }
-          }
-          if (threadIdx.x == 128) XMC_TRACE(1, g, 3);
-          tc_fence_before();
-          mbar_arrive(dk_empty);
+          mbar_arrive(sw_consumed);
         }
+        if (tracer) XMC_TRACE(1, gm, 2);
+        ++gm;
+        if (++cm == nch) { cm = 0; ++iim; }
+      };
+
+      arithmetic();                                   // chunk 0
+      int c = 0, ii = 0;
+      for (int g = 0; g < G; ++g) {
+        const int img = img0 + ii;
+        const int n = min(CH, p.Rpad - c * CH);
+        const bool active = col0 < n;
+        const int r0 = c * CH + col0;
+        // ---- X,Y(g) -> smem.  Safe: dk_full(g-1) was waited for below, so the MMAs that read X,Y(g-1) are done.
+        if (active) {
+          // row `row` of the [128 x 64] bf16 tiles, 16-byte chunks XOR-swizzled by (row & 7)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int phys = ((col0 >> 3) + u) ^ (row & 7);
+            *reinterpret_cast<uint4*>(Xs + row * 128 + phys * 16) = make_uint4(xp[4 * u], xp[4 * u + 1], xp[4 * u + 2], xp[4 * u + 3]);
+            *reinterpret_cast<uint4*>(Ys + row * 128 + phys * 16) = make_uint4(yp[4 * u], yp[4 * u + 1], yp[4 * u + 2], yp[4 * u + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(xy_full);
+        if (tracer) XMC_TRACE(2, g, 0);
+        if (active && has_rn && r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
+        // ---- arithmetic of chunk g+1 while dQ(g), dK^T(g) run on the tensor pipe ----
+        if (g + 1 < G) arithmetic();
+        if (tracer) XMC_TRACE(2, g, 1);
+        // ---- X,Y(g) stay live until dQ(g), dK^T(g) have executed ----
+        mbar_wait(dk_full, g & 1, wc, 21);
+        if (tracer) XMC_TRACE(2, g, 2);
+        if (++c == nch) { c = 0; ++ii; }
       }
-      if (warp == 4 && lane == 0) bulk_wait<0>();                // all reductions performed before exit
       // ---- dQ of this CTA's word tile (summed over its images) ----
       mbar_wait(dq_full, 0, wc, 22);
       tc_fence_after();
@@ -873,6 +914,48 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             for (int j = 0; j < 32; ++j) atomicAdd(dst + blk * 32 + j, __uint_as_float(dv[j]));
           }
         }
+      }
+    }
+  } else {
+    setmaxnreg_dec<kBwdRegsDrain>();
+    if (G > 0) {
+      // ===== drain warpgroup: dK^T(g) TMEM -> registers -> red.global.add.f32 into dkn.  Thread = TMEM
+      //       lane = feature d of an M-tile; a warp adds 32 consecutive d of one region row (128 bytes). =====
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
+      const bool tracer = (threadIdx.x == 384);
+      int c = 0, ii = 0;
+      for (int g = 0; g < G; ++g) {
+        const int n = min(CH, p.Rpad - c * CH);
+        mbar_wait(dk_full, g & 1, wc, 23);
+        tc_fence_after();
+        if (tracer) XMC_TRACE(3, g, 0);
+#pragma unroll
+        for (int h = 0; h < Cfg::kTilesD; ++h) {
+          float* dst0 = p.dkn + ((size_t)(img0 + ii) * p.Rpad + c * CH) * D + h * 128 + row;
+          uint32_t dva[32], dvb[32];
+          tmem_ld32(lane_base + Cfg::kColDK + h * CH, dva);            // rows of the chunk past n hold stale data:
+          if (n > 32) tmem_ld32(lane_base + Cfg::kColDK + h * CH + 32, dvb);   // never added below
+          tmem_wait_ld();
+          if (h == Cfg::kTilesD - 1) {                                 // dK^T(g) is in registers
+            tc_fence_before();
+            mbar_arrive(dk_empty);
+            if (tracer) XMC_TRACE(3, g, 1);
+          }
+          if (!(p.dbg_flags & 2)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < n) red_add_f32(dst0 + (size_t)j * D, __uint_as_float(dva[j]));
+            if (n > 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (32 + j < n) red_add_f32(dst0 + (size_t)(32 + j) * D, __uint_as_float(dvb[j]));
+            }
+          }
+        }
+        if (tracer) XMC_TRACE(3, g, 2);
+        if (++c == nch) { c = 0; ++ii; }
       }
     }
   }
