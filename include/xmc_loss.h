@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define XMC_ABI_VERSION 1
+#define XMC_ABI_VERSION 2
 
 typedef enum {
   XMC_OK = 0,
@@ -137,16 +137,29 @@ int xmc_make_labels(const float* sim, int B, float p, float smooth_global,
  * The [Bi,Bc,T,R] score tensor never exists in global memory.
  * ------------------------------------------------------------------------------------------- */
 
+/* Compaction of the word rows (tcgen05 path).  mask[Bc,T] bytes, non-zero = padding
+ * (encoder.py:61,149).  Padded words are excluded from the loss and have zero gradient, so the
+ * tensor-core kernels only visit the valid rows, in caption-major order:
+ *   row_of[c*T+t] = compact row of word (c,t), or -1 for padding;
+ *   cap_ptr[c]    = first compact row of caption c; cap_ptr[Bc] = number of valid rows
+ * (a device-side count: pass &cap_ptr[Bc] as nq_dev below; the host never reads it). */
+int xmc_word_rows_compact(const uint8_t* mask, int Bc, int T, int* row_of /*[Bc*T]*/,
+                          int* cap_ptr /*[Bc+1]*/, void* stream);
+
 /* x[B, D, L] (channel-major, L contiguous) -> xn[B, Lpad, D] = x / max(||x||,1e-12) per (b,l),
- * rows l >= L zero-filled; norm[B, Lpad] = max(||x||,1e-12) (0 for padding rows). */
+ * rows l >= L zero-filled; norm[B, Lpad] = max(||x||,1e-12) (0 for padding rows).
+ * row_of (nullable; needs Lpad == L): row (b,l) is written to xn[row_of[b*L+l]] instead and
+ * skipped when that is negative (the caller zero-fills xn[B*L, D] first); norm stays dense. */
 int xmc_normalize_transpose(const void* x, int B, int D, int L, int Lpad, int in_dtype,
-                            int out_dtype, void* xn, float* norm, void* stream);
+                            int out_dtype, const int* row_of, void* xn, float* norm, void* stream);
 
 /* Backward of the above.  dxn[B,Lpad,D] fp32 is the gradient w.r.t. the unit rows; dnorm[B,Lpad]
- * (nullable) the gradient w.r.t. the norm.  dx[B,D,L] has dtype out_dtype. */
+ * (nullable) the gradient w.r.t. the norm.  dx[B,D,L] has dtype out_dtype.  With row_of the
+ * rows of xn / dxn are the compact ones and dropped words get a zero gradient. */
 int xmc_normalize_transpose_backward(const void* xn, const float* norm, const float* dxn,
                                      const float* dnorm, int B, int D, int L, int Lpad,
-                                     int xn_dtype, int out_dtype, void* dx, void* stream);
+                                     int xn_dtype, int out_dtype, const int* row_of, void* dx,
+                                     void* stream);
 
 size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad, int D);
 
@@ -159,10 +172,14 @@ size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad,
  * chat[Bi,NQ,D] bf16 (tcgen05 path only, nullable): the attended context sums lsum * c_q
  * (= sum_r exp(rho1*(s_qr - 1)) v_r), saved for the backward pass when gradients are needed (the
  * fp32 path recomputes them and ignores it).
- * Rpad must be a multiple of 16 and >= R. */
+ * Rpad must be a multiple of 16 and >= R.
+ * nq_dev (tcgen05 path, nullable): DEVICE pointer to the number of valid word rows (<= NQ, e.g.
+ * &cap_ptr[Bc] of xmc_word_rows_compact); NQ stays the row stride of every [Bi, NQ] buffer and
+ * rows at or beyond *nq_dev are neither read nor written.  The kernels size their own schedule
+ * from it (one persistent CTA per SM), so no host synchronisation is needed. */
 int xmc_wordregion_forward(int path, const void* qn, const void* kn, const float* rnorm,
                            int NQ, int Bi, int R, int Rpad, int D, float rho1,
-                           float* lsum, float* cnorm, float* rel, void* chat,
+                           float* lsum, float* cnorm, float* rel, void* chat, const int* nq_dev,
                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* grel[Bi,NQ] = d loss / d rel.  dqn[NQ,D], dkn[Bi,Rpad,D], drnorm[Bi,Rpad] (nullable iff rnorm
@@ -171,17 +188,19 @@ int xmc_wordregion_forward(int path, const void* qn, const void* kn, const float
 int xmc_wordregion_backward(int path, const void* qn, const void* kn, const float* rnorm,
                             int NQ, int Bi, int R, int Rpad, int D, float rho1,
                             const float* lsum, const float* cnorm, const float* rel, const void* chat,
-                            const float* grel, float* dqn, float* dkn, float* drnorm,
+                            const float* grel, float* dqn, float* dkn, float* drnorm, const int* nq_dev,
                             void* workspace, size_t workspace_bytes, void* stream);
 
-/* scores[Bi,Bc] = (1/rho2) * log sum_{t: !mask[c][t]} exp(rho2 * rel[i][c*T+t]);
- * mask[Bc,T] bytes, non-zero = padding (encoder.py:61,149), NULL = no padding.
+/* scores[Bi,Bc] = (1/rho2) * log sum_{t: !mask[c][t]} exp(rho2 * rel[i][row(c,t)]);  rel has row
+ * stride NQs.  Dense rows (cap_ptr NULL): row(c,t) = c*T+t, mask[Bc,T] bytes, non-zero = padding
+ * (encoder.py:61,149), NULL = no padding.  Compact rows: caption c owns rows
+ * [cap_ptr[c], cap_ptr[c+1]) and mask is ignored.
  * A fully padded caption scores 0 and receives zero gradient. */
-int xmc_word_scores(const float* rel, const uint8_t* mask, int Bi, int Bc, int T, float rho2,
-                    float* scores, void* stream);
-int xmc_word_scores_backward(const float* rel, const uint8_t* mask, const float* scores,
-                             const float* dscores, int Bi, int Bc, int T, float rho2,
-                             float* grel, void* stream);
+int xmc_word_scores(const float* rel, const uint8_t* mask, const int* cap_ptr, int Bi, int Bc, int T,
+                    int NQs, float rho2, float* scores, void* stream);
+int xmc_word_scores_backward(const float* rel, const uint8_t* mask, const int* cap_ptr,
+                             const float* scores, const float* dscores, int Bi, int Bc, int T,
+                             int NQs, float rho2, float* grel, void* stream);
 
 #ifdef __cplusplus
 }

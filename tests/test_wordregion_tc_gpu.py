@@ -124,3 +124,45 @@ def test_word_loss_bf16_vs_oracle(B, D, T_, R):
     assert lerr(loss, lo) <= TOL_BF16, (float(loss), float(lo))
     assert nerr(r.grad, ro.grad) <= TOL_BF16, nerr(r.grad, ro.grad)
     assert nerr(w.grad, wo.grad) <= TOL_BF16, nerr(w.grad, wo.grad)
+
+
+@pytest.mark.parametrize("Bc,T_", [(7, 18), (256, 18), (100, 32), (3, 5)])
+def test_word_rows_compact(ops, Bc, T_):
+    g = torch.Generator().manual_seed(Bc)
+    mask = torch.rand(Bc, T_, generator=g) < 0.4          # arbitrary pattern, not only suffix padding
+    mask[0] = True                                         # a fully padded caption
+    row_of, cap_ptr = ops.word_rows_compact(mask.to(torch.uint8).cuda())
+    valid = (~mask).flatten()
+    ref = torch.where(valid, torch.cumsum(valid.int(), 0) - 1, torch.full_like(valid.int(), -1))
+    assert torch.equal(row_of.cpu(), ref.int())
+    ptr = torch.cat([torch.zeros(1, dtype=torch.long), (~mask).sum(1).cumsum(0)])
+    assert torch.equal(cap_ptr.cpu().long(), ptr)
+
+
+@pytest.mark.parametrize("B,D,T_,R", [(32, 256, 18, 289), (12, 128, 9, 64), (150, 256, 18, 40)])
+def test_compact_rows_match_dense_rows(B, D, T_, R):
+    """The compacted schedule (valid word rows only, device-side count, persistent CTAs) and the dense one
+    (every padded row visited) give the same loss and gradients."""
+    from xmc_gan_b200 import train_gan as T
+    from xmc_gan_b200.ops import default_ops
+    words, regions, mask = word_inputs(B, D, T_, R, seed=11 * B)
+    mask[1] = True                                         # one fully padded caption
+    labels = T.make_labels(B, None, False)
+    out = []
+    ops = default_ops()
+    for compact in (True, False):
+        ops.supports_compaction = compact
+        try:
+            r = regions.bfloat16().cuda().requires_grad_()
+            w = words.bfloat16().cuda().requires_grad_()
+            loss = T.word_loss(r, w, mask.cuda(), labels, False, precision="bf16")
+            loss.backward()
+            out.append((loss.detach(), r.grad, w.grad))
+        finally:
+            ops.supports_compaction = True
+    (l1, r1, w1), (l0, r0, w0) = out
+    assert lerr(l1, l0) <= 1e-5, (float(l1), float(l0))
+    assert nerr(r1, r0) <= 2e-3, nerr(r1, r0)             # bf16 outputs, different summation order
+    assert nerr(w1, w0) <= 2e-3, nerr(w1, w0)
+    assert float(w1[1].abs().max()) == 0.0                 # padded words: exactly zero gradient
+    assert float((w1 * mask.cuda()[:, None, :]).abs().max()) == 0.0

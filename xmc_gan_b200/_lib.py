@@ -42,14 +42,15 @@ SIGNATURES = {
     "xmc_simloss_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp,
                                   _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "xmc_make_labels": (_i, [_vp, _i, _f, _f, _vp, _vp, _vp, _vp]),
-    "xmc_normalize_transpose": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "xmc_normalize_transpose_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "xmc_word_rows_compact": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "xmc_normalize_transpose": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "xmc_normalize_transpose_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "xmc_wordregion_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "xmc_wordregion_forward": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xmc_wordregion_forward": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "xmc_wordregion_backward": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,
-                                     _vp, _vp, _vp, _vp, _sz, _vp]),
-    "xmc_word_scores": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
-    "xmc_word_scores_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+                                     _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xmc_word_scores": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "xmc_word_scores_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
 }
 
 

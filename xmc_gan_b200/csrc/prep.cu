@@ -12,9 +12,57 @@ namespace xmc {
 
 constexpr int kLT = 32;  // (b, 32 consecutive l) per CTA
 
+// Compaction of the word rows: captions are padded to T words (mask non-zero = padding,
+// encoder.py:61,149); padded words never contribute (their relevance is excluded from the
+// log-sum-exp and their gradient is zero), so the tensor-core kernels work on the valid rows only.
+// row_of[c*T+t] = index of the word among the valid ones (caption-major order) or -1;
+// cap_ptr[c] = first compact row of caption c, cap_ptr[Bc] = number of valid rows.  One CTA.
+__global__ void __launch_bounds__(1024) word_rows_compact_kernel(const uint8_t* __restrict__ mask, int n, int T,
+                                                                  int* __restrict__ row_of, int* __restrict__ cap_ptr) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_sh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_sh = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const int v = (i < n && !mask[i]) ? 1 : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_tot[lane] = w;                          // inclusive over warps
+    }
+    __syncthreads();
+    const int base = base_sh;
+    const int excl = base + (warp ? warp_tot[warp - 1] : 0) + incl - v;
+    if (i < n) {
+      row_of[i] = v ? excl : -1;
+      if (i % T == 0) cap_ptr[i / T] = excl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base_sh = base + warp_tot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cap_ptr[n / T] = base_sh;
+}
+
 // x[B,D,L] -> xn[B,Lpad,D], norm[B,Lpad].  256 threads; dynamic smem D*(kLT+1) floats.
+// row_of (nullable, needs Lpad == L): row (b,l) goes to xn[row_of[b*L+l]] and is skipped when negative.
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) norm_tr_kernel(const TI* __restrict__ x, int D, int L, int Lpad,
+                                                       const int* __restrict__ row_of,
                                                        TO* __restrict__ xn, float* __restrict__ norm) {
   extern __shared__ float tile[];                 // [D][kLT+1]
   __shared__ float part[8][kLT];
@@ -44,7 +92,12 @@ __global__ void __launch_bounds__(256) norm_tr_kernel(const TI* __restrict__ x, 
     const int lr = l0 + r;
     if (lr >= Lpad) break;
     const float inv = inv_sh[r];
-    TO* dst = xn + ((size_t)b * Lpad + lr) * D;
+    long long orow = (long long)b * Lpad + lr;
+    if (row_of) {
+      orow = row_of[orow];
+      if (orow < 0) continue;
+    }
+    TO* dst = xn + (size_t)orow * D;
     for (int d = lx; d < D; d += 32) st1(dst + d, tile[d * (kLT + 1) + r] * inv);
   }
 }
@@ -53,17 +106,20 @@ __global__ void __launch_bounds__(256) norm_tr_kernel(const TI* __restrict__ x, 
 template <typename TX, typename TO>
 __global__ void __launch_bounds__(256) norm_tr_bwd_kernel(const TX* __restrict__ xn, const float* __restrict__ norm,
                                                            const float* __restrict__ dxn, const float* __restrict__ dnorm,
-                                                           int D, int L, int Lpad, TO* __restrict__ dx) {
+                                                           int D, int L, int Lpad, const int* __restrict__ row_of,
+                                                           TO* __restrict__ dx) {
   extern __shared__ float tile[];                 // [D][kLT+1] holds the finished dx tile
   const int b = blockIdx.y, l0 = blockIdx.x * kLT;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = warp; r < kLT; r += 8) {
     const int l = l0 + r;
-    if (l >= L) {
+    long long irow = (long long)b * Lpad + l;
+    if (l < L && row_of) irow = row_of[irow];          // compact rows: a dropped (padding) word has no gradient
+    if (l >= L || irow < 0) {
       for (int d = lane; d < D; d += 32) tile[d * (kLT + 1) + r] = 0.f;
       continue;
     }
-    const size_t row = ((size_t)b * Lpad + l) * D;
+    const size_t row = (size_t)irow * D;
     float proj = 0.f;
     for (int d = lane; d < D; d += 32) proj = fmaf(ld1(xn + row + d), dxn[row + d], proj);
     proj = warp_sum(proj);
@@ -83,56 +139,66 @@ __global__ void __launch_bounds__(256) norm_tr_bwd_kernel(const TX* __restrict__
     for (int d = warp; d < D; d += 8) st1(dx + ((size_t)b * D + d) * L + l, tile[d * (kLT + 1) + lane]);
 }
 
-// scores[i,c] = (1/rho2) log sum_{t unmasked} exp(rho2 rel[i, c*T+t]);   one thread per (i,c)
+// scores[i,c] = (1/rho2) log sum_{t unmasked} exp(rho2 rel[i, row(c,t)]);   one thread per (i,c).
+// Dense rows: row(c,t) = c*T+t with the padding mask; compact rows: caption c owns rows [cap_ptr[c], cap_ptr[c+1]).
 __global__ void __launch_bounds__(256) word_scores_kernel(const float* __restrict__ rel, const uint8_t* __restrict__ mask,
-                                                           int Bi, int Bc, int T, float rho2, float* __restrict__ scores) {
+                                                           const int* __restrict__ cap_ptr, int Bi, int Bc, int T, int NQs,
+                                                           float rho2, float* __restrict__ scores) {
   const size_t k = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (k >= (size_t)Bi * Bc) return;
   const int c = (int)(k % Bc);
-  const float* r = rel + k * T;                     // (i*Bc + c)*T
+  const size_t i = k / Bc;
+  const int lo = cap_ptr ? cap_ptr[c] : c * T, hi = cap_ptr ? cap_ptr[c + 1] : c * T + T;
+  const float* r = rel + i * NQs;
+  const uint8_t* mk = (mask && !cap_ptr) ? mask : nullptr;
   float m = -INFINITY;
-  for (int t = 0; t < T; ++t)
-    if (!mask || !mask[(size_t)c * T + t]) m = fmaxf(m, rho2 * r[t]);
+  for (int q = lo; q < hi; ++q)
+    if (!mk || !mk[q]) m = fmaxf(m, rho2 * r[q]);
   if (m == -INFINITY) { scores[k] = 0.f; return; }  // fully padded caption
   float s = 0.f;
-  for (int t = 0; t < T; ++t)
-    if (!mask || !mask[(size_t)c * T + t]) s += __expf(rho2 * r[t] - m);
+  for (int q = lo; q < hi; ++q)
+    if (!mk || !mk[q]) s += __expf(rho2 * r[q] - m);
   scores[k] = (m + logf(s)) / rho2;
 }
 
-// grel[i, c*T+t] = dscores[i,c] * softmax_t(rho2 rel)[t]  (0 for padding)
+// grel[i, row(c,t)] = dscores[i,c] * softmax_t(rho2 rel)[t]  (0 for padding); one thread per (i,c)
 __global__ void __launch_bounds__(256) word_scores_bwd_kernel(const float* __restrict__ rel, const uint8_t* __restrict__ mask,
+                                                               const int* __restrict__ cap_ptr,
                                                                const float* __restrict__ scores, const float* __restrict__ dscores,
-                                                               int Bi, int Bc, int T, float rho2, float* __restrict__ grel) {
-  const size_t n = (size_t)Bi * Bc * T;
-  for (size_t k = (size_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (size_t)gridDim.x * 256) {
-    const size_t ic = k / T;
-    const int t = (int)(k % T), c = (int)(ic % Bc);
-    const bool pad = mask && mask[(size_t)c * T + t];
-    grel[k] = pad ? 0.f : dscores[ic] * __expf(rho2 * (rel[k] - scores[ic]));
+                                                               int Bi, int Bc, int T, int NQs, float rho2, float* __restrict__ grel) {
+  const size_t k = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (k >= (size_t)Bi * Bc) return;
+  const int c = (int)(k % Bc);
+  const size_t i = k / Bc;
+  const int lo = cap_ptr ? cap_ptr[c] : c * T, hi = cap_ptr ? cap_ptr[c + 1] : c * T + T;
+  const uint8_t* mk = (mask && !cap_ptr) ? mask : nullptr;
+  const float sc = scores[k], ds = dscores[k];
+  for (int q = lo; q < hi; ++q) {
+    const bool pad = mk && mk[q];
+    grel[i * NQs + q] = pad ? 0.f : ds * __expf(rho2 * (rel[i * NQs + q] - sc));
   }
 }
 
 template <typename TI>
-static int launch_norm_tr(const void* x, int B, int D, int L, int Lpad, int out_dtype, void* xn, float* norm, cudaStream_t st) {
+static int launch_norm_tr(const void* x, int B, int D, int L, int Lpad, int out_dtype, const int* row_of, void* xn, float* norm, cudaStream_t st) {
   dim3 grid((Lpad + kLT - 1) / kLT, B);
   size_t smem = (size_t)D * (kLT + 1) * sizeof(float);
   if (out_dtype == XMC_F32)
-    norm_tr_kernel<TI, float><<<grid, 256, smem, st>>>(static_cast<const TI*>(x), D, L, Lpad, static_cast<float*>(xn), norm);
+    norm_tr_kernel<TI, float><<<grid, 256, smem, st>>>(static_cast<const TI*>(x), D, L, Lpad, row_of, static_cast<float*>(xn), norm);
   else
-    norm_tr_kernel<TI, __nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const TI*>(x), D, L, Lpad, static_cast<__nv_bfloat16*>(xn), norm);
+    norm_tr_kernel<TI, __nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const TI*>(x), D, L, Lpad, row_of, static_cast<__nv_bfloat16*>(xn), norm);
   return cuda_fail(cudaGetLastError(), "norm_tr_kernel launch");
 }
 
 template <typename TX>
 static int launch_norm_tr_bwd(const void* xn, const float* norm, const float* dxn, const float* dnorm, int B, int D, int L,
-                              int Lpad, int out_dtype, void* dx, cudaStream_t st) {
+                              int Lpad, int out_dtype, const int* row_of, void* dx, cudaStream_t st) {
   dim3 grid((L + kLT - 1) / kLT, B);
   size_t smem = (size_t)D * (kLT + 1) * sizeof(float);
   if (out_dtype == XMC_F32)
-    norm_tr_bwd_kernel<TX, float><<<grid, 256, smem, st>>>(static_cast<const TX*>(xn), norm, dxn, dnorm, D, L, Lpad, static_cast<float*>(dx));
+    norm_tr_bwd_kernel<TX, float><<<grid, 256, smem, st>>>(static_cast<const TX*>(xn), norm, dxn, dnorm, D, L, Lpad, row_of, static_cast<float*>(dx));
   else
-    norm_tr_bwd_kernel<TX, __nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const TX*>(xn), norm, dxn, dnorm, D, L, Lpad, static_cast<__nv_bfloat16*>(dx));
+    norm_tr_bwd_kernel<TX, __nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const TX*>(xn), norm, dxn, dnorm, D, L, Lpad, row_of, static_cast<__nv_bfloat16*>(dx));
   return cuda_fail(cudaGetLastError(), "norm_tr_bwd_kernel launch");
 }
 
@@ -148,40 +214,48 @@ static int check_nt(const void* a, const void* b, int B, int D, int L, int Lpad,
 
 using namespace xmc;
 
+extern "C" int xmc_word_rows_compact(const uint8_t* mask, int Bc, int T, int* row_of, int* cap_ptr, void* stream) {
+  XMC_REQUIRE(mask && row_of && cap_ptr, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(Bc > 0 && T > 0, XMC_ERR_INVALID_ARG, "bad shape Bc=%d T=%d", Bc, T);
+  word_rows_compact_kernel<<<1, 1024, 0, as_stream(stream)>>>(mask, Bc * T, T, row_of, cap_ptr);
+  return cuda_fail(cudaGetLastError(), "word_rows_compact_kernel launch");
+}
+
 extern "C" int xmc_normalize_transpose(const void* x, int B, int D, int L, int Lpad, int in_dtype,
-                                       int out_dtype, void* xn, float* norm, void* stream) {
+                                       int out_dtype, const int* row_of, void* xn, float* norm, void* stream) {
   if (int rc = check_nt(x, xn, B, D, L, Lpad, in_dtype, out_dtype)) return rc;
   XMC_REQUIRE(norm, XMC_ERR_INVALID_ARG, "null norm");
-  return in_dtype == XMC_F32 ? launch_norm_tr<float>(x, B, D, L, Lpad, out_dtype, xn, norm, as_stream(stream))
-                             : launch_norm_tr<__nv_bfloat16>(x, B, D, L, Lpad, out_dtype, xn, norm, as_stream(stream));
+  XMC_REQUIRE(!row_of || Lpad == L, XMC_ERR_INVALID_ARG, "row_of needs Lpad == L");
+  return in_dtype == XMC_F32 ? launch_norm_tr<float>(x, B, D, L, Lpad, out_dtype, row_of, xn, norm, as_stream(stream))
+                             : launch_norm_tr<__nv_bfloat16>(x, B, D, L, Lpad, out_dtype, row_of, xn, norm, as_stream(stream));
 }
 
 extern "C" int xmc_normalize_transpose_backward(const void* xn, const float* norm, const float* dxn,
                                                 const float* dnorm, int B, int D, int L, int Lpad,
-                                                int xn_dtype, int out_dtype, void* dx, void* stream) {
+                                                int xn_dtype, int out_dtype, const int* row_of, void* dx, void* stream) {
   if (int rc = check_nt(xn, dx, B, D, L, Lpad, xn_dtype, out_dtype)) return rc;
   XMC_REQUIRE(norm && dxn, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(!row_of || (Lpad == L && !dnorm), XMC_ERR_INVALID_ARG, "row_of needs Lpad == L and no dnorm");
   return xn_dtype == XMC_F32
-             ? launch_norm_tr_bwd<float>(xn, norm, dxn, dnorm, B, D, L, Lpad, out_dtype, dx, as_stream(stream))
-             : launch_norm_tr_bwd<__nv_bfloat16>(xn, norm, dxn, dnorm, B, D, L, Lpad, out_dtype, dx, as_stream(stream));
+             ? launch_norm_tr_bwd<float>(xn, norm, dxn, dnorm, B, D, L, Lpad, out_dtype, row_of, dx, as_stream(stream))
+             : launch_norm_tr_bwd<__nv_bfloat16>(xn, norm, dxn, dnorm, B, D, L, Lpad, out_dtype, row_of, dx, as_stream(stream));
 }
 
-extern "C" int xmc_word_scores(const float* rel, const uint8_t* mask, int Bi, int Bc, int T, float rho2,
-                               float* scores, void* stream) {
+extern "C" int xmc_word_scores(const float* rel, const uint8_t* mask, const int* cap_ptr, int Bi, int Bc, int T,
+                               int NQs, float rho2, float* scores, void* stream) {
   XMC_REQUIRE(rel && scores, XMC_ERR_INVALID_ARG, "null pointer");
-  XMC_REQUIRE(Bi > 0 && Bc > 0 && T > 0 && rho2 > 0.f, XMC_ERR_INVALID_ARG, "bad shape / rho2");
+  XMC_REQUIRE(Bi > 0 && Bc > 0 && T > 0 && NQs >= Bc && rho2 > 0.f, XMC_ERR_INVALID_ARG, "bad shape / rho2");
   size_t n = (size_t)Bi * Bc;
-  word_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(rel, mask, Bi, Bc, T, rho2, scores);
+  word_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(rel, mask, cap_ptr, Bi, Bc, T, NQs, rho2, scores);
   return cuda_fail(cudaGetLastError(), "word_scores_kernel launch");
 }
 
-extern "C" int xmc_word_scores_backward(const float* rel, const uint8_t* mask, const float* scores,
-                                        const float* dscores, int Bi, int Bc, int T, float rho2,
+extern "C" int xmc_word_scores_backward(const float* rel, const uint8_t* mask, const int* cap_ptr, const float* scores,
+                                        const float* dscores, int Bi, int Bc, int T, int NQs, float rho2,
                                         float* grel, void* stream) {
   XMC_REQUIRE(rel && scores && dscores && grel, XMC_ERR_INVALID_ARG, "null pointer");
-  XMC_REQUIRE(Bi > 0 && Bc > 0 && T > 0 && rho2 > 0.f, XMC_ERR_INVALID_ARG, "bad shape / rho2");
-  size_t n = (size_t)Bi * Bc * T;
-  size_t g = (n + 255) / 256; if (g > 148 * 16) g = 148 * 16;
-  word_scores_bwd_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(rel, mask, scores, dscores, Bi, Bc, T, rho2, grel);
+  XMC_REQUIRE(Bi > 0 && Bc > 0 && T > 0 && NQs >= Bc && rho2 > 0.f, XMC_ERR_INVALID_ARG, "bad shape / rho2");
+  size_t n = (size_t)Bi * Bc;
+  word_scores_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(rel, mask, cap_ptr, scores, dscores, Bi, Bc, T, NQs, rho2, grel);
   return cuda_fail(cudaGetLastError(), "word_scores_bwd_kernel launch");
 }

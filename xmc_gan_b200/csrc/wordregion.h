@@ -8,7 +8,8 @@ namespace xmc {
 // Operands are unit rows: qn[NQ,D], kn[Bi,Rpad,D]; storage fp32 (SIMT path) or bf16 (tcgen05 path).
 struct WrParams {
   const void* qn; const void* kn; const float* rnorm;
-  int NQ, Bi, R, Rpad;
+  int NQ, Bi, R, Rpad;                     // NQ: rows allocated (row stride of lsum / cnorm / rel / chat)
+  const int* nq_dev;                       // device count of valid word rows (compacted captions), nullable: all NQ
   float rho1;
   float* lsum; float* cnorm; float* rel;   // forward outputs / backward inputs, [Bi, NQ]
   void* chat;                              // [Bi, NQ, D] bf16 context sums C = l c_t (tcgen05 path), nullable

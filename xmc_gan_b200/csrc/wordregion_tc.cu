@@ -18,6 +18,7 @@
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
 // allocator, warps 4-7 = softmax/epilogue warpgroup (thread = TMEM lane = word row).
 // TMEM map (512 columns): C [0,D) | Q [D, D+D/2) | S0 | S1 (64 columns each, P' aliases S).
+#include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
@@ -31,6 +32,31 @@ using namespace tc;
 constexpr int TM = 128;            // word rows per tile (UMMA M)
 constexpr int CH = 64;             // region rows per chunk
 constexpr float kLog2eTc = 1.4426950408889634f;
+
+// Persistent schedule shared by both kernels.  Work items are (word tile, image) pairs, tile-major; the
+// grid is one CTA per SM and CTA k owns the contiguous span [k*per, (k+1)*per) of items.  A span is
+// walked as SEGMENTS = runs of images of one word tile (the stationary operand changes between
+// segments).  The number of word rows is read from device memory (compacted captions: the host does
+// not know it), so the span is computed in the kernel.
+struct Seg { int tile, img0, nimg; };
+struct SegIter {
+  int item, end, Bi;
+  __device__ __forceinline__ bool next(Seg& s) {
+    if (item >= end) return false;
+    s.tile = item / Bi;
+    s.img0 = item - s.tile * Bi;
+    s.nimg = min(Bi - s.img0, end - item);
+    item += s.nimg;
+    return true;
+  }
+};
+__device__ __forceinline__ SegIter seg_iter(int NQ, int Bi) {
+  const int W = ((NQ + TM - 1) / TM) * Bi;
+  const int per = (W + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int b = min(W, (int)blockIdx.x * per);
+  return SegIter{b, min(W, b + per), Bi};
+}
+__device__ __forceinline__ int device_rows(const int* nq_dev, int NQ) { return nq_dev ? min(NQ, __ldg(nq_dev)) : NQ; }
 
 constexpr int kFwdThreads = 512;     // 4 role warps + 2 softmax warpgroups + 1 epilogue warpgroup
 
@@ -58,7 +84,7 @@ struct TcFwdParams {
   float rho1;
   float* lsum; float* cnorm; float* rel;
   int save_ctx;                // context sums C = l * c_t go out through tm_ctx (bf16 [Bi, NQ, D]) for the backward
-  int imgs_per_cta;
+  const int* nq_dev;           // device count of valid word rows (<= NQ, the row stride of every buffer) or null
   int* err;
   float* dbg;                  // optional: S chunk 0 and C of the first tile/image (tests)
   long long* trace;            // perf experiments only (flag 4): clock64 timeline of CTA (0,0), [4 roles][64][4]
@@ -66,7 +92,7 @@ struct TcFwdParams {
 
 #define XMC_TRACE(role, g, k)                                                             \
   do {                                                                                   \
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (g) < 64)                      \
+    if (p.trace && blockIdx.x == 0 && (g) < 64)                      \
       p.trace[((role) * 64 + (g)) * 4 + (k)] = clock64();                               \
   } while (0)
 
@@ -108,12 +134,8 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
   const WaitCtx wc{abort_flag, p.err};
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TM;
-  const int img0 = blockIdx.y * p.imgs_per_cta;
-  const int img1 = min(p.Bi, img0 + p.imgs_per_cta);
-  const int nimg = img1 - img0;
+  const int NQ = device_rows(p.nq_dev, p.NQ);
   const int nch = (p.Rpad + CH - 1) / CH;
-  const int G = nimg * nch;
   const bool has_rn = p.rnorm != nullptr;
 
   if (threadIdx.x == 0) {
@@ -137,22 +159,28 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
   if (threadIdx.x == 0 && *tmem_slot != 0) { *abort_flag = 1; if (p.err) atomicExch(p.err, 999); }
   __syncthreads();
 
-  if (G > 0) {
+  {
     if (warp == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer: region chunks of every (segment, image), one continuous ring =====
       if (elect_one()) {
-        int st = 0, ph = 1, c = 0, img = img0;       // ph: parity to wait on kv_empty (first pass free)
-        for (int g = 0; g < G; ++g) {
-          const int n = min(CH, p.Rpad - c * CH);
-          mbar_wait(kv_empty + st, ph, wc, 1);
-          mbar_expect_tx(kv_full + st, Cfg::kStageBytes + (has_rn ? n * 4 : 0));
-          uint8_t* dst = kv + st * Cfg::kStageBytes;
+        int st = 0, ph = 1;                          // ph: parity to wait on kv_empty (first pass free)
+        SegIter it = seg_iter(NQ, p.Bi);
+        Seg sg;
+        while (it.next(sg)) {
+          for (int ii = 0; ii < sg.nimg; ++ii) {
+            const int img = sg.img0 + ii;
+            for (int c = 0; c < nch; ++c) {
+              const int n = min(CH, p.Rpad - c * CH);
+              mbar_wait(kv_empty + st, ph, wc, 1);
+              mbar_expect_tx(kv_full + st, Cfg::kStageBytes + (has_rn ? n * 4 : 0));
+              uint8_t* dst = kv + st * Cfg::kStageBytes;
 #pragma unroll
-          for (int kb = 0; kb < D / 64; ++kb)
-            tma_load_3d(dst + kb * Cfg::kBlockBytes, &tm_k, kb * 64, c * CH, img, kv_full + st);
-          if (has_rn) bulk_load_1d(rn_s + st * CH, p.rnorm + (size_t)img * p.Rpad + c * CH, n * 4, kv_full + st);
-          if (++st == Cfg::kStages) { st = 0; ph ^= 1; }
-          if (++c == nch) { c = 0; ++img; }
+              for (int kb = 0; kb < D / 64; ++kb)
+                tma_load_3d(dst + kb * Cfg::kBlockBytes, &tm_k, kb * 64, c * CH, img, kv_full + st);
+              if (has_rn) bulk_load_1d(rn_s + st * CH, p.rnorm + (size_t)img * p.Rpad + c * CH, n * 4, kv_full + st);
+              if (++st == Cfg::kStages) { st = 0; ph ^= 1; }
+            }
+          }
         }
       }
       __syncwarp();
@@ -172,57 +200,63 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
           for (int k = 0; k < D / 16; ++k)
             mma_ts(d_tmem, tmem + Cfg::kColQ + k * 8, base + (((k >> 2) * Cfg::kBlockBytes + (k & 3) * 32) >> 4), idesc1, k > 0);
         };
-        // Issue order on the (in-order) tensor pipe: G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ...
+        // Issue order on the (in-order) tensor pipe, per segment: G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ...
         // One exposed synchronisation point per chunk: P(g) written (and, at the first chunk of an image,
         // the previous image's C drained); region chunk g+2 has normally landed long before.
-        mbar_wait(q_ready, 0, wc, 2);
-        mbar_wait(kv_full + 0, 0, wc, 3);
-        tc_fence_after();
-        issue_g1(0, min(CH, p.Rpad), 0);
-        mma_commit(s_full + 0);
-        // chunk g: stage st, chunk-in-image c, image ii.  chunk g+2: stage st2 (parity ph2), chunk-in-image c2
-        int st = 0, c = 0, ii = 0;
-        int st2 = 0, ph2 = 0, c2 = 0;
-        auto advance2 = [&]() {
-          if (++st2 == Cfg::kStages) { st2 = 0; ph2 ^= 1; }
-          if (++c2 == nch) c2 = 0;
-        };
-        advance2();
-        if (G > 1) {
-          mbar_wait(kv_full + st2, ph2, wc, 4);
+        // Running counters (never reset): x = chunks issued so far (S/P buffer = x & 1, their barrier
+        // parity = (x >> 1) & 1), ic = images finished (parity of c_full / c_empty), stage ring (st, st2, ph2).
+        int x = 0, ic = 0, seg = 0;
+        int st = 0;                                  // stage of chunk g
+        int st2 = 0, ph2 = 0;                        // stage / kv_full parity of the chunk G1 is issued for next
+        auto advance2 = [&]() { if (++st2 == Cfg::kStages) { st2 = 0; ph2 ^= 1; } };
+        SegIter it = seg_iter(NQ, p.Bi);
+        Seg sg;
+        while (it.next(sg)) {
+          const int G = sg.nimg * nch;
+          mbar_wait(q_ready, seg & 1, wc, 2);
+          int c2 = 0;                                // chunk-in-image of the chunk G1 is issued for next
+          mbar_wait(kv_full + st2, ph2, wc, 3);
           tc_fence_after();
-          issue_g1(st2, min(CH, p.Rpad - c2 * CH), 1);
-          mma_commit(s_full + 1);
-        }
-        advance2();
-        for (int g = 0; g < G; ++g) {
-          const int sb = g & 1;
-          mbar_wait(p_full + sb, (g >> 1) & 1, wc, 5);
-          if (c == 0 && ii > 0) mbar_wait(c_empty, (ii - 1) & 1, wc, 6);
-          tc_fence_after();
-          XMC_TRACE(0, g, 0);
-          const int n = min(CH, p.Rpad - c * CH);
-          const Desc vbase = vdesc0 + ((uint32_t)(st * Cfg::kStageBytes) >> 4);
-          const uint32_t a_tmem = tmem + (sb ? Cfg::kColS1 : Cfg::kColS0);
-          // P' of region cols [0,32) sits at S cols [0,16), of [32,64) at S cols [32,48)
-#pragma unroll
-          for (int ks = 0; ks < CH / 16; ++ks)
-            if (ks * 16 < n)
-              mma_ts(tmem + Cfg::kColC, a_tmem + (ks >> 1) * 32 + (ks & 1) * 8, vbase + ((ks * 2048) >> 4), idesc2, (c > 0) || (ks > 0));
-          mma_commit(kv_empty + st);
-          if (c == nch - 1) mma_commit(c_full);
-          XMC_TRACE(0, g, 1);
-          if (g + 2 < G) {
-            mbar_wait(kv_full + st2, ph2, wc, 4);               // its latency hides behind G2(g) on the pipe
+          issue_g1(st2, min(CH, p.Rpad), x & 1);
+          mma_commit(s_full + (x & 1));
+          advance2(); if (++c2 == nch) c2 = 0;
+          if (G > 1) {
+            mbar_wait(kv_full + st2, ph2, wc, 4);
             tc_fence_after();
-            issue_g1(st2, min(CH, p.Rpad - c2 * CH), sb);       // overwrites P(g) after G2(g): same pipe, in order
-            mma_commit(s_full + sb);
+            issue_g1(st2, min(CH, p.Rpad - c2 * CH), (x + 1) & 1);
+            mma_commit(s_full + ((x + 1) & 1));
+            advance2(); if (++c2 == nch) c2 = 0;
           }
-          XMC_TRACE(0, g, 2);
-          // advance
-          if (++st == Cfg::kStages) st = 0;
-          if (++c == nch) { c = 0; ++ii; }
-          advance2();
+          int c = 0;
+          for (int g = 0; g < G; ++g, ++x) {
+            const int sb = x & 1;
+            mbar_wait(p_full + sb, (x >> 1) & 1, wc, 5);
+            if (c == 0 && ic > 0) mbar_wait(c_empty, (ic - 1) & 1, wc, 6);
+            tc_fence_after();
+            XMC_TRACE(0, x, 0);
+            const int n = min(CH, p.Rpad - c * CH);
+            const Desc vbase = vdesc0 + ((uint32_t)(st * Cfg::kStageBytes) >> 4);
+            const uint32_t a_tmem = tmem + (sb ? Cfg::kColS1 : Cfg::kColS0);
+            // P' of region cols [0,32) sits at S cols [0,16), of [32,64) at S cols [32,48)
+#pragma unroll
+            for (int ks = 0; ks < CH / 16; ++ks)
+              if (ks * 16 < n)
+                mma_ts(tmem + Cfg::kColC, a_tmem + (ks >> 1) * 32 + (ks & 1) * 8, vbase + ((ks * 2048) >> 4), idesc2, (c > 0) || (ks > 0));
+            mma_commit(kv_empty + st);
+            if (c == nch - 1) mma_commit(c_full);
+            XMC_TRACE(0, x, 1);
+            if (g + 2 < G) {
+              mbar_wait(kv_full + st2, ph2, wc, 4);               // its latency hides behind G2(g) on the pipe
+              tc_fence_after();
+              issue_g1(st2, min(CH, p.Rpad - c2 * CH), sb);       // overwrites P(g) after G2(g): same pipe, in order
+              mma_commit(s_full + sb);
+              advance2(); if (++c2 == nch) c2 = 0;
+            }
+            XMC_TRACE(0, x, 2);
+            if (++st == Cfg::kStages) st = 0;
+            if (++c == nch) { c = 0; ++ic; }
+          }
+          ++seg;
         }
       }
       __syncwarp();
@@ -231,184 +265,195 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
       const int h = (warp - 4) >> 2;
       const int q = warp & 3;
       const int row = q * 32 + lane;
-      const int grow = m0 + row;
       const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
-      // Q row -> TMEM (A operand: 32-bit column c holds bf16 elements 2c, 2c+1); each WG writes half of D
-      {
-        const uint4* src = reinterpret_cast<const uint4*>(p.qn + (size_t)grow * D);
-#pragma unroll
-        for (int b = 0; b < D / 64; ++b) {                 // 32 bf16 = 16 columns per store
-          const int blk = h * (D / 64) + b;
-          uint32_t v[16];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 w = (grow < p.NQ) ? __ldg(src + blk * 4 + u) : make_uint4(0, 0, 0, 0);
-            v[4 * u + 0] = w.x; v[4 * u + 1] = w.y; v[4 * u + 2] = w.z; v[4 * u + 3] = w.w;
-          }
-          tmem_st16(lane_base + Cfg::kColQ + blk * 16, v);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(q_ready);
-      }
       const float c1 = p.rho1 * kLog2eTc;
       const int col0 = h * 32;
-      int st = 0, g = 0;
-      for (int ii = 0; ii < nimg; ++ii) {
-        float l = 0.f, a = 0.f;
-        for (int c = 0; c < nch; ++c, ++g) {
-          const int n = min(CH, p.Rpad - c * CH);
-          const uint32_t s_col = (g & 1) ? Cfg::kColS1 : Cfg::kColS0;
-          mbar_wait(s_full + (g & 1), (g >> 1) & 1, wc, 7);
-          tc_fence_after();
-          if (threadIdx.x == 128) XMC_TRACE(1, g, 0);
-          if (col0 < n) {
-            uint32_t sv[32];
-            tmem_ld32(lane_base + s_col + col0, sv);
-            tmem_wait_ld();
-            if (threadIdx.x == 128) XMC_TRACE(1, g, 1);
-            if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && g == 0) {
+      int st = 0, x = 0, ic = 0;                     // running: rn_s stage, chunk count, image count
+      SegIter it = seg_iter(NQ, p.Bi);
+      Seg sg;
+      while (it.next(sg)) {
+        const int grow = sg.tile * TM + row;
+        // Q row -> TMEM (A operand: 32-bit column c holds bf16 elements 2c, 2c+1); each WG writes half of D.
+        // Every G1 of the previous segment has completed (this thread consumed its S), so Q may be replaced.
+        {
+          const uint4* src = reinterpret_cast<const uint4*>(p.qn + (size_t)grow * D);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) p.dbg[row * CH + col0 + j] = __uint_as_float(sv[j]);
+          for (int b = 0; b < D / 64; ++b) {                 // 32 bf16 = 16 columns per store
+            const int blk = h * (D / 64) + b;
+            uint32_t v[16];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4 w = (grow < NQ) ? __ldg(src + blk * 4 + u) : make_uint4(0, 0, 0, 0);
+              v[4 * u + 0] = w.x; v[4 * u + 1] = w.y; v[4 * u + 2] = w.z; v[4 * u + 3] = w.w;
             }
-            uint32_t pk[16];
-            const int r0 = c * CH + col0;
-            const float* wsm = rn_s + st * CH + col0;
-            // phase 1: all exponentials back to back (packed fp32x2 FMAs feed the MUFU)
-            float pv[32];
-            {
-              const float2 cc = make_float2(c1, c1), ncc = make_float2(-c1, -c1);
-#pragma unroll
-              for (int j2 = 0; j2 < 16; ++j2) {
-                const float2 arg = __ffma2_rn(make_float2(__uint_as_float(sv[2 * j2]), __uint_as_float(sv[2 * j2 + 1])), cc, ncc);
-                pv[2 * j2] = ex2_approx(arg.x);
-                pv[2 * j2 + 1] = ex2_approx(arg.y);
-              }
-            }
-            if (r0 + 32 > p.R) {                            // ragged tail of the image: padded columns weigh 0
-#pragma unroll
-              for (int j = 0; j < 32; ++j) pv[j] = (r0 + j) < p.R ? pv[j] : 0.f;
-            }
-            if (threadIdx.x == 128) XMC_TRACE(3, g, 0);
-            // phase 2: l += p, p' = p * ||v_r||, a += p' s, pack (packed fp32x2, two chains each)
-            float2 l2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-            float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + j4 * 4);   // rows past Rpad of the chunk: pv = 0
-              const float2 mr2[2] = {make_float2(mr.x, mr.y), make_float2(mr.z, mr.w)};
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int j = j4 * 4 + 2 * u;
-                const float2 p2 = make_float2(pv[j], pv[j + 1]);
-                const float2 s2 = make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
-                l2[u] = __fadd2_rn(l2[u], p2);
-                const float2 pw = has_rn ? __fmul2_rn(p2, mr2[u]) : p2;
-                a2[u] = __ffma2_rn(pw, s2, a2[u]);
-                pk[j4 * 2 + u] = pack_bf16(pw.x, pw.y);
-              }
-            }
-            l += (l2[0].x + l2[0].y) + (l2[1].x + l2[1].y);
-            a += (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
-            if (threadIdx.x == 128) XMC_TRACE(3, g, 1);
-            tmem_st16(lane_base + s_col + col0, pk);        // WG0 -> S cols [0,16), WG1 -> [32,48)
-            tmem_wait_st();
+            tmem_st16(lane_base + Cfg::kColQ + blk * 16, v);
           }
-          if (threadIdx.x == 128) XMC_TRACE(1, g, 2);
+          tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(p_full + (g & 1));
-          if (threadIdx.x == 128) XMC_TRACE(1, g, 3);
-          if (++st == Cfg::kStages) st = 0;
+          mbar_arrive(q_ready);
         }
-        // hand this warpgroup's partial l, a of the image to the epilogue warpgroup
-        mbar_wait(la_empty + (ii & 1), ((ii >> 1) & 1) ^ 1, wc, 9);
-        float* ex = ex_s + (ii & 1) * (2 * 2 * TM);
-        ex[(h * 2 + 0) * TM + row] = l;
-        ex[(h * 2 + 1) * TM + row] = a;
-        mbar_arrive(la_full + (ii & 1));                    // release semantics: the stores above are visible
+        for (int ii = 0; ii < sg.nimg; ++ii, ++ic) {
+          float l = 0.f, a = 0.f;
+          for (int c = 0; c < nch; ++c, ++x) {
+            const int n = min(CH, p.Rpad - c * CH);
+            const uint32_t s_col = (x & 1) ? Cfg::kColS1 : Cfg::kColS0;
+            mbar_wait(s_full + (x & 1), (x >> 1) & 1, wc, 7);
+            tc_fence_after();
+            if (threadIdx.x == 128) XMC_TRACE(1, x, 0);
+            if (col0 < n) {
+              uint32_t sv[32];
+              tmem_ld32(lane_base + s_col + col0, sv);
+              tmem_wait_ld();
+              if (threadIdx.x == 128) XMC_TRACE(1, x, 1);
+              if (p.dbg && blockIdx.x == 0 && x == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) p.dbg[row * CH + col0 + j] = __uint_as_float(sv[j]);
+              }
+              uint32_t pk[16];
+              const int r0 = c * CH + col0;
+              const float* wsm = rn_s + st * CH + col0;
+              // phase 1: all exponentials back to back (packed fp32x2 FMAs feed the MUFU)
+              float pv[32];
+              {
+                const float2 cc = make_float2(c1, c1), ncc = make_float2(-c1, -c1);
+#pragma unroll
+                for (int j2 = 0; j2 < 16; ++j2) {
+                  const float2 arg = __ffma2_rn(make_float2(__uint_as_float(sv[2 * j2]), __uint_as_float(sv[2 * j2 + 1])), cc, ncc);
+                  pv[2 * j2] = ex2_approx(arg.x);
+                  pv[2 * j2 + 1] = ex2_approx(arg.y);
+                }
+              }
+              if (r0 + 32 > p.R) {                            // ragged tail of the image: padded columns weigh 0
+#pragma unroll
+                for (int j = 0; j < 32; ++j) pv[j] = (r0 + j) < p.R ? pv[j] : 0.f;
+              }
+              if (threadIdx.x == 128) XMC_TRACE(3, x, 0);
+              // phase 2: l += p, p' = p * ||v_r||, a += p' s, pack (packed fp32x2, two chains each)
+              float2 l2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+              float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + j4 * 4);   // rows past Rpad of the chunk: pv = 0
+                const float2 mr2[2] = {make_float2(mr.x, mr.y), make_float2(mr.z, mr.w)};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int j = j4 * 4 + 2 * u;
+                  const float2 p2 = make_float2(pv[j], pv[j + 1]);
+                  const float2 s2 = make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
+                  l2[u] = __fadd2_rn(l2[u], p2);
+                  const float2 pw = has_rn ? __fmul2_rn(p2, mr2[u]) : p2;
+                  a2[u] = __ffma2_rn(pw, s2, a2[u]);
+                  pk[j4 * 2 + u] = pack_bf16(pw.x, pw.y);
+                }
+              }
+              l += (l2[0].x + l2[0].y) + (l2[1].x + l2[1].y);
+              a += (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
+              if (threadIdx.x == 128) XMC_TRACE(3, x, 1);
+              tmem_st16(lane_base + s_col + col0, pk);        // WG0 -> S cols [0,16), WG1 -> [32,48)
+              tmem_wait_st();
+            }
+            if (threadIdx.x == 128) XMC_TRACE(1, x, 2);
+            tc_fence_before();
+            mbar_arrive(p_full + (x & 1));
+            if (threadIdx.x == 128) XMC_TRACE(1, x, 3);
+            if (++st == Cfg::kStages) st = 0;
+          }
+          // hand this warpgroup's partial l, a of the image to the epilogue warpgroup
+          mbar_wait(la_empty + (ic & 1), ((ic >> 1) & 1) ^ 1, wc, 9);
+          float* ex = ex_s + (ic & 1) * (2 * 2 * TM);
+          ex[(h * 2 + 0) * TM + row] = l;
+          ex[(h * 2 + 1) * TM + row] = a;
+          mbar_arrive(la_full + (ic & 1));                    // release semantics: the stores above are visible
+        }
       }
     } else if (warp >= 12) {
       // ===== epilogue warpgroup: thread = TMEM lane = word row.  One pass over C per image:
       //       ||C|| -> statistics;  bf16 C -> swizzled smem boxes -> TMA store (saved for the backward)
       const int q = warp & 3;
       const int row = q * 32 + lane;
-      const int grow = m0 + row;
       const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
       const bool issuer = (threadIdx.x == 384);
-      for (int ii = 0; ii < nimg; ++ii) {
-        const int img = img0 + ii;
-        mbar_wait(la_full + (ii & 1), (ii >> 1) & 1, wc, 10);
-        const float* ex = ex_s + (ii & 1) * (2 * 2 * TM);
-        const float l = ex[0 * TM + row] + ex[2 * TM + row];
-        const float a = ex[1 * TM + row] + ex[3 * TM + row];
-        mbar_arrive(la_empty + (ii & 1));
-        const float inv_l = 1.f / l;
-        if (p.save_ctx) {
-          if (issuer) bulk_wait_read<0>();                  // the previous image's stores have read the boxes
-          named_bar_sync(2, 128);
-        }
-        mbar_wait(c_full, ii & 1, wc, 8);
-        tc_fence_after();
-        if (issuer) XMC_TRACE(2, ii, 0);
-        float2 c2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        uint32_t cva[32], cvb[32];
-        // 32 columns -> square-sum (packed fp32x2), bf16 -> four 16-byte units of the row's 128-byte box line.
-        // The saved tile is the UNSCALED sum C = l * c; the backward folds 1/(l ||c||) into its coefficients.
-        auto consume = [&](const uint32_t (&cv)[32], int blk32) {
-          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ii == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) p.dbg[TM * CH + row * D + blk32 * 32 + j] = __uint_as_float(cv[j]);
+      int ic = 0;
+      SegIter it = seg_iter(NQ, p.Bi);
+      Seg sg;
+      while (it.next(sg)) {
+        const int m0 = sg.tile * TM;
+        const int grow = m0 + row;
+        for (int ii = 0; ii < sg.nimg; ++ii, ++ic) {
+          const int img = sg.img0 + ii;
+          mbar_wait(la_full + (ic & 1), (ic >> 1) & 1, wc, 10);
+          const float* ex = ex_s + (ic & 1) * (2 * 2 * TM);
+          const float l = ex[0 * TM + row] + ex[2 * TM + row];
+          const float a = ex[1 * TM + row] + ex[3 * TM + row];
+          mbar_arrive(la_empty + (ic & 1));
+          const float inv_l = 1.f / l;
+          if (p.save_ctx) {
+            if (issuer) bulk_wait_read<0>();                  // the previous image's stores have read the boxes
+            named_bar_sync(2, 128);
           }
-          uint8_t* line = out_s + (blk32 >> 1) * Cfg::kOutBytes + row * 128;
+          mbar_wait(c_full, ic & 1, wc, 8);
+          tc_fence_after();
+          if (issuer) XMC_TRACE(2, ic, 0);
+          float2 c2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+          uint32_t cva[32], cvb[32];
+          // 32 columns -> square-sum (packed fp32x2), bf16 -> four 16-byte units of the row's 128-byte box line.
+          // The saved tile is the UNSCALED sum C = l * c; the backward folds 1/(l ||c||) into its coefficients.
+          auto consume = [&](const uint32_t (&cv)[32], int blk32) {
+            if (p.dbg && blockIdx.x == 0 && ic == 0) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {                     // 8 bf16 = one 16-byte unit
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 v = make_float2(__uint_as_float(cv[8 * u + 2 * e]), __uint_as_float(cv[8 * u + 2 * e + 1]));
-              c2[e & 1] = __ffma2_rn(v, v, c2[e & 1]);
-              w[e] = pack_bf16(v.x, v.y);
+              for (int j = 0; j < 32; ++j) p.dbg[TM * CH + row * D + blk32 * 32 + j] = __uint_as_float(cv[j]);
             }
-            if (p.save_ctx)
-              *reinterpret_cast<uint4*>(line + ((((blk32 & 1) * 4 + u) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        };
-        tmem_ld32(lane_base + Cfg::kColC, cva);
-#pragma unroll 1
-        for (int b2 = 0; b2 < D / 64; ++b2) {               // two 32-column loads in flight / being consumed
-          tmem_wait_ld();
-          tmem_ld32(lane_base + Cfg::kColC + b2 * 64 + 32, cvb);
-          consume(cva, 2 * b2);
-          tmem_wait_ld();
-          if (b2 + 1 < D / 64) {
-            tmem_ld32(lane_base + Cfg::kColC + b2 * 64 + 64, cva);
-          } else {                                          // C is in registers: the next image may overwrite it
-            tc_fence_before();
-            mbar_arrive(c_empty);
-            if (issuer) XMC_TRACE(2, ii, 1);
-          }
-          consume(cvb, 2 * b2 + 1);
-        }
-        if (p.save_ctx) {
-          fence_proxy_async_smem();
-          named_bar_sync(2, 128);
-          if (issuer) {
+            uint8_t* line = out_s + (blk32 >> 1) * Cfg::kOutBytes + row * 128;
 #pragma unroll
-            for (int b = 0; b < Cfg::kOutBoxes; ++b) tma_store_3d(&tm_ctx, out_s + b * Cfg::kOutBytes, b * 64, m0, img);
-            bulk_commit();
+            for (int u = 0; u < 4; ++u) {                     // 8 bf16 = one 16-byte unit
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 v = make_float2(__uint_as_float(cv[8 * u + 2 * e]), __uint_as_float(cv[8 * u + 2 * e + 1]));
+                c2[e & 1] = __ffma2_rn(v, v, c2[e & 1]);
+                w[e] = pack_bf16(v.x, v.y);
+              }
+              if (p.save_ctx)
+                *reinterpret_cast<uint4*>(line + ((((blk32 & 1) * 4 + u) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          };
+          tmem_ld32(lane_base + Cfg::kColC, cva);
+#pragma unroll 1
+          for (int b2 = 0; b2 < D / 64; ++b2) {               // two 32-column loads in flight / being consumed
+            tmem_wait_ld();
+            tmem_ld32(lane_base + Cfg::kColC + b2 * 64 + 32, cvb);
+            consume(cva, 2 * b2);
+            tmem_wait_ld();
+            if (b2 + 1 < D / 64) {
+              tmem_ld32(lane_base + Cfg::kColC + b2 * 64 + 64, cva);
+            } else {                                          // C is in registers: the next image may overwrite it
+              tc_fence_before();
+              mbar_arrive(c_empty);
+              if (issuer) XMC_TRACE(2, ic, 1);
+            }
+            consume(cvb, 2 * b2 + 1);
           }
-        }
-        if (issuer) XMC_TRACE(2, ii, 3);
-        if (grow < p.NQ) {
-          const float cn = sqrtf((c2[0].x + c2[0].y) + (c2[1].x + c2[1].y)) * inv_l;
-          const size_t o2 = (size_t)img * p.NQ + grow;
-          p.lsum[o2] = l;
-          p.cnorm[o2] = cn;
-          p.rel[o2] = (a * inv_l) / fmaxf(cn, kEps);
+          if (p.save_ctx) {
+            fence_proxy_async_smem();
+            named_bar_sync(2, 128);
+            if (issuer) {
+#pragma unroll
+              for (int b = 0; b < Cfg::kOutBoxes; ++b) tma_store_3d(&tm_ctx, out_s + b * Cfg::kOutBytes, b * 64, m0, img);
+              bulk_commit();
+            }
+          }
+          if (issuer) XMC_TRACE(2, ic, 3);
+          if (grow < NQ) {
+            const float cn = sqrtf((c2[0].x + c2[0].y) + (c2[1].x + c2[1].y)) * inv_l;
+            const size_t o2 = (size_t)img * p.NQ + grow;
+            p.lsum[o2] = l;
+            p.cnorm[o2] = cn;
+            p.rel[o2] = (a * inv_l) / fmaxf(cn, kEps);
+          }
         }
       }
-      if (issuer) bulk_wait<0>();                           // all context stores performed before exit
+      if (issuer) bulk_wait<0>();                             // all context stores performed before exit
     }
   }
   tc_fence_before();
@@ -488,14 +533,11 @@ static int launch_fwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
   p.dbg = ((g_debug_dump & 1) && ws_bytes >= 64 + sizeof(float) * (size_t)(TM * CH + TM * D))
               ? reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
   p.trace = ((g_debug_dump & 4) && ws_bytes >= 64 + 4 * 64 * 4 * 8) ? reinterpret_cast<long long*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
-  const int tiles = (w.NQ + TM - 1) / TM;
-  int splits = num_sms() / tiles;
-  if (splits < 1) splits = 1;
-  if (splits > w.Bi) splits = w.Bi;
-  p.imgs_per_cta = (w.Bi + splits - 1) / splits;
-  splits = (w.Bi + p.imgs_per_cta - 1) / p.imgs_per_cta;
+  p.nq_dev = w.nq_dev;
+  const long long items = (long long)((w.NQ + TM - 1) / TM) * w.Bi;      // upper bound (all rows valid)
+  const int grid = (int)std::min<long long>(num_sms(), items);
   XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  wr_fwd_tc_kernel<D><<<dim3(tiles, splits), kFwdThreads, Cfg::kSmemBytes, st>>>(tm, tctx, p);
+  wr_fwd_tc_kernel<D><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(tm, tctx, p);
   return cuda_fail(cudaGetLastError(), "wr_fwd_tc_kernel launch");
 }
 
@@ -566,7 +608,7 @@ struct TcBwdParams {
   float rho1;
   const float* lsum; const float* cnorm; const float* rel; const float* grel;
   float* dqn; float* dkn; float* drnorm;
-  int imgs_per_cta;
+  const int* nq_dev;           // device count of valid word rows (<= NQ) or null
   int* err;
   int dbg_flags;               // perf experiments only (xmc_internal_set_debug_dump): 2 = skip the dK reduce
   long long* trace;            // perf experiments only (flag 4): clock64 timeline of CTA (0,0), [4 roles][64 chunks][4]
@@ -618,17 +660,15 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint64_t* xy_full = bars + 9;
   uint64_t* dk_full = bars + 10;
   uint64_t* dk_empty = bars + 11;
-  uint64_t* dq_full = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* dq_full = bars + 12;   // per segment: every MMA of the segment has executed
+  uint64_t* dq_empty = bars + 13;  // per segment: dQ has been read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   int* abort_flag = reinterpret_cast<int*>(tmem_slot + 1);
   const WaitCtx wc{abort_flag, p.err};
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TM;
-  const int img0 = blockIdx.y * p.imgs_per_cta;
-  const int nimg = min(p.Bi, img0 + p.imgs_per_cta) - img0;
+  const int NQ = device_rows(p.nq_dev, p.NQ);
   const int nch = (p.Rpad + CH - 1) / CH;
-  const int G = nimg * nch;
   const bool has_rn = p.rnorm != nullptr;
 
   if (threadIdx.x == 0) {
@@ -636,7 +676,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     mbar_init(q_full, 1); mbar_init(ch_full, 1); mbar_init(ch_empty, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
     mbar_init(sw_full, 1); mbar_init(sw_consumed, 256); mbar_init(xy_full, 256);
-    mbar_init(dk_full, 1); mbar_init(dk_empty, 128); mbar_init(dq_full, 1);
+    mbar_init(dk_full, 1); mbar_init(dk_empty, 128); mbar_init(dq_full, 1); mbar_init(dq_empty, 256);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -650,44 +690,57 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (threadIdx.x == 0 && *tmem_slot != 0) { *abort_flag = 1; if (p.err) atomicExch(p.err, 999); }
   __syncthreads();
 
+  // Running counters used by every role (never reset across segments): x = chunk index (region stage
+  // x & 1 with parity (x >> 1) & 1; parity x & 1 of the per-chunk barriers), ic = image index (parity
+  // of ch_full / ch_empty), seg = segment index (parity of q_full / dq_full / dq_empty).
+  //
   // setmaxnreg sits at the top of each role's branch so that it dominates the role's code (ptxas
   // allocates registers per region only then)
   if (warp < 4) {
     setmaxnreg_dec<kBwdRegsRole>();
-    if (G > 0 && warp == 0) {
+    if (warp == 0) {
       // ===== TMA producer =====
       if (elect_one()) {
-        mbar_expect_tx(q_full, Cfg::kQBytes);
+        int x = 0, ic = 0, seg = 0;
+        SegIter it = seg_iter(NQ, p.Bi);
+        Seg sg;
+        while (it.next(sg)) {
+          const int m0 = sg.tile * TM;
+          if (seg > 0) mbar_wait(dq_full, (seg - 1) & 1, wc, 10);   // no MMA reads the old word tile any more
+          mbar_expect_tx(q_full, Cfg::kQBytes);
 #pragma unroll
-        for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(Qs + kb * Cfg::kQBlock, &tm_q, kb * 64, m0, q_full);
-        int c = 0, ii = 0;
-        for (int g = 0; g < G; ++g) {
-          const int st = g & 1;
-          const int n = min(CH, p.Rpad - c * CH);
-          mbar_wait(kv_empty + st, ((g >> 1) & 1) ^ 1, wc, 11);
-          mbar_expect_tx(kv_full + st, Cfg::kKvStage + (has_rn ? n * 4 : 0));
+          for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(Qs + kb * Cfg::kQBlock, &tm_q, kb * 64, m0, q_full);
+          for (int ii = 0; ii < sg.nimg; ++ii, ++ic) {
+            const int img = sg.img0 + ii;
+            for (int c = 0; c < nch; ++c, ++x) {
+              const int st = x & 1;
+              const int n = min(CH, p.Rpad - c * CH);
+              mbar_wait(kv_empty + st, ((x >> 1) & 1) ^ 1, wc, 11);
+              mbar_expect_tx(kv_full + st, Cfg::kKvStage + (has_rn ? n * 4 : 0));
 #pragma unroll
-          for (int kb = 0; kb < D / 64; ++kb)
-            tma_load_3d(kv + st * Cfg::kKvStage + kb * Cfg::kKvBlock, &tm_k, kb * 64, c * CH, img0 + ii, kv_full + st);
-          if (has_rn) bulk_load_1d(rn_s + st * CH, p.rnorm + (size_t)(img0 + ii) * p.Rpad + c * CH, n * 4, kv_full + st);
-          if (c == 0) {
-            mbar_wait(ch_empty, (ii & 1) ^ 1, wc, 12);
-            mbar_expect_tx(ch_full, Cfg::kQBytes);
+              for (int kb = 0; kb < D / 64; ++kb)
+                tma_load_3d(kv + st * Cfg::kKvStage + kb * Cfg::kKvBlock, &tm_k, kb * 64, c * CH, img, kv_full + st);
+              if (has_rn) bulk_load_1d(rn_s + st * CH, p.rnorm + (size_t)img * p.Rpad + c * CH, n * 4, kv_full + st);
+              if (c == 0) {
+                mbar_wait(ch_empty, (ic & 1) ^ 1, wc, 12);
+                mbar_expect_tx(ch_full, Cfg::kQBytes);
 #pragma unroll
-            for (int kb = 0; kb < D / 64; ++kb)
-              tma_load_3d(Cs + kb * Cfg::kQBlock, &tm_c, kb * 64, m0, img0 + ii, ch_full);
+                for (int kb = 0; kb < D / 64; ++kb)
+                  tma_load_3d(Cs + kb * Cfg::kQBlock, &tm_c, kb * 64, m0, img, ch_full);
+              }
+              // the next image's contexts come from HBM and are needed the moment this image ends (the single
+              // buffer cannot be refilled earlier): pull them into L2 shortly before
+              if (c == max(0, nch - 3) && ii + 1 < sg.nimg) {
+#pragma unroll
+                for (int kb = 0; kb < D / 64; ++kb) tma_prefetch_l2_3d(&tm_c, kb * 64, m0, img + 1);
+              }
+            }
           }
-          // the next image's contexts come from HBM and are needed the moment this image ends (the single
-          // buffer cannot be refilled earlier): pull them into L2 shortly before
-          if (c == max(0, nch - 3) && ii + 1 < nimg) {
-#pragma unroll
-            for (int kb = 0; kb < D / 64; ++kb) tma_prefetch_l2_3d(&tm_c, kb * 64, m0, img0 + ii + 1);
-          }
-          if (++c == nch) { c = 0; ++ii; }
+          ++seg;
         }
       }
       __syncwarp();
-    } else if (G > 0 && warp == 1) {
+    } else if (warp == 1) {
       // ===== MMA issuer: one elected thread runs the whole role =====
       if (elect_one()) {
         constexpr uint32_t idesc_dq = idesc_bf16(TM, D, false, true);
@@ -705,257 +758,282 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             mma_ss(tmem + d_col, a_k + (((k >> 2) * Cfg::kQBlock + (k & 3) * 32) >> 4),
                    b_k + (((k >> 2) * Cfg::kKvBlock + (k & 3) * 32) >> 4), idesc, k > 0);
         };
-        mbar_wait(q_full, 0, wc, 13);
-        mbar_wait(kv_full + 0, 0, wc, 14);
-        tc_fence_after();
-        issue_scores(0, min(CH, p.Rpad), q_k, Cfg::kColS);
-        mbar_wait(ch_full, 0, wc, 15);
-        tc_fence_after();
-        issue_scores(0, min(CH, p.Rpad), c_k, Cfg::kColW);
-        mma_commit(sw_full);
-        int c = 0, ii = 0;
-        for (int g = 0; g < G; ++g) {
-          const int st = g & 1, n = min(CH, p.Rpad - c * CH);
-          const bool last_chunk = (c == nch - 1);
-          const bool has_next = g + 1 < G;
-          const int n1 = last_chunk ? min(CH, p.Rpad) : min(CH, p.Rpad - (c + 1) * CH);
-          if (has_next) {
-            // S,W(g) are in the elementwise warps' registers: the next scores may overwrite them now
-            mbar_wait(sw_consumed, g & 1, wc, 16);
-            mbar_wait(kv_full + (st ^ 1), ((g + 1) >> 1) & 1, wc, 18);
+        int x = 0, ic = 0, seg = 0;
+        SegIter it = seg_iter(NQ, p.Bi);
+        Seg sg;
+        while (it.next(sg)) {
+          const int G = sg.nimg * nch;
+          mbar_wait(q_full, seg & 1, wc, 13);
+          mbar_wait(kv_full + (x & 1), (x >> 1) & 1, wc, 14);
+          tc_fence_after();
+          issue_scores(x & 1, min(CH, p.Rpad), q_k, Cfg::kColS);
+          mbar_wait(ch_full, ic & 1, wc, 15);
+          tc_fence_after();
+          issue_scores(x & 1, min(CH, p.Rpad), c_k, Cfg::kColW);
+          mma_commit(sw_full);
+          int c = 0;
+          for (int g = 0; g < G; ++g, ++x) {
+            const int st = x & 1, n = min(CH, p.Rpad - c * CH);
+            const bool last_chunk = (c == nch - 1);
+            const bool has_next = g + 1 < G;
+            const int n1 = last_chunk ? min(CH, p.Rpad) : min(CH, p.Rpad - (c + 1) * CH);
+            if (has_next) {
+              // S,W(g) are in the elementwise warps' registers: the next scores may overwrite them now
+              mbar_wait(sw_consumed, x & 1, wc, 16);
+              mbar_wait(kv_full + (st ^ 1), ((x + 1) >> 1) & 1, wc, 18);
+              tc_fence_after();
+              XMC_TRACE(0, x, 0);
+              issue_scores(st ^ 1, n1, q_k, Cfg::kColS);
+              if (!last_chunk) {
+                issue_scores(st ^ 1, n1, c_k, Cfg::kColW);
+                mma_commit(sw_full);
+              }
+            }
+            mbar_wait(xy_full, x & 1, wc, 17);
+            if (x > 0) mbar_wait(dk_empty, (x - 1) & 1, wc, 19);
+            if (g == 0 && seg > 0) mbar_wait(dq_empty, (seg - 1) & 1, wc, 9);   // the previous tile's dQ has left TMEM
             tc_fence_after();
-            XMC_TRACE(0, g, 0);
-            issue_scores(st ^ 1, n1, q_k, Cfg::kColS);
-            if (!last_chunk) {
+            XMC_TRACE(0, x, 1);
+            const uint32_t idesc_dk = idesc_bf16(TM, n, true, true);
+            auto issue_dq = [&]() {                       // dQ += X Khat_chunk
+              const Desc b_mn = kv_mn + ((uint32_t)(st * Cfg::kKvStage) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < CH / 16; ++ks)
+                if (ks * 16 < n) mma_ss(tmem + Cfg::kColDQ, x_k + ((ks * 32) >> 4), b_mn + ((ks * 2048) >> 4), idesc_dq, (g > 0) || (ks > 0));
+              mma_commit(kv_empty + st);
+            };
+            auto issue_dk_c = [&]() {                     // dK^T = Chat^T Y   [128 d x n] per M-tile, contraction over the 128 word rows
+#pragma unroll
+              for (int h = 0; h < Cfg::kTilesD; ++h) {
+#pragma unroll
+                for (int kt = 0; kt < TM / 16; ++kt)
+                  mma_ss(tmem + Cfg::kColDK + h * CH, c_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), y_mn + ((kt * 2048) >> 4), idesc_dk, kt > 0);
+              }
+            };
+            if (last_chunk) {
+              // end of the image: release the context buffer first, the refill overlaps dQ and the Q part of dK^T
+              issue_dk_c();
+              mma_commit(ch_empty);
+              issue_dq();
+            } else {
+              // inside the image: release the region stage first, the next chunk's load overlaps dK^T
+              issue_dq();
+              issue_dk_c();
+            }
+#pragma unroll
+            for (int h = 0; h < Cfg::kTilesD; ++h) {      // dK^T += Q^T X
+#pragma unroll
+              for (int kt = 0; kt < TM / 16; ++kt)
+                mma_ss(tmem + Cfg::kColDK + h * CH, q_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), x_mn + ((kt * 2048) >> 4), idesc_dk, true);
+            }
+            mma_commit(dk_full);          // X / Y are dead once this fires
+            XMC_TRACE(0, x, 2);
+            if (has_next && last_chunk) {
+              mbar_wait(ch_full, (ic + 1) & 1, wc, 15);
+              tc_fence_after();
               issue_scores(st ^ 1, n1, c_k, Cfg::kColW);
               mma_commit(sw_full);
             }
+            XMC_TRACE(0, x, 3);
+            if (++c == nch) { c = 0; ++ic; }
           }
-          mbar_wait(xy_full, g & 1, wc, 17);
-          if (g > 0) mbar_wait(dk_empty, (g - 1) & 1, wc, 19);
-          tc_fence_after();
-          XMC_TRACE(0, g, 1);
-          const uint32_t idesc_dk = idesc_bf16(TM, n, true, true);
-          auto issue_dq = [&]() {                       // dQ += X Khat_chunk
-            const Desc b_mn = kv_mn + ((uint32_t)(st * Cfg::kKvStage) >> 4);
-#pragma unroll
-            for (int ks = 0; ks < CH / 16; ++ks)
-              if (ks * 16 < n) mma_ss(tmem + Cfg::kColDQ, x_k + ((ks * 32) >> 4), b_mn + ((ks * 2048) >> 4), idesc_dq, (g > 0) || (ks > 0));
-            mma_commit(kv_empty + st);
-          };
-          auto issue_dk_c = [&]() {                     // dK^T = Chat^T Y   [128 d x n] per M-tile, contraction over the 128 word rows
-#pragma unroll
-            for (int h = 0; h < Cfg::kTilesD; ++h) {
-#pragma unroll
-              for (int kt = 0; kt < TM / 16; ++kt)
-                mma_ss(tmem + Cfg::kColDK + h * CH, c_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), y_mn + ((kt * 2048) >> 4), idesc_dk, kt > 0);
-            }
-          };
-          if (last_chunk) {
-            // end of the image: release the context buffer first, the refill overlaps dQ and the Q part of dK^T
-            issue_dk_c();
-            mma_commit(ch_empty);
-            issue_dq();
-          } else {
-            // inside the image: release the region stage first, the next chunk's load overlaps dK^T
-            issue_dq();
-            issue_dk_c();
-          }
-#pragma unroll
-          for (int h = 0; h < Cfg::kTilesD; ++h) {      // dK^T += Q^T X
-#pragma unroll
-            for (int kt = 0; kt < TM / 16; ++kt)
-              mma_ss(tmem + Cfg::kColDK + h * CH, q_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), x_mn + ((kt * 2048) >> 4), idesc_dk, true);
-          }
-          mma_commit(dk_full);          // X / Y are dead once this fires
-          XMC_TRACE(0, g, 2);
-          if (has_next && last_chunk) {
-            mbar_wait(ch_full, (ii + 1) & 1, wc, 15);
-            tc_fence_after();
-            issue_scores(st ^ 1, n1, c_k, Cfg::kColW);
-            mma_commit(sw_full);
-          }
-          XMC_TRACE(0, g, 3);
-          if (++c == nch) { c = 0; ++ii; }
+          mma_commit(dq_full);
+          ++seg;
         }
-        mma_commit(dq_full);
       }
       __syncwarp();
     }
   } else if (warp < 12) {
     setmaxnreg_inc<kBwdRegsEw>();
-    if (G > 0) {
+    {
       // ===== elementwise warpgroups: thread = TMEM lane = word row =====
       const int h = (warp - 4) >> 2;              // 0: chunk cols 0-31, 1: cols 32-63
       const int q = warp & 3;
       const int row = q * 32 + lane;
-      const int grow = m0 + row;
       const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
       const float c1 = p.rho1 * kLog2eTc;
       const int col0 = h * 32;
       const bool tracer = (threadIdx.x == 128);
 
-      // ---- arithmetic of one chunk (gm): S,W -> X,Y (packed bf16, registers) and the drnorm column sum ----
-      int gm = 0, cm = 0, iim = 0;
-      float inv_l = 1.f, gam = 0.f, ngrl = 0.f;
-      uint32_t xp[16], yp[16];
-      float colsum = 0.f;
-      auto arithmetic = [&]() {
-        if (cm == 0) {
-          inv_l = 1.f; gam = 0.f; ngrl = 0.f;
-          if (grow < p.NQ) {
-            const size_t o = (size_t)(img0 + iim) * p.NQ + grow;
-            const float inv_cn = 1.f / fmaxf(__ldg(p.cnorm + o), kEps);
-            inv_l = 1.f / __ldg(p.lsum + o);
-            gam = __ldg(p.grel + o) * inv_cn;
-            // the saved context is the unscaled sum C = l c (not the unit vector): W = C K^T and the
-            // Chat^T Y term both carry 1 / (l ||c||), folded into the coefficient that multiplies them
-            ngrl = -gam * __ldg(p.rel + o) * inv_cn * inv_l;
-          }
-        }
-        const int n = min(CH, p.Rpad - cm * CH);
-        const int r0 = cm * CH + col0;
-        mbar_wait(sw_full, gm & 1, wc, 20);
-        tc_fence_after();
-        if (tracer) XMC_TRACE(1, gm, 0);
-        if (col0 < n) {                               // warp-uniform: this warpgroup has columns in the chunk
-          const float* wsm = rn_s + (gm & 1) * CH + col0;
-          float z[32];
-          // two halves of 16 columns (register budget); S,W are released after the second load
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t sv[16], wv[16];
-            tmem_ld16(lane_base + Cfg::kColS + col0 + hf * 16, sv);
-            tmem_ld16(lane_base + Cfg::kColW + col0 + hf * 16, wv);
-            tmem_wait_ld();
-            if (hf == 1) {
-              tc_fence_before();
-              mbar_arrive(sw_consumed);
-              if (tracer) XMC_TRACE(1, gm, 1);
+      int xm = 0;                                 // running index of the chunk whose arithmetic is next
+      int x = 0, seg = 0;
+      SegIter it = seg_iter(NQ, p.Bi);
+      Seg sg;
+      while (it.next(sg)) {
+        const int grow = sg.tile * TM + row;
+        const int G = sg.nimg * nch;
+        // ---- arithmetic of one chunk: S,W -> X,Y (packed bf16, registers) and the drnorm column sum ----
+        int cm = 0, iim = 0;                      // chunk-in-image / image-in-segment of the arithmetic chunk
+        float inv_l = 1.f, gam = 0.f, ngrl = 0.f;
+        uint32_t xp[16], yp[16];
+        float colsum = 0.f;
+        auto arithmetic = [&]() {
+          if (cm == 0) {
+            inv_l = 1.f; gam = 0.f; ngrl = 0.f;
+            if (grow < NQ) {
+              const size_t o = (size_t)(sg.img0 + iim) * p.NQ + grow;
+              const float inv_cn = 1.f / fmaxf(__ldg(p.cnorm + o), kEps);
+              inv_l = 1.f / __ldg(p.lsum + o);
+              gam = __ldg(p.grel + o) * inv_cn;
+              // the saved context is the unscaled sum C = l c (not the unit vector): W = C K^T and the
+              // Chat^T Y term both carry 1 / (l ||c||), folded into the coefficient that multiplies them
+              ngrl = -gam * __ldg(p.rel + o) * inv_cn * inv_l;
             }
-            auto elementwise = [&](auto full_tag) {
-              constexpr bool kFull = decltype(full_tag)::value;   // every column is a real region: no predicates
+          }
+          const int n = min(CH, p.Rpad - cm * CH);
+          const int r0 = cm * CH + col0;
+          mbar_wait(sw_full, xm & 1, wc, 20);
+          tc_fence_after();
+          if (tracer) XMC_TRACE(1, xm, 0);
+          if (col0 < n) {                               // warp-uniform: this warpgroup has columns in the chunk
+            const float* wsm = rn_s + (xm & 1) * CH + col0;
+            float z[32];
+            // two halves of 16 columns (register budget); S,W are released after the second load
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + hf * 16 + j4 * 4);
-                const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
-                float xv[4], yv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const int j = j4 * 4 + u;
-                  const float s = __uint_as_float(sv[j]);
-                  const float w = __uint_as_float(wv[j]);
-                  float al = ex2_approx(fmaf(c1, s, -c1)) * inv_l;                       // alpha
-                  if (!kFull) al = (r0 + hf * 16 + j) < p.R ? al : 0.f;                  // padded region rows: alpha = 0 zeroes X, Y, z
-                  const float alp = al * mrv[u];                                         // alpha' = alpha * ||v_r||
-                  const float dap = fmaf(ngrl, w, gam * s);                              // d loss / d alpha'
-                  xv[u] = alp * fmaf(p.rho1, dap, gam);                                  // dS + gamma*alpha'
-                  yv[u] = ngrl * alp;
-                  z[hf * 16 + j] = al * dap;
-                }
-                xp[hf * 8 + j4 * 2 + 0] = pack_bf16(xv[0], xv[1]); xp[hf * 8 + j4 * 2 + 1] = pack_bf16(xv[2], xv[3]);
-                yp[hf * 8 + j4 * 2 + 0] = pack_bf16(yv[0], yv[1]); yp[hf * 8 + j4 * 2 + 1] = pack_bf16(yv[2], yv[3]);
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t sv[16], wv[16];
+              tmem_ld16(lane_base + Cfg::kColS + col0 + hf * 16, sv);
+              tmem_ld16(lane_base + Cfg::kColW + col0 + hf * 16, wv);
+              tmem_wait_ld();
+              if (hf == 1) {
+                tc_fence_before();
+                mbar_arrive(sw_consumed);
+                if (tracer) XMC_TRACE(1, xm, 1);
               }
-            };
-            if (r0 + 32 <= p.R) elementwise(std::true_type{}); else elementwise(std::false_type{});
+              auto elementwise = [&](auto full_tag) {
+                constexpr bool kFull = decltype(full_tag)::value;   // every column is a real region: no predicates
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
+                  if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + hf * 16 + j4 * 4);
+                  const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
+                  float xv[4], yv[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int j = j4 * 4 + u;
+                    const float s = __uint_as_float(sv[j]);
+                    const float w = __uint_as_float(wv[j]);
+                    float al = ex2_approx(fmaf(c1, s, -c1)) * inv_l;                       // alpha
+                    if (!kFull) al = (r0 + hf * 16 + j) < p.R ? al : 0.f;                  // padded region rows: alpha = 0 zeroes X, Y, z
+                    const float alp = al * mrv[u];                                         // alpha' = alpha * ||v_r||
+                    const float dap = fmaf(ngrl, w, gam * s);                              // d loss / d alpha'
+                    xv[u] = alp * fmaf(p.rho1, dap, gam);                                  // dS + gamma*alpha'
+                    yv[u] = ngrl * alp;
+                    z[hf * 16 + j] = al * dap;
+                  }
+                  xp[hf * 8 + j4 * 2 + 0] = pack_bf16(xv[0], xv[1]); xp[hf * 8 + j4 * 2 + 1] = pack_bf16(xv[2], xv[3]);
+                  yp[hf * 8 + j4 * 2 + 0] = pack_bf16(yv[0], yv[1]); yp[hf * 8 + j4 * 2 + 1] = pack_bf16(yv[2], yv[3]);
+                }
+              };
+              if (r0 + 32 <= p.R) elementwise(std::true_type{}); else elementwise(std::false_type{});
+            }
+            if (has_rn) colsum = warp_transpose_sum32(z, lane);      // column (r0 + lane) over this warp's 32 rows
+          } else {
+            tc_fence_before();
+            mbar_arrive(sw_consumed);
           }
-          if (has_rn) colsum = warp_transpose_sum32(z, lane);      // column (r0 + lane) over this warp's 32 rows
-        } else {
-          tc_fence_before();
-          mbar_arrive(sw_consumed);
-        }
-        if (tracer) XMC_TRACE(1, gm, 2);
-        ++gm;
-        if (++cm == nch) { cm = 0; ++iim; }
-      };
+          if (tracer) XMC_TRACE(1, xm, 2);
+          ++xm;
+          if (++cm == nch) { cm = 0; ++iim; }
+        };
 
-      arithmetic();                                   // chunk 0
-      int c = 0, ii = 0;
-      for (int g = 0; g < G; ++g) {
-        const int img = img0 + ii;
-        const int n = min(CH, p.Rpad - c * CH);
-        const bool active = col0 < n;
-        const int r0 = c * CH + col0;
-        // ---- X,Y(g) -> smem.  Safe: dk_full(g-1) was waited for below, so the MMAs that read X,Y(g-1) are done.
-        if (active) {
-          // row `row` of the [128 x 64] bf16 tiles, 16-byte chunks XOR-swizzled by (row & 7)
+        arithmetic();                                   // first chunk of the segment
+        int c = 0, ii = 0;
+        for (int g = 0; g < G; ++g, ++x) {
+          const int img = sg.img0 + ii;
+          const int n = min(CH, p.Rpad - c * CH);
+          const bool active = col0 < n;
+          const int r0 = c * CH + col0;
+          // ---- X,Y(g) -> smem.  Safe: dk_full of the previous chunk was waited for below, so the MMAs that read X,Y are done.
+          if (active) {
+            // row `row` of the [128 x 64] bf16 tiles, 16-byte chunks XOR-swizzled by (row & 7)
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int phys = ((col0 >> 3) + u) ^ (row & 7);
-            *reinterpret_cast<uint4*>(Xs + row * 128 + phys * 16) = make_uint4(xp[4 * u], xp[4 * u + 1], xp[4 * u + 2], xp[4 * u + 3]);
-            *reinterpret_cast<uint4*>(Ys + row * 128 + phys * 16) = make_uint4(yp[4 * u], yp[4 * u + 1], yp[4 * u + 2], yp[4 * u + 3]);
+            for (int u = 0; u < 4; ++u) {
+              const int phys = ((col0 >> 3) + u) ^ (row & 7);
+              *reinterpret_cast<uint4*>(Xs + row * 128 + phys * 16) = make_uint4(xp[4 * u], xp[4 * u + 1], xp[4 * u + 2], xp[4 * u + 3]);
+              *reinterpret_cast<uint4*>(Ys + row * 128 + phys * 16) = make_uint4(yp[4 * u], yp[4 * u + 1], yp[4 * u + 2], yp[4 * u + 3]);
+            }
           }
+          fence_proxy_async_smem();
+          mbar_arrive(xy_full);
+          if (tracer) XMC_TRACE(2, x, 0);
+          if (active && has_rn && r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
+          // ---- arithmetic of chunk g+1 while dQ(g), dK^T(g) run on the tensor pipe ----
+          if (g + 1 < G) arithmetic();
+          if (tracer) XMC_TRACE(2, x, 1);
+          // ---- X,Y(g) stay live until dQ(g), dK^T(g) have executed ----
+          mbar_wait(dk_full, x & 1, wc, 21);
+          if (tracer) XMC_TRACE(2, x, 2);
+          if (++c == nch) { c = 0; ++ii; }
         }
-        fence_proxy_async_smem();
-        mbar_arrive(xy_full);
-        if (tracer) XMC_TRACE(2, g, 0);
-        if (active && has_rn && r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
-        // ---- arithmetic of chunk g+1 while dQ(g), dK^T(g) run on the tensor pipe ----
-        if (g + 1 < G) arithmetic();
-        if (tracer) XMC_TRACE(2, g, 1);
-        // ---- X,Y(g) stay live until dQ(g), dK^T(g) have executed ----
-        mbar_wait(dk_full, g & 1, wc, 21);
-        if (tracer) XMC_TRACE(2, g, 2);
-        if (++c == nch) { c = 0; ++ii; }
-      }
-      // ---- dQ of this CTA's word tile (summed over its images) ----
-      mbar_wait(dq_full, 0, wc, 22);
-      tc_fence_after();
-      {
-        float* dst = p.dqn + (size_t)grow * D + h * (D / 2);
+        // ---- dQ of this segment's word tile (summed over its images) ----
+        mbar_wait(dq_full, seg & 1, wc, 22);
+        tc_fence_after();
+        {
+          float* dst = p.dqn + (size_t)grow * D + h * (D / 2);
 #pragma unroll 1
-        for (int blk = 0; blk < D / 64; ++blk) {
-          uint32_t dv[32];
-          tmem_ld32(lane_base + Cfg::kColDQ + h * (D / 2) + blk * 32, dv);   // warp-collective: never predicate
-          tmem_wait_ld();
-          if (grow < p.NQ) {
+          for (int blk = 0; blk < D / 64; ++blk) {
+            uint32_t dv[32];
+            tmem_ld32(lane_base + Cfg::kColDQ + h * (D / 2) + blk * 32, dv);   // warp-collective: never predicate
+            tmem_wait_ld();
+            if (blk == D / 64 - 1) {                    // dQ is in registers: the next segment may overwrite it
+              tc_fence_before();
+              mbar_arrive(dq_empty);
+            }
+            if (grow < NQ) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + blk * 32 + j, __uint_as_float(dv[j]));
+              for (int j = 0; j < 32; ++j) atomicAdd(dst + blk * 32 + j, __uint_as_float(dv[j]));
+            }
           }
         }
+        ++seg;
       }
     }
   } else {
     setmaxnreg_dec<kBwdRegsDrain>();
-    if (G > 0) {
+    {
       // ===== drain warpgroup: dK^T(g) TMEM -> registers -> red.global.add.f32 into dkn.  Thread = TMEM
       //       lane = feature d of an M-tile; a warp adds 32 consecutive d of one region row (128 bytes). =====
       const int q = warp & 3;
       const int row = q * 32 + lane;
       const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
       const bool tracer = (threadIdx.x == 384);
-      int c = 0, ii = 0;
-      for (int g = 0; g < G; ++g) {
-        const int n = min(CH, p.Rpad - c * CH);
-        mbar_wait(dk_full, g & 1, wc, 23);
-        tc_fence_after();
-        if (tracer) XMC_TRACE(3, g, 0);
+      int x = 0;
+      SegIter it = seg_iter(NQ, p.Bi);
+      Seg sg;
+      while (it.next(sg)) {
+        for (int ii = 0; ii < sg.nimg; ++ii) {
+          for (int c = 0; c < nch; ++c, ++x) {
+            const int n = min(CH, p.Rpad - c * CH);
+            mbar_wait(dk_full, x & 1, wc, 23);
+            tc_fence_after();
+            if (tracer) XMC_TRACE(3, x, 0);
 #pragma unroll
-        for (int h = 0; h < Cfg::kTilesD; ++h) {
-          float* dst0 = p.dkn + ((size_t)(img0 + ii) * p.Rpad + c * CH) * D + h * 128 + row;
-          uint32_t dva[32], dvb[32];
-          tmem_ld32(lane_base + Cfg::kColDK + h * CH, dva);            // rows of the chunk past n hold stale data:
-          if (n > 32) tmem_ld32(lane_base + Cfg::kColDK + h * CH + 32, dvb);   // never added below
-          tmem_wait_ld();
-          if (h == Cfg::kTilesD - 1) {                                 // dK^T(g) is in registers
-            tc_fence_before();
-            mbar_arrive(dk_empty);
-            if (tracer) XMC_TRACE(3, g, 1);
-          }
-          if (!(p.dbg_flags & 2)) {
+            for (int h = 0; h < Cfg::kTilesD; ++h) {
+              float* dst0 = p.dkn + ((size_t)(sg.img0 + ii) * p.Rpad + c * CH) * D + h * 128 + row;
+              uint32_t dva[32], dvb[32];
+              tmem_ld32(lane_base + Cfg::kColDK + h * CH, dva);            // rows of the chunk past n hold stale data:
+              if (n > 32) tmem_ld32(lane_base + Cfg::kColDK + h * CH + 32, dvb);   // never added below
+              tmem_wait_ld();
+              if (h == Cfg::kTilesD - 1) {                                 // dK^T(g) is in registers
+                tc_fence_before();
+                mbar_arrive(dk_empty);
+                if (tracer) XMC_TRACE(3, x, 1);
+              }
+              if (!(p.dbg_flags & 2)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < n) red_add_f32(dst0 + (size_t)j * D, __uint_as_float(dva[j]));
-            if (n > 32) {
+                for (int j = 0; j < 32; ++j)
+                  if (j < n) red_add_f32(dst0 + (size_t)j * D, __uint_as_float(dva[j]));
+                if (n > 32) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (32 + j < n) red_add_f32(dst0 + (size_t)(32 + j) * D, __uint_as_float(dvb[j]));
+                  for (int j = 0; j < 32; ++j)
+                    if (32 + j < n) red_add_f32(dst0 + (size_t)(32 + j) * D, __uint_as_float(dvb[j]));
+                }
+              }
             }
+            if (tracer) XMC_TRACE(3, x, 2);
           }
         }
-        if (tracer) XMC_TRACE(3, g, 2);
-        if (++c == nch) { c = 0; ++ii; }
       }
     }
   }
@@ -980,14 +1058,11 @@ static int launch_bwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
   p.err = static_cast<int*>(ws);
   p.dbg_flags = g_debug_dump;
   p.trace = ((g_debug_dump & 4) && ws_bytes >= 64 + 4 * 64 * 4 * 8) ? reinterpret_cast<long long*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
-  const int tiles = (w.NQ + TM - 1) / TM;
-  int splits = num_sms() / tiles;
-  if (splits < 1) splits = 1;
-  if (splits > w.Bi) splits = w.Bi;
-  p.imgs_per_cta = (w.Bi + splits - 1) / splits;
-  splits = (w.Bi + p.imgs_per_cta - 1) / p.imgs_per_cta;
+  p.nq_dev = w.nq_dev;
+  const long long items = (long long)((w.NQ + TM - 1) / TM) * w.Bi;      // upper bound (all rows valid)
+  const int grid = (int)std::min<long long>(num_sms(), items);
   XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_bwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  wr_bwd_tc_kernel<D><<<dim3(tiles, splits), kBwdThreads, Cfg::kSmemBytes, st>>>(tq, tcm, tk, p);
+  wr_bwd_tc_kernel<D><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(tq, tcm, tk, p);
   return cuda_fail(cudaGetLastError(), "wr_bwd_tc_kernel launch");
 }
 

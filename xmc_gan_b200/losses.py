@@ -192,15 +192,31 @@ class WordLossFn(torch.autograd.Function):
         else:
             m_all = None
         Rpad = _ceil_to(R, 16)
-        qn, qnorm = ops.normalize_transpose(w_all, T, op_dtype)    # [Bc_g, T, D]
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        use_tc_bwd = path == _lib.PATH_BF16_TCGEN05 and D in TC_BACKWARD_DIMS
+        # Padding words never contribute (excluded from the log-sum-exp, zero gradient): on the tcgen05
+        # path the kernels visit only the valid word rows, compacted in caption-major order.  Their
+        # number stays on the device (cap_ptr[Bc]); nothing here synchronises with the host.
+        compact = (m_all is not None and path == _lib.PATH_BF16_TCGEN05 and (use_tc_bwd or not need_grad)
+                   and getattr(ops, "supports_compaction", False))
+        row_of = cap_ptr = nq_dev = None
+        if compact:
+            row_of, cap_ptr = ops.word_rows_compact(m_all)
+            nq_dev = cap_ptr[Bc:]
+            qn, qnorm = ops.normalize_transpose(w_all, T, op_dtype, row_of=row_of)   # compact rows of [Bc_g*T, D]
+        else:
+            qn, qnorm = ops.normalize_transpose(w_all, T, op_dtype)                  # [Bc_g, T, D]
         kn, rnorm = ops.normalize_transpose(reg, Rpad, op_dtype)   # [Bi, Rpad, D]
         qn2 = qn.view(Bc * T, D)
         rn = None if normalize_values else rnorm
-        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        use_tc_bwd = path == _lib.PATH_BF16_TCGEN05 and D in TC_BACKWARD_DIMS
-        lsum, cnorm, rel, chat = ops.wordregion_forward(path, qn2, kn, rn, R, rho1,
-                                                        save_context=need_grad and use_tc_bwd)
-        scores = ops.word_scores(rel, m_all, Bc, T, rho2)          # [Bi, Bc_g]
+        if compact:
+            lsum, cnorm, rel, chat = ops.wordregion_forward(path, qn2, kn, rn, R, rho1,
+                                                            save_context=need_grad and use_tc_bwd, nq_dev=nq_dev)
+            scores = ops.word_scores(rel, m_all, Bc, T, rho2, cap_ptr=cap_ptr)       # [Bi, Bc_g]
+        else:
+            lsum, cnorm, rel, chat = ops.wordregion_forward(path, qn2, kn, rn, R, rho1,
+                                                            save_context=need_grad and use_tc_bwd)
+            scores = ops.word_scores(rel, m_all, Bc, T, rho2)      # [Bi, Bc_g]
 
         lab, diag, rc = _label_args(labels, comm, Bi)
         if lab is not None and tuple(lab.shape) != (Bi, Bc):
@@ -218,19 +234,19 @@ class WordLossFn(torch.autograd.Function):
         ctx.meta = (path, R, T, float(rho1), float(rho2), float(rho3), diag, num_pos, rows_total, Bc,
                     tuple(regions.shape), regions.dtype, words.dtype)
         ctx.has = (rn is not None, m_all is not None, lab is not None, row_div is not None, col_div is not None,
-                   chat is not None)
+                   chat is not None, compact)
         e = torch.empty(0)
         ctx.save_for_backward(qn, qnorm, kn, rnorm, lsum, cnorm, rel, scores, row_stats, col_stats,
                               m_all if m_all is not None else e, lab if lab is not None else e,
                               row_div if row_div is not None else e, col_div if col_div is not None else e,
-                              chat if chat is not None else e)
+                              chat if chat is not None else e, row_of if compact else e, cap_ptr if compact else e)
         return loss3[0]
 
     @staticmethod
     def backward(ctx, grad_out):
         (qn, qnorm, kn, rnorm, lsum, cnorm, rel, scores, row_stats, col_stats,
-         m_all, lab, row_div, col_div, chat) = ctx.saved_tensors
-        has_rn, has_m, has_lab, has_rd, has_cd, has_chat = ctx.has
+         m_all, lab, row_div, col_div, chat, row_of, cap_ptr) = ctx.saved_tensors
+        has_rn, has_m, has_lab, has_rd, has_cd, has_chat, compact = ctx.has
         m_all = m_all if has_m else None
         lab = lab if has_lab else None
         row_div = row_div if has_rd else None
@@ -243,20 +259,30 @@ class WordLossFn(torch.autograd.Function):
         go = grad_out.detach().to(torch.float32).contiguous()
         dscores = ops.infonce_grad(scores, lab, diag, rho3, row_stats, col_stats, row_div, col_div, num_pos,
                                    rows_total, Bc, go)
-        grel = ops.word_scores_backward(rel, m_all, scores, dscores, T, rho2)
         D = qn.shape[2]
-        if path == _lib.PATH_BF16_TCGEN05 and not has_chat:
-            # D outside the tcgen05 backward kernel's set: run the fp32 CUDA-core backward kernel on the
-            # (bf16-rounded) operands the forward used.  Still libxmcloss, never PyTorch.
-            dqn, dkn, drnorm = ops.wordregion_backward(_lib.PATH_FP32_SIMT, qn.view(-1, D).float(), kn.float(),
-                                                       rnorm if has_rn else None, R, rho1, lsum, cnorm, rel, grel)
-        else:
+        if compact:
+            nq_dev = cap_ptr[Bc:]
+            grel = ops.word_scores_backward(rel, m_all, scores, dscores, T, rho2, cap_ptr=cap_ptr)
             dqn, dkn, drnorm = ops.wordregion_backward(path, qn.view(-1, D), kn, rnorm if has_rn else None, R, rho1,
-                                                       lsum, cnorm, rel, grel, chat if has_chat else None)
+                                                       lsum, cnorm, rel, grel, chat, nq_dev=nq_dev)
+        else:
+            grel = ops.word_scores_backward(rel, m_all, scores, dscores, T, rho2)
+            if path == _lib.PATH_BF16_TCGEN05 and not has_chat:
+                # D outside the tcgen05 backward kernel's set: run the fp32 CUDA-core backward kernel on the
+                # (bf16-rounded) operands the forward used.  Still libxmcloss, never PyTorch.
+                dqn, dkn, drnorm = ops.wordregion_backward(_lib.PATH_FP32_SIMT, qn.view(-1, D).float(), kn.float(),
+                                                           rnorm if has_rn else None, R, rho1, lsum, cnorm, rel, grel)
+            else:
+                dqn, dkn, drnorm = ops.wordregion_backward(path, qn.view(-1, D), kn, rnorm if has_rn else None, R, rho1,
+                                                           lsum, cnorm, rel, grel, chat if has_chat else None)
         dreg = dwords = None
         if need_reg:
             dreg = ops.normalize_transpose_backward(kn, rnorm, dkn, drnorm, R, reg_dtype).view(reg_shape)
         if need_w:
-            dw_all = ops.normalize_transpose_backward(qn, qnorm, dqn.view(qn.shape), None, T, torch.float32)
+            if compact:
+                dw_all = ops.normalize_transpose_backward(qn, qnorm, dqn.view(qn.shape), None, T, torch.float32,
+                                                          row_of=row_of)
+            else:
+                dw_all = ops.normalize_transpose_backward(qn, qnorm, dqn.view(qn.shape), None, T, torch.float32)
             dwords = comm.reduce_scatter_sum(dw_all).to(w_dtype)
         return (dreg, dwords) + (None,) * 10

@@ -175,24 +175,40 @@ class CudaOps:
         return labels, row_count
 
     # -- word-region --------------------------------------------------------------------------
-    def normalize_transpose(self, x, Lpad, out_dtype):
+    supports_compaction = True     # the tcgen05 kernels visit only the non-padding word rows
+
+    def word_rows_compact(self, mask_u8):
+        """mask [Bc, T] (non-zero = padding) -> row_of [Bc*T] int32 (-1 = dropped), cap_ptr [Bc+1] int32."""
+        _cuda(mask_u8)
+        Bc, T = mask_u8.shape
+        row_of = torch.empty(Bc * T, device=mask_u8.device, dtype=torch.int32)
+        cap_ptr = torch.empty(Bc + 1, device=mask_u8.device, dtype=torch.int32)
+        with torch.cuda.device_of(mask_u8):
+            _lib.check(self.L.xmc_word_rows_compact(_p(mask_u8), Bc, T, _p(row_of), _p(cap_ptr), _stream()))
+        self.launches += 1
+        return row_of, cap_ptr
+
+    def normalize_transpose(self, x, Lpad, out_dtype, row_of=None):
         _cuda(x)
         B, D, L = x.shape
-        xn = torch.empty(B, Lpad, D, device=x.device, dtype=out_dtype)
+        if row_of is not None:        # compact rows: unwritten rows (dropped words, tail) must read as zeros
+            xn = torch.zeros(B, Lpad, D, device=x.device, dtype=out_dtype)
+        else:
+            xn = torch.empty(B, Lpad, D, device=x.device, dtype=out_dtype)
         norm = torch.empty(B, Lpad, device=x.device, dtype=torch.float32)
         with torch.cuda.device_of(x):
-            _lib.check(self.L.xmc_normalize_transpose(_p(x), B, D, L, Lpad, _dt(x), _DT[out_dtype],
+            _lib.check(self.L.xmc_normalize_transpose(_p(x), B, D, L, Lpad, _dt(x), _DT[out_dtype], _p(row_of),
                                                       _p(xn), _p(norm), _stream()))
         self.launches += 1
         return xn, norm
 
-    def normalize_transpose_backward(self, xn, norm, dxn, dnorm, L, out_dtype):
+    def normalize_transpose_backward(self, xn, norm, dxn, dnorm, L, out_dtype, row_of=None):
         _cuda(xn, dxn)
         B, Lpad, D = xn.shape
         dx = torch.empty(B, D, L, device=xn.device, dtype=out_dtype)
         with torch.cuda.device_of(xn):
             _lib.check(self.L.xmc_normalize_transpose_backward(_p(xn), _p(norm), _p(dxn), _p(dnorm), B, D, L, Lpad,
-                                                               _dt(xn), _DT[out_dtype], _p(dx), _stream()))
+                                                               _dt(xn), _DT[out_dtype], _p(row_of), _p(dx), _stream()))
         self.launches += 1
         return dx
 
@@ -203,26 +219,31 @@ class CudaOps:
         self.last_workspace = ws
         return ws, n
 
-    def wordregion_forward(self, path, qn, kn, rnorm, R, rho1, save_context=False):
-        """-> lsum, cnorm, rel [Bi, NQ] (+ chat [Bi, NQ, D] bf16 on the tcgen05 path when asked)."""
+    def wordregion_forward(self, path, qn, kn, rnorm, R, rho1, save_context=False, nq_dev=None):
+        """-> lsum, cnorm, rel [Bi, NQ] (+ chat [Bi, NQ, D] bf16 on the tcgen05 path when asked).
+
+        nq_dev: device int32 holding the number of valid (compact) rows of qn; rows beyond it are
+        neither read nor written, so with it the statistics are zero-initialised."""
         _cuda(qn, kn, rnorm)
         NQ, D = qn.shape
         Bi, Rpad, _ = kn.shape
         dev = qn.device
-        lsum = torch.empty(Bi, NQ, device=dev, dtype=torch.float32)
-        cnorm = torch.empty_like(lsum)
-        rel = torch.empty_like(lsum)
+        alloc = torch.zeros if nq_dev is not None else torch.empty
+        lsum = alloc(Bi, NQ, device=dev, dtype=torch.float32)
+        cnorm = alloc(Bi, NQ, device=dev, dtype=torch.float32)
+        rel = alloc(Bi, NQ, device=dev, dtype=torch.float32)
         chat = None
         if save_context and path == _lib.PATH_BF16_TCGEN05:
             chat = torch.empty(Bi, NQ, D, device=dev, dtype=torch.bfloat16)
         ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
         with torch.cuda.device_of(qn), self._timed("wordregion_fwd"):
             _lib.check(self.L.xmc_wordregion_forward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
-                                                     _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(ws), n, _stream()))
+                                                     _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(nq_dev), _p(ws), n,
+                                                     _stream()))
         self.launches += 1
         return lsum, cnorm, rel, chat
 
-    def wordregion_backward(self, path, qn, kn, rnorm, R, rho1, lsum, cnorm, rel, grel, chat=None):
+    def wordregion_backward(self, path, qn, kn, rnorm, R, rho1, lsum, cnorm, rel, grel, chat=None, nq_dev=None):
         _cuda(qn, kn, grel)
         NQ, D = qn.shape
         Bi, Rpad, _ = kn.shape
@@ -234,26 +255,28 @@ class CudaOps:
         with torch.cuda.device_of(qn), self._timed("wordregion_bwd"):
             _lib.check(self.L.xmc_wordregion_backward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
                                                       _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(grel), _p(dqn), _p(dkn),
-                                                      _p(drnorm), _p(ws), n, _stream()))
+                                                      _p(drnorm), _p(nq_dev), _p(ws), n, _stream()))
         self.launches += 1
         return dqn, dkn, drnorm
 
-    def word_scores(self, rel, mask_u8, Bc, T, rho2):
+    def word_scores(self, rel, mask_u8, Bc, T, rho2, cap_ptr=None):
         _cuda(rel, mask_u8)
-        Bi = rel.shape[0]
+        Bi, NQs = rel.shape
         scores = torch.empty(Bi, Bc, device=rel.device, dtype=torch.float32)
         with torch.cuda.device_of(rel):
-            _lib.check(self.L.xmc_word_scores(_p(rel), _p(mask_u8), Bi, Bc, T, float(rho2), _p(scores), _stream()))
+            _lib.check(self.L.xmc_word_scores(_p(rel), _p(mask_u8), _p(cap_ptr), Bi, Bc, T, NQs, float(rho2),
+                                              _p(scores), _stream()))
         self.launches += 1
         return scores
 
-    def word_scores_backward(self, rel, mask_u8, scores, dscores, T, rho2):
+    def word_scores_backward(self, rel, mask_u8, scores, dscores, T, rho2, cap_ptr=None):
         _cuda(rel, dscores)
         Bi, Bc = scores.shape
-        grel = torch.empty_like(rel)
+        NQs = rel.shape[1]
+        grel = torch.zeros_like(rel) if cap_ptr is not None else torch.empty_like(rel)
         with torch.cuda.device_of(rel):
-            _lib.check(self.L.xmc_word_scores_backward(_p(rel), _p(mask_u8), _p(scores), _p(dscores), Bi, Bc, T,
-                                                       float(rho2), _p(grel), _stream()))
+            _lib.check(self.L.xmc_word_scores_backward(_p(rel), _p(mask_u8), _p(cap_ptr), _p(scores), _p(dscores),
+                                                       Bi, Bc, T, NQs, float(rho2), _p(grel), _stream()))
         self.launches += 1
         return grel
 
