@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_version_and_error_string(built):
     L = _lib.lib()
-    assert L.xmc_version() == 1
+    assert L.xmc_version() == 2
     assert isinstance(L.xmc_last_error(), bytes)
 
 
@@ -36,9 +36,9 @@ def test_argument_validation_without_gpu(built):
     L = _lib.lib()
     rc = L.xmc_cosine_scores(None, None, 4, 4, 8, 0, None, None, None, None)
     assert rc == 1 and b"null" in L.xmc_last_error()
-    rc = L.xmc_wordregion_forward(0, 16, 16, None, 8, 2, 5, 7, 64, 5.0, 16, 16, 16, None, None, 0, None)
+    rc = L.xmc_wordregion_forward(0, 16, 16, None, 8, 2, 5, 7, 64, 5.0, 16, 16, 16, None, None, None, 0, None)
     assert rc == 1 and b"Rpad" in L.xmc_last_error()
-    rc = L.xmc_wordregion_forward(0, 16, 16, None, 8, 2, 5, 16, 96, 5.0, 16, 16, 16, None, None, 0, None)
+    rc = L.xmc_wordregion_forward(0, 16, 16, None, 8, 2, 5, 16, 96, 5.0, 16, 16, 16, None, None, None, 0, None)
     assert rc == 2 and b"unsupported" in L.xmc_last_error()
     rc = L.xmc_cosine_scores(8, 16, 4, 4, 8, 0, 16, None, None, None)
     assert rc == 3
