@@ -23,7 +23,7 @@ hook(0)
 tr = ops.last_workspace[64:64 + 4 * 64 * 4 * 8].view(torch.int64).view(4, 64, 4).cpu()
 t0 = int(tr[1, 0, 0])
 print("chunk | MMA: SW(g+1) issue start, XY(g) ready, dQ/dK(g) issued, end | arith(g): sw ready, consumed, done | loop(g): XY stored, arith(g+1) done, dk ready, drain done")
-for g_ in range(4, 24):
+for g_ in range(1, 60):
     m = [int(v) - t0 for v in tr[0, g_]]
     a = [int(v) - t0 for v in tr[1, g_]]
     e = [int(v) - t0 for v in tr[2, g_]]

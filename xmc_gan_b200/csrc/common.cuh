@@ -43,6 +43,15 @@ __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
   float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
   return make_float4(a.x, a.y, b.x, b.y);
 }
+// read-only (non-coherent) variants: the compiler may hoist them over stores to other buffers
+__device__ __forceinline__ float4 ld4_nc(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4_nc(const __nv_bfloat16* p) {
+  uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+  __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+  __nv_bfloat162 hi = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+  float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
   __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);

@@ -120,13 +120,39 @@ __global__ void __launch_bounds__(256) norm_tr_bwd_kernel(const TX* __restrict__
       continue;
     }
     const size_t row = (size_t)irow * D;
-    float proj = 0.f;
-    for (int d = lane; d < D; d += 32) proj = fmaf(ld1(xn + row + d), dxn[row + d], proj);
-    proj = warp_sum(proj);
     const float n = norm[(size_t)b * Lpad + l];
     const bool clamped = n <= kEps;               // x/eps is linear: no projection, no norm path
     const float inv = 1.f / n;
     const float dn = (dnorm && !clamped) ? dnorm[(size_t)b * Lpad + l] : 0.f;
+    if (D % 128 == 0 && D <= 512) {
+      // one pass: each lane keeps its 4-element groups of the row in registers (128-bit loads)
+      float4 xh[4], g[4];
+      float proj = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int d = c * 128 + lane * 4;
+        if (d < D) {
+          xh[c] = ld4_nc(xn + row + d);
+          g[c] = __ldg(reinterpret_cast<const float4*>(dxn + row + d));
+          proj += dot4(xh[c], g[c]);
+        }
+      }
+      proj = clamped ? 0.f : warp_sum(proj);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int d = c * 128 + lane * 4;
+        if (d < D) {
+          tile[(d + 0) * (kLT + 1) + r] = (g[c].x - xh[c].x * proj) * inv + dn * xh[c].x;
+          tile[(d + 1) * (kLT + 1) + r] = (g[c].y - xh[c].y * proj) * inv + dn * xh[c].y;
+          tile[(d + 2) * (kLT + 1) + r] = (g[c].z - xh[c].z * proj) * inv + dn * xh[c].z;
+          tile[(d + 3) * (kLT + 1) + r] = (g[c].w - xh[c].w * proj) * inv + dn * xh[c].w;
+        }
+      }
+      continue;
+    }
+    float proj = 0.f;
+    for (int d = lane; d < D; d += 32) proj = fmaf(ld1(xn + row + d), dxn[row + d], proj);
+    proj = warp_sum(proj);
     if (clamped) proj = 0.f;
     for (int d = lane; d < D; d += 32) {
       float xh = ld1(xn + row + d);

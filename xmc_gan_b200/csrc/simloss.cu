@@ -90,15 +90,29 @@ __global__ void __launch_bounds__(kSimThreads) sim_fwd_kernel(SimParams p) {
   const bool xi_ok = xi < NX;
   Stat st; st.init();
 
+  // the streamed vector of the NEXT iteration is fetched before this one is consumed (the loop is
+  // otherwise a chain of exposed L2 latencies)
+  auto fetch = [&](int y, float4 (&yv)[DCH]) {
+#pragma unroll
+    for (int c = 0; c < DCH; ++c) {
+      const int col = c * 128 + lane * 4;
+      yv[c] = (y < NY && col < p.D) ? ld4_nc(Y + (size_t)y * p.D + col) : make_float4(0, 0, 0, 0);
+    }
+  };
+  float4 ynext[DCH];
+  fetch(warp, ynext);
   for (int y = warp; y < NY; y += kSimWarps) {
+    float4 ycur[DCH];
+#pragma unroll
+    for (int c = 0; c < DCH; ++c) ycur[c] = ynext[c];
+    fetch(y + kSimWarps, ynext);
     float dots[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) dots[r] = 0.f;
     float nn = 0.f;
 #pragma unroll
     for (int c = 0; c < DCH; ++c) {
-      int col = c * 128 + lane * 4;
-      float4 yv = (col < p.D) ? ld4(Y + (size_t)y * p.D + col) : make_float4(0, 0, 0, 0);
+      const float4 yv = ycur[c];
       nn += dot4(yv, yv);
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) dots[r] += dot4(yv, xr[r][c]);
@@ -201,19 +215,25 @@ __global__ void __launch_bounds__(kSimThreads) sim_bwd_kernel(SimParams p) {
     }
     __syncwarp();
     const int cnt = min(32, NY - y0);
-    for (int t = 0; t < cnt; ++t) {
-      float4 yv[DCH];
+    // rows beyond cnt carry weight 0 in ds_sh (v = 0 above), so the loop runs in groups of 4 with the
+    // four streamed vectors fetched up front
+    for (int t0 = 0; t0 < cnt; t0 += 4) {
+      float4 yv[4][DCH];
 #pragma unroll
-      for (int c = 0; c < DCH; ++c) {
-        int col = c * 128 + lane * 4;
-        yv[c] = (col < p.D) ? ld4(Y + (size_t)(y0 + t) * p.D + col) : make_float4(0, 0, 0, 0);
-      }
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r) {
-        const float w = ds_sh[warp][r][t];
+        for (int c = 0; c < DCH; ++c) {
+          const int col = c * 128 + lane * 4;
+          yv[u][c] = (t0 + u < cnt && col < p.D) ? ld4_nc(Y + (size_t)(y0 + t0 + u) * p.D + col) : make_float4(0, 0, 0, 0);
+        }
 #pragma unroll
-        for (int c = 0; c < DCH; ++c) fma4(acc[r][c], w, yv[c]);
-      }
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          const float w = ds_sh[warp][r][t0 + u];
+#pragma unroll
+          for (int c = 0; c < DCH; ++c) fma4(acc[r][c], w, yv[u][c]);
+        }
     }
     __syncwarp();
   }

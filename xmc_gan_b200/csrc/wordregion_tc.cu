@@ -33,28 +33,63 @@ constexpr int TM = 128;            // word rows per tile (UMMA M)
 constexpr int CH = 64;             // region rows per chunk
 constexpr float kLog2eTc = 1.4426950408889634f;
 
-// Persistent schedule shared by both kernels.  Work items are (word tile, image) pairs, tile-major; the
-// grid is one CTA per SM and CTA k owns the contiguous span [k*per, (k+1)*per) of items.  A span is
-// walked as SEGMENTS = runs of images of one word tile (the stationary operand changes between
-// segments).  The number of word rows is read from device memory (compacted captions: the host does
-// not know it), so the span is computed in the kernel.
-struct Seg { int tile, img0, nimg; };
+// Persistent schedule shared by both kernels.  Work items are (word tile, image) pairs; the grid is one
+// CTA per SM and every CTA gets the same number of items (+-1).  A CTA walks SEGMENTS = runs of images
+// of ONE word tile (the stationary operand and its accumulator change only between segments); the
+// images of a segment are img0 + j*stride.
+// The images of a tile are dealt into s = ceil(grid / tiles) interleaved ROWS (row c = images c, c+s,
+// c+2s, ...; s = 1 when a CTA owns at least a whole tile), the item list is tile-major, row-major, and
+// CTA k owns the contiguous span [k*per, (k+1)*per) of it, which it walks starting at the first row
+// start inside the span (wrapping to the span's head at the end).  Every CTA therefore sweeps the
+// images in the same direction at nearly the same pace: at any moment the grid works on a window of a
+// few images whose region tiles and gradient rows stay L2-resident (a contiguous image split spreads
+// the grid over all images: +35% DRAM traffic, measured), and the load is still balanced to one item.
+// The number of word rows is read from device memory (compacted captions: the host does not know it),
+// so the schedule is computed in the kernel.
+struct Seg { int tile, img0, stride, nimg; };
 struct SegIter {
-  int item, end, Bi;
-  __device__ __forceinline__ bool next(Seg& s) {
-    if (item >= end) return false;
-    s.tile = item / Bi;
-    s.img0 = item - s.tile * Bi;
-    s.nimg = min(Bi - s.img0, end - item);
-    item += s.nimg;
+  int Bi, s, q, r;                 // rows per tile; Bi = q*s + r: rows c < r hold q+1 images, the others q
+  int P, Pend, P0, Pwrap, phase;
+  __device__ __forceinline__ void decode(int pos, int& tile, int& c, int& col, int& len) const {
+    tile = pos / Bi;
+    const int pp = pos - tile * Bi;
+    const int big = r * (q + 1);
+    if (pp < big) { c = pp / (q + 1); col = pp - c * (q + 1); len = q + 1; }
+    else { const int p2 = pp - big; c = r + p2 / q; col = p2 - (c - r) * q; len = q; }
+  }
+  __device__ __forceinline__ bool next(Seg& sg) {
+    if (P >= Pend) {
+      if (phase != 0) return false;
+      phase = 1; P = P0; Pend = Pwrap;
+      if (P >= Pend) return false;
+    }
+    int tile, c, col, len;
+    decode(P, tile, c, col, len);
+    const int cnt = min(len - col, Pend - P);
+    sg.tile = tile; sg.img0 = col * s + c; sg.stride = s; sg.nimg = cnt;
+    P += cnt;
     return true;
   }
 };
 __device__ __forceinline__ SegIter seg_iter(int NQ, int Bi) {
-  const int W = ((NQ + TM - 1) / TM) * Bi;
-  const int per = (W + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int b = min(W, (int)blockIdx.x * per);
-  return SegIter{b, min(W, b + per), Bi};
+  const int G = (int)gridDim.x, k = (int)blockIdx.x;
+  const int tiles = (NQ + TM - 1) / TM;
+  const int W = tiles * Bi;
+  const int per = (W + G - 1) / G;
+  SegIter it;
+  it.Bi = Bi;
+  it.s = tiles < G ? min(Bi, (G + tiles - 1) / max(tiles, 1)) : 1;
+  it.q = Bi / it.s; it.r = Bi - it.q * it.s;
+  it.P0 = min(W, k * per);
+  const int P1 = min(W, it.P0 + per);
+  int start = it.P0;
+  if (it.P0 < P1) {
+    int tile, c, col, len;
+    it.decode(it.P0, tile, c, col, len);
+    if (col != 0 && it.P0 + (len - col) < P1) start = it.P0 + (len - col);    // first row start inside the span
+  }
+  it.P = start; it.Pend = P1; it.Pwrap = start; it.phase = 0;
+  return it;
 }
 __device__ __forceinline__ int device_rows(const int* nq_dev, int NQ) { return nq_dev ? min(NQ, __ldg(nq_dev)) : NQ; }
 
@@ -168,7 +203,7 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
         Seg sg;
         while (it.next(sg)) {
           for (int ii = 0; ii < sg.nimg; ++ii) {
-            const int img = sg.img0 + ii;
+            const int img = sg.img0 + ii * sg.stride;
             for (int c = 0; c < nch; ++c) {
               const int n = min(CH, p.Rpad - c * CH);
               mbar_wait(kv_empty + st, ph, wc, 1);
@@ -381,7 +416,7 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
         const int m0 = sg.tile * TM;
         const int grow = m0 + row;
         for (int ii = 0; ii < sg.nimg; ++ii, ++ic) {
-          const int img = sg.img0 + ii;
+          const int img = sg.img0 + ii * sg.stride;
           mbar_wait(la_full + (ic & 1), (ic >> 1) & 1, wc, 10);
           const float* ex = ex_s + (ic & 1) * (2 * 2 * TM);
           const float l = ex[0 * TM + row] + ex[2 * TM + row];
@@ -510,6 +545,21 @@ static int make_rows_map(CUtensorMap* m, const void* base, int outer, int rows, 
   return XMC_OK;
 }
 
+// 2-D [rows, D] fp32 tensor map, box = 32 floats (128 B) x box_rows, 128B swizzle (reduce-add target)
+static int make_f32_rows_map(CUtensorMap* m, const void* base, int rows, int D, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  XMC_REQUIRE(enc != nullptr, XMC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)D * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XMC_REQUIRE(r == CUDA_SUCCESS, XMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return XMC_OK;
+}
+
 static int num_sms() {
   int dev = 0, n = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -534,8 +584,7 @@ static int launch_fwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
               ? reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
   p.trace = ((g_debug_dump & 4) && ws_bytes >= 64 + 4 * 64 * 4 * 8) ? reinterpret_cast<long long*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
   p.nq_dev = w.nq_dev;
-  const long long items = (long long)((w.NQ + TM - 1) / TM) * w.Bi;      // upper bound (all rows valid)
-  const int grid = (int)std::min<long long>(num_sms(), items);
+  const int grid = num_sms();                                             // persistent: the schedule adapts in the kernel
   XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_fwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   wr_fwd_tc_kernel<D><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(tm, tctx, p);
   return cuda_fail(cudaGetLastError(), "wr_fwd_tc_kernel launch");
@@ -580,10 +629,10 @@ int wordregion_tc_forward(const WrParams& p, int D, void* ws, size_t ws_bytes, c
 // Warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 elementwise WG0 (chunk cols 0-31), 8-11 elementwise WG1
 // (cols 32-63), 12-15 drain WG (dK^T rows d<128, then d>=128).  Registers are re-partitioned with
 // setmaxnreg (the sum must stay within the CTA's launch allocation, 512 x 128): 168 per elementwise
-// thread, 88 per drain thread, 80 per role thread.
+// thread, 96 per drain thread, 80 per role thread.
 // =====================================================================================================
 constexpr int kBwdThreads = 512;
-constexpr int kBwdRegsRole = 80, kBwdRegsEw = 168, kBwdRegsDrain = 88;
+constexpr int kBwdRegsRole = 80, kBwdRegsEw = 168, kBwdRegsDrain = 96;
 static_assert(128 * kBwdRegsRole + 256 * kBwdRegsEw + 128 * kBwdRegsDrain <= 512 * 128, "register pool of the CTA");
 
 template <int D>
@@ -611,7 +660,8 @@ struct TcBwdParams {
   const int* nq_dev;           // device count of valid word rows (<= NQ) or null
   int* err;
   int dbg_flags;               // perf experiments only (xmc_internal_set_debug_dump): 2 = skip the dK reduce
-  long long* trace;            // perf experiments only (flag 4): clock64 timeline of CTA (0,0), [4 roles][64 chunks][4]
+  long long* trace;            // perf experiments only: flag 4 = clock64 timeline of CTA 0, [4 roles][64 chunks][4];
+                               // flag 8 = per-CTA {start ns, end ns, segments, images} after it
 };
 
 // lane L returns sum over the warp of v[L] (31 shuffles instead of 160)
@@ -639,7 +689,7 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 template <int D>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_c,
-                 const __grid_constant__ CUtensorMap tm_k, TcBwdParams p) {
+                 const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_dq, TcBwdParams p) {
   using Cfg = BwdCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -680,7 +730,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_c); tma_prefetch_desc(&tm_k); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_c); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_dq); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -711,7 +761,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
           for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(Qs + kb * Cfg::kQBlock, &tm_q, kb * 64, m0, q_full);
           for (int ii = 0; ii < sg.nimg; ++ii, ++ic) {
-            const int img = sg.img0 + ii;
+            const int img = sg.img0 + ii * sg.stride;
             for (int c = 0; c < nch; ++c, ++x) {
               const int st = x & 1;
               const int n = min(CH, p.Rpad - c * CH);
@@ -732,7 +782,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               // buffer cannot be refilled earlier): pull them into L2 shortly before
               if (c == max(0, nch - 3) && ii + 1 < sg.nimg) {
 #pragma unroll
-                for (int kb = 0; kb < D / 64; ++kb) tma_prefetch_l2_3d(&tm_c, kb * 64, m0, img + 1);
+                for (int kb = 0; kb < D / 64; ++kb) tma_prefetch_l2_3d(&tm_c, kb * 64, m0, img + sg.stride);
               }
             }
           }
@@ -859,9 +909,12 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       int x = 0, seg = 0;
       SegIter it = seg_iter(NQ, p.Bi);
       Seg sg;
+      long long* cta_log = (p.dbg_flags & 8) && tracer ? p.trace + 4 * 64 * 4 + 4 * (long long)blockIdx.x : nullptr;
+      if (cta_log) { cta_log[0] = (long long)global_ns(); cta_log[2] = 0; cta_log[3] = 0; }
       while (it.next(sg)) {
         const int grow = sg.tile * TM + row;
         const int G = sg.nimg * nch;
+        if (cta_log) { cta_log[2] += 1; cta_log[3] += sg.nimg; }
         // ---- arithmetic of one chunk: S,W -> X,Y (packed bf16, registers) and the drnorm column sum ----
         int cm = 0, iim = 0;                      // chunk-in-image / image-in-segment of the arithmetic chunk
         float inv_l = 1.f, gam = 0.f, ngrl = 0.f;
@@ -871,7 +924,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           if (cm == 0) {
             inv_l = 1.f; gam = 0.f; ngrl = 0.f;
             if (grow < NQ) {
-              const size_t o = (size_t)(sg.img0 + iim) * p.NQ + grow;
+              const size_t o = (size_t)(sg.img0 + iim * sg.stride) * p.NQ + grow;
               const float inv_cn = 1.f / fmaxf(__ldg(p.cnorm + o), kEps);
               inv_l = 1.f / __ldg(p.lsum + o);
               gam = __ldg(p.grel + o) * inv_cn;
@@ -940,7 +993,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         arithmetic();                                   // first chunk of the segment
         int c = 0, ii = 0;
         for (int g = 0; g < G; ++g, ++x) {
-          const int img = sg.img0 + ii;
+          const int img = sg.img0 + ii * sg.stride;
           const int n = min(CH, p.Rpad - c * CH);
           const bool active = col0 < n;
           const int r0 = c * CH + col0;
@@ -966,11 +1019,13 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           if (tracer) XMC_TRACE(2, x, 2);
           if (++c == nch) { c = 0; ++ii; }
         }
-        // ---- dQ of this segment's word tile (summed over its images) ----
+        // ---- dQ of this segment's word tile (summed over its images): TMEM -> swizzled fp32 boxes in the
+        //      (now dead) X|Y bytes -> TMA reduce-add into dqn; warpgroup h owns columns [128h, 128h+128) ----
         mbar_wait(dq_full, seg & 1, wc, 22);
         tc_fence_after();
         {
-          float* dst = p.dqn + (size_t)grow * D + h * (D / 2);
+          uint8_t* box = Xs + h * Cfg::kXBytes;         // [128 rows x 32 fp32] = 16 KB, 128B-swizzled rows
+          const bool issuer = (q == 0 && lane == 0);
 #pragma unroll 1
           for (int blk = 0; blk < D / 64; ++blk) {
             uint32_t dv[32];
@@ -980,14 +1035,27 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               tc_fence_before();
               mbar_arrive(dq_empty);
             }
-            if (grow < NQ) {
+            if (blk > 0) {                              // the previous reduce has read the box
+              if (issuer) bulk_wait_read<0>();
+              named_bar_sync(2 + h, 128);
+            }
 #pragma unroll
-              for (int j = 0; j < 32; ++j) atomicAdd(dst + blk * 32 + j, __uint_as_float(dv[j]));
+            for (int u = 0; u < 8; ++u)
+              *reinterpret_cast<uint4*>(box + row * 128 + ((u ^ (row & 7)) << 4)) = make_uint4(dv[4 * u], dv[4 * u + 1], dv[4 * u + 2], dv[4 * u + 3]);
+            fence_proxy_async_smem();
+            named_bar_sync(2 + h, 128);
+            if (issuer) {
+              tma_reduce_add_2d(&tm_dq, box, h * (D / 2) + blk * 32, sg.tile * TM);   // rows past the buffer are clipped
+              bulk_commit();
             }
           }
+          if (issuer) bulk_wait_read<0>();              // X|Y are rewritten by the next segment
+          named_bar_sync(2 + h, 128);
         }
         ++seg;
       }
+      if (q == 0 && lane == 0) bulk_wait<0>();          // all dQ reductions performed before exit
+      if (cta_log) cta_log[1] = (long long)global_ns();
     }
   } else {
     setmaxnreg_dec<kBwdRegsDrain>();
@@ -1010,7 +1078,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (tracer) XMC_TRACE(3, x, 0);
 #pragma unroll
             for (int h = 0; h < Cfg::kTilesD; ++h) {
-              float* dst0 = p.dkn + ((size_t)(sg.img0 + ii) * p.Rpad + c * CH) * D + h * 128 + row;
+              float* dst0 = p.dkn + ((size_t)(sg.img0 + ii * sg.stride) * p.Rpad + c * CH) * D + h * 128 + row;
               uint32_t dva[32], dvb[32];
               tmem_ld32(lane_base + Cfg::kColDK + h * CH, dva);            // rows of the chunk past n hold stale data:
               if (n > 32) tmem_ld32(lane_base + Cfg::kColDK + h * CH + 32, dvb);   // never added below
@@ -1047,7 +1115,8 @@ static int launch_bwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
   using Cfg = BwdCfg<D>;
   XMC_REQUIRE(ws && ws_bytes >= 64, XMC_ERR_WORKSPACE, "workspace too small (%zu bytes)", ws_bytes);
   XMC_REQUIRE(w.chat != nullptr, XMC_ERR_INVALID_ARG, "the tcgen05 backward needs the contexts saved by the forward (chat)");
-  CUtensorMap tq, tcm, tk;
+  CUtensorMap tq, tcm, tk, tdq;
+  if (int rc = make_f32_rows_map(&tdq, w.dqn, w.NQ, D, TM)) return rc;
   if (int rc = make_rows_map(&tq, w.qn, 0, w.NQ, D, TM)) return rc;
   if (int rc = make_rows_map(&tcm, w.chat, w.Bi, w.NQ, D, TM)) return rc;
   if (int rc = make_region_map(&tk, w.kn, w.Bi, w.Rpad, D)) return rc;
@@ -1057,12 +1126,12 @@ static int launch_bwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
   p.dqn = w.dqn; p.dkn = w.dkn; p.drnorm = w.drnorm;
   p.err = static_cast<int*>(ws);
   p.dbg_flags = g_debug_dump;
-  p.trace = ((g_debug_dump & 4) && ws_bytes >= 64 + 4 * 64 * 4 * 8) ? reinterpret_cast<long long*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
+  p.trace = ((g_debug_dump & 12) && ws_bytes >= 64 + (4 * 64 * 4 + 4 * 160) * 8) ? reinterpret_cast<long long*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
+  if (!p.trace) p.dbg_flags &= ~12;
   p.nq_dev = w.nq_dev;
-  const long long items = (long long)((w.NQ + TM - 1) / TM) * w.Bi;      // upper bound (all rows valid)
-  const int grid = (int)std::min<long long>(num_sms(), items);
+  const int grid = num_sms();                                             // persistent: the schedule adapts in the kernel
   XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_bwd_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  wr_bwd_tc_kernel<D><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(tq, tcm, tk, p);
+  wr_bwd_tc_kernel<D><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(tq, tcm, tk, tdq, p);
   return cuda_fail(cudaGetLastError(), "wr_bwd_tc_kernel launch");
 }
 

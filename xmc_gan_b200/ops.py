@@ -223,15 +223,14 @@ class CudaOps:
         """-> lsum, cnorm, rel [Bi, NQ] (+ chat [Bi, NQ, D] bf16 on the tcgen05 path when asked).
 
         nq_dev: device int32 holding the number of valid (compact) rows of qn; rows beyond it are
-        neither read nor written, so with it the statistics are zero-initialised."""
+        neither read nor written by any kernel of the path."""
         _cuda(qn, kn, rnorm)
         NQ, D = qn.shape
         Bi, Rpad, _ = kn.shape
         dev = qn.device
-        alloc = torch.zeros if nq_dev is not None else torch.empty
-        lsum = alloc(Bi, NQ, device=dev, dtype=torch.float32)
-        cnorm = alloc(Bi, NQ, device=dev, dtype=torch.float32)
-        rel = alloc(Bi, NQ, device=dev, dtype=torch.float32)
+        lsum = torch.empty(Bi, NQ, device=dev, dtype=torch.float32)
+        cnorm = torch.empty(Bi, NQ, device=dev, dtype=torch.float32)
+        rel = torch.empty(Bi, NQ, device=dev, dtype=torch.float32)
         chat = None
         if save_context and path == _lib.PATH_BF16_TCGEN05:
             chat = torch.empty(Bi, NQ, D, device=dev, dtype=torch.bfloat16)
@@ -273,7 +272,7 @@ class CudaOps:
         _cuda(rel, dscores)
         Bi, Bc = scores.shape
         NQs = rel.shape[1]
-        grel = torch.zeros_like(rel) if cap_ptr is not None else torch.empty_like(rel)
+        grel = torch.empty_like(rel)
         with torch.cuda.device_of(rel):
             _lib.check(self.L.xmc_word_scores_backward(_p(rel), _p(mask_u8), _p(cap_ptr), _p(scores), _p(dscores),
                                                        Bi, Bc, T, NQs, float(rho2), _p(grel), _stream()))
