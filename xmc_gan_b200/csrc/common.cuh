@@ -99,6 +99,11 @@ __device__ __forceinline__ int owner_row<4>(int lane) {
   return ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1);
 }
 
+template <>
+__device__ __forceinline__ int owner_row<2>(int lane) {
+  return (lane >> 4) & 1;
+}
+
 template <int N>
 __device__ __forceinline__ void fold_step(float (&v)[8], int lane, int bit) {
   // pairs (v[2k], v[2k+1]) -> v[k]; lanes with `bit` clear keep the even member.
@@ -113,8 +118,16 @@ __device__ __forceinline__ void fold_step(float (&v)[8], int lane, int bit) {
 
 template <int ROWS>
 __device__ __forceinline__ float warp_multi_sum(float (&v)[8], int lane) {
-  static_assert(ROWS == 8 || ROWS == 4, "ROWS");
-  if (ROWS == 8) {
+  static_assert(ROWS == 8 || ROWS == 4 || ROWS == 2, "ROWS");
+  if (ROWS == 2) {
+    fold_step<2>(v, lane, 16);
+    float t = v[0];
+    t += __shfl_xor_sync(0xffffffffu, t, 8);
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;
+  } else if (ROWS == 8) {
     fold_step<8>(v, lane, 16);
     fold_step<4>(v, lane, 8);
     fold_step<2>(v, lane, 4);

@@ -122,14 +122,14 @@ __global__ void __launch_bounds__(kSimThreads) sim_fwd_kernel(SimParams p) {
     const float s = warp_multi_sum<ROWS>(dots, lane) * invy;   // cosine(x_mine, y)
     if (xi_ok) {
       const int i = row_side ? xi : y, j = row_side ? y : xi;
-      if (row_side && (lane & 3) == 0) p.scores[(size_t)i * p.Bk + j] = s;
+      if (row_side && (lane & (32 / ROWS - 1)) == 0) p.scores[(size_t)i * p.Bk + j] = s;
       st.add(p.scale * s, label_at(p.labels, p.Bk, i, j, p.diag));
     }
   }
 
   // combine the 8 warps' partial statistics
   __shared__ Stat sh[kSimWarps][ROWS];
-  if ((lane & 3) == 0 && (ROWS == 8 || (lane & 4) == 0)) sh[warp][mine] = st;
+  if ((lane & (32 / ROWS - 1)) == 0) sh[warp][mine] = st;
   __syncthreads();
   if (threadIdx.x < ROWS && r0 + (int)threadIdx.x < NX) {
     Stat t = sh[0][threadIdx.x];
@@ -453,14 +453,28 @@ static int launch_sim(int which, const SimParams& p, cudaStream_t st) {
   return cuda_fail(cudaGetLastError(), "similarity-loss kernel launch");
 }
 
+template <typename T, int DCH>
+static int dispatch_rows(int which, SimParams p, int max_rows, cudaStream_t st) {
+  // ROWS resident vectors per CTA.  The problem is small and latency-bound: take the largest ROWS
+  // (fewest passes over the streamed side) that still gives three quarters of the SMs a CTA, else the smallest.
+  auto ctas = [&](int r) { return (p.Bq + r - 1) / r + (p.Bk + r - 1) / r; };
+  int rows = 2;
+  for (int r = max_rows; r >= 2; r >>= 1)
+    if (ctas(r) >= 112) { rows = r; break; }
+  p.n_row_blocks = (p.Bq + rows - 1) / rows;
+  if (rows == 8) { if constexpr (DCH <= 2) return launch_sim<T, 8, DCH>(which, p, st); }
+  if (rows == 4) return launch_sim<T, 4, DCH>(which, p, st);
+  return launch_sim<T, 2, DCH>(which, p, st);
+}
+
 template <typename T>
 static int dispatch_dch(int which, SimParams p, cudaStream_t st) {
   const int dch = (p.D + 127) / 128;
-  // ROWS resident vectors per CTA: 8 while they fit in 64 registers, else 4
-  if (dch == 1) { p.n_row_blocks = (p.Bq + 7) / 8; return launch_sim<T, 8, 1>(which, p, st); }
-  if (dch == 2) { p.n_row_blocks = (p.Bq + 7) / 8; return launch_sim<T, 8, 2>(which, p, st); }
-  if (dch <= 4) { p.n_row_blocks = (p.Bq + 3) / 4; return launch_sim<T, 4, 4>(which, p, st); }
-  if (dch <= 6) { p.n_row_blocks = (p.Bq + 3) / 4; return launch_sim<T, 4, 6>(which, p, st); }
+  // at most 8 resident vectors while they fit in 64 registers, else 4
+  if (dch == 1) return dispatch_rows<T, 1>(which, p, 8, st);
+  if (dch == 2) return dispatch_rows<T, 2>(which, p, 8, st);
+  if (dch <= 4) return dispatch_rows<T, 4>(which, p, 4, st);
+  if (dch <= 6) return dispatch_rows<T, 6>(which, p, 4, st);
   set_error("D=%d unsupported (max 768)", p.D);
   return XMC_ERR_UNSUPPORTED;
 }

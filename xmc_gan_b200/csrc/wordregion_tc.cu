@@ -430,10 +430,10 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
           mbar_wait(c_full, ic & 1, wc, 8);
           tc_fence_after();
           if (issuer) XMC_TRACE(2, ic, 0);
-          float2 c2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
           uint32_t cva[32], cvb[32];
-          // 32 columns -> square-sum (packed fp32x2), bf16 -> four 16-byte units of the row's 128-byte box line.
-          // The saved tile is the UNSCALED sum C = l * c; the backward folds 1/(l ||c||) into its coefficients.
+          // Critical section (C blocks the next image's GEMM2): 32 columns -> bf16 -> four 16-byte units of
+          // the row's 128-byte box line, nothing else.  The saved tile is the UNSCALED sum C = l * c; the
+          // backward folds 1/(l ||c||) into its coefficients.  ||C|| is taken afterwards from the bf16 copy.
           auto consume = [&](const uint32_t (&cv)[32], int blk32) {
             if (p.dbg && blockIdx.x == 0 && ic == 0) {
 #pragma unroll
@@ -444,13 +444,9 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
             for (int u = 0; u < 4; ++u) {                     // 8 bf16 = one 16-byte unit
               uint32_t w[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 v = make_float2(__uint_as_float(cv[8 * u + 2 * e]), __uint_as_float(cv[8 * u + 2 * e + 1]));
-                c2[e & 1] = __ffma2_rn(v, v, c2[e & 1]);
-                w[e] = pack_bf16(v.x, v.y);
-              }
-              if (p.save_ctx)
-                *reinterpret_cast<uint4*>(line + ((((blk32 & 1) * 4 + u) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+              for (int e = 0; e < 4; ++e)
+                w[e] = pack_bf16(__uint_as_float(cv[8 * u + 2 * e]), __uint_as_float(cv[8 * u + 2 * e + 1]));
+              *reinterpret_cast<uint4*>(line + ((((blk32 & 1) * 4 + u) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           };
           tmem_ld32(lane_base + Cfg::kColC, cva);
@@ -468,6 +464,22 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
               if (issuer) XMC_TRACE(2, ic, 1);
             }
             consume(cvb, 2 * b2 + 1);
+          }
+          // off the critical path: ||C||^2 of this thread's row from its own bf16 copy (packed fp32x2)
+          float2 c2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll 2
+          for (int b = 0; b < Cfg::kOutBoxes; ++b) {
+            const uint8_t* line = out_s + b * Cfg::kOutBytes + row * 128;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint4 w = *reinterpret_cast<const uint4*>(line + ((u ^ (row & 7)) << 4));
+              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 v = make_float2(__uint_as_float(ww[e] << 16), __uint_as_float(ww[e] & 0xffff0000u));
+                c2[e & 1] = __ffma2_rn(v, v, c2[e & 1]);
+              }
+            }
           }
           if (p.save_ctx) {
             fence_proxy_async_smem();
