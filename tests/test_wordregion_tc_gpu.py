@@ -166,3 +166,94 @@ def test_compact_rows_match_dense_rows(B, D, T_, R):
     assert nerr(w1, w0) <= 2e-3, nerr(w1, w0)
     assert float(w1[1].abs().max()) == 0.0                 # padded words: exactly zero gradient
     assert float((w1 * mask.cuda()[:, None, :]).abs().max()) == 0.0
+
+
+def test_full_size_coco256_tc_matches_fp32_path():
+    """BASELINE config 2 at full size (B=256, T=18, R=17x17, D=256, caption lengths U{5..18}): the tcgen05
+    path (compacted rows, persistent schedule over 148 CTAs) against the fp32 CUDA-core path, which is itself
+    checked against the oracle at the sizes the oracle can run.  Plus linearity in the upstream gradient."""
+    from xmc_gan_b200 import train_gan as T
+    B, D, T_, R = 256, 256, 18, 289
+    words, regions, mask = word_inputs(B, D, T_, R, seed=2024, min_len=5)
+    wb, rb = words.bfloat16(), regions.bfloat16()
+    labels = T.make_labels(B, None, False)
+
+    def run(precision, scale):
+        r = rb.cuda().to(torch.float32 if precision == "fp32" else torch.bfloat16).requires_grad_()
+        w = wb.cuda().to(torch.float32 if precision == "fp32" else torch.bfloat16).requires_grad_()
+        loss = T.word_loss(r.view(B, D, 17, 17), w, mask.cuda(), labels, False, precision=precision)
+        (loss * scale).backward()
+        return loss.detach(), r.grad.float(), w.grad.float()
+
+    l_tc, r_tc, w_tc = run("bf16", 1.0)
+    l_32, r_32, w_32 = run("fp32", 1.0)
+    assert torch.isfinite(l_tc) and torch.isfinite(r_tc).all() and torch.isfinite(w_tc).all()
+    assert lerr(l_tc, l_32) <= TOL_BF16, (float(l_tc), float(l_32))
+    assert nerr(r_tc, r_32) <= TOL_BF16, nerr(r_tc, r_32)
+    assert nerr(w_tc, w_32) <= TOL_BF16, nerr(w_tc, w_32)
+    _, r_3, w_3 = run("bf16", 3.0)                         # gradients are linear in grad_out
+    assert nerr(r_3, 3.0 * r_tc) <= 6e-3, nerr(r_3, 3.0 * r_tc)      # bf16 outputs + atomic summation order
+    assert nerr(w_3, 3.0 * w_tc) <= 6e-3, nerr(w_3, 3.0 * w_tc)
+    assert float((w_tc * mask.cuda()[:, None, :]).abs().max()) == 0.0
+
+
+def test_more_word_tiles_than_sms(ops):
+    """Rows local / columns gathered, as one rank of the 8-GPU run sees it: 1100 captions x 18 words = 155 word
+    tiles (> 148 SMs: full rounds plus a shared last round of the persistent schedule) against 40 images."""
+    from xmc_gan_b200 import _lib
+    Bc, Bi, D, T_, R = 1100, 40, 256, 18, 100
+    g = torch.Generator().manual_seed(5)
+    words = torch.randn(Bc, D, T_, generator=g)
+    regions = torch.randn(Bi, D, R, generator=g) + 0.3 * words[:Bi, :, torch.randint(0, T_, (R,), generator=g)]
+    lens = torch.randint(5, T_ + 1, (Bc,), generator=g)
+    mask = (torch.arange(T_).unsqueeze(0) >= lens.unsqueeze(1)).to(torch.uint8).cuda()
+    Rpad = (R + 15) // 16 * 16
+    row_of, cap_ptr = ops.word_rows_compact(mask)
+    nq = cap_ptr[Bc:]
+    qc, _ = ops.normalize_transpose(words.cuda(), T_, torch.bfloat16, row_of=row_of)
+    qd, _ = ops.normalize_transpose(words.cuda(), T_, torch.bfloat16)
+    kn, rnorm = ops.normalize_transpose(regions.cuda(), Rpad, torch.bfloat16)
+    qc, qd = qc.view(Bc * T_, D), qd.view(Bc * T_, D)
+    l1, c1, r1, chat = ops.wordregion_forward(_lib.PATH_BF16_TCGEN05, qc, kn, rnorm, R, 5.0, save_context=True, nq_dev=nq)
+    assert _err_word(ops) == 0
+    l0, c0, r0, _ = ops.wordregion_forward(_lib.PATH_FP32_SIMT, qd.float(), kn.float(), rnorm, R, 5.0)
+    valid = row_of >= 0
+    idx = row_of[valid].long()
+    assert nerr(r1[:, idx], r0[:, valid]) < 5e-3
+    assert nerr(l1[:, idx], l0[:, valid]) < 5e-3
+    grel_d = torch.randn(Bi, Bc * T_, generator=g).cuda() * 0.1 * valid.float()
+    grel_c = torch.zeros_like(grel_d)
+    grel_c[:, idx] = grel_d[:, valid]
+    dq1, dk1, dr1 = ops.wordregion_backward(_lib.PATH_BF16_TCGEN05, qc, kn, rnorm, R, 5.0, l1, c1, r1, grel_c, chat, nq_dev=nq)
+    assert _err_word(ops) == 0
+    dq0, dk0, dr0 = ops.wordregion_backward(_lib.PATH_FP32_SIMT, qd.float(), kn.float(), rnorm, R, 5.0, l0, c0, r0, grel_d)
+    assert nerr(dq1[idx], dq0[valid]) < 1.5e-2
+    assert nerr(dk1, dk0) < 1.5e-2
+    assert nerr(dr1, dr0) < 1.5e-2
+
+
+@pytest.mark.parametrize("B,D,T_,R", [(6, 256, 18, 40), (5, 128, 7, 17), (9, 256, 12, 289), (4, 256, 18, 64)])
+def test_never_written_tmem_columns_are_not_read(B, D, T_, R):
+    """Chunks narrower than 64 regions leave TMEM columns the MMAs never write.  With tensor memory filled
+    with NaNs first (debug flag 16) the result must not change: nothing stale may leak into the sums."""
+    from xmc_gan_b200 import _lib
+    from xmc_gan_b200 import train_gan as T
+    hook = _lib.lib().xmc_internal_set_debug_dump
+    hook.argtypes, hook.restype = [ctypes.c_int], None
+    words, regions, mask = word_inputs(B, D, T_, R, seed=B + R)
+    labels = T.make_labels(B, None, False)
+    out = []
+    for flag in (0, 16):
+        hook(flag)
+        try:
+            r = regions.bfloat16().cuda().requires_grad_()
+            w = words.bfloat16().cuda().requires_grad_()
+            loss = T.word_loss(r, w, mask.cuda(), labels, False, precision="bf16")
+            loss.backward()
+            torch.cuda.synchronize()
+            out.append((loss.detach(), r.grad.float(), w.grad.float()))
+        finally:
+            hook(0)
+    (l0, r0, w0), (l1, r1, w1) = out
+    assert torch.isfinite(l1) and torch.isfinite(r1).all() and torch.isfinite(w1).all()
+    assert lerr(l1, l0) <= 1e-6 and nerr(r1, r0) <= 2e-3 and nerr(w1, w0) <= 2e-3

@@ -120,6 +120,7 @@ struct TcFwdParams {
   float* lsum; float* cnorm; float* rel;
   int save_ctx;                // context sums C = l * c_t go out through tm_ctx (bf16 [Bi, NQ, D]) for the backward
   const int* nq_dev;           // device count of valid word rows (<= NQ, the row stride of every buffer) or null
+  int poison;                  // tests (debug flag 16): fill TMEM with NaNs first, so that a read of a never-written column shows
   int* err;
   float* dbg;                  // optional: S chunk 0 and C of the first tile/image (tests)
   long long* trace;            // perf experiments only (flag 4): clock64 timeline of CTA (0,0), [4 roles][64][4]
@@ -142,6 +143,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// tests only: every TMEM column of this warp's lane quadrant <- quiet NaNs
+__device__ __forceinline__ void poison_tmem(int quadrant) {
+  uint32_t v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0x7fc00000u;
+  for (int c = 0; c < 512; c += 16) tmem_st16((static_cast<uint32_t>(quadrant * 32) << 16) + c, v);
+  tmem_wait_st();
+  tc_fence_before();
 }
 
 template <int D>
@@ -183,6 +194,8 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
     mbar_init(c_full, 1); mbar_init(c_empty, 128); mbar_init(q_ready, 256);
     fence_barrier_init();
   }
+  // region-norm slots past a chunk's rows are never loaded: make them finite (they multiply weights that are 0)
+  for (int i = threadIdx.x; i < Cfg::kStages * CH; i += kFwdThreads) rn_s[i] = 0.f;
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_ctx); }
   tc_fence_before();
@@ -192,6 +205,7 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
   // column 0; using the literal keeps every TMEM address an immediate for the MMA issue path.
   constexpr uint32_t tmem = 0;
   if (threadIdx.x == 0 && *tmem_slot != 0) { *abort_flag = 1; if (p.err) atomicExch(p.err, 999); }
+  if (p.poison && warp >= 12) poison_tmem(warp & 3);
   __syncthreads();
 
   {
@@ -358,9 +372,13 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
                   pv[2 * j2 + 1] = ex2_approx(arg.y);
                 }
               }
-              if (r0 + 32 > p.R) {                            // ragged tail of the image: padded columns weigh 0
-#pragma unroll
-                for (int j = 0; j < 32; ++j) pv[j] = (r0 + j) < p.R ? pv[j] : 0.f;
+              if (r0 + 32 > p.R) {                            // ragged tail of the image: padded columns weigh 0;
+#pragma unroll                                                // columns past the MMA's N hold stale TMEM bits (maybe NaN)
+                for (int j = 0; j < 32; ++j) {
+                  const bool valid = (r0 + j) < p.R;
+                  pv[j] = valid ? pv[j] : 0.f;
+                  sv[j] = valid ? sv[j] : 0u;
+                }
               }
               if (threadIdx.x == 128) XMC_TRACE(3, x, 0);
               // phase 2: l += p, p' = p * ||v_r||, a += p' s, pack (packed fp32x2, two chains each)
@@ -591,6 +609,7 @@ static int launch_fwd_tc(const WrParams& w, void* ws, size_t ws_bytes, cudaStrea
   p.rnorm = w.rnorm; p.NQ = w.NQ; p.Bi = w.Bi; p.R = w.R; p.Rpad = w.Rpad; p.rho1 = w.rho1;
   p.lsum = w.lsum; p.cnorm = w.cnorm; p.rel = w.rel;
   p.save_ctx = w.chat != nullptr;
+  p.poison = (g_debug_dump & 16) != 0;
   p.err = static_cast<int*>(ws);
   p.dbg = ((g_debug_dump & 1) && ws_bytes >= 64 + sizeof(float) * (size_t)(TM * CH + TM * D))
               ? reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64) : nullptr;
@@ -671,7 +690,7 @@ struct TcBwdParams {
   float* dqn; float* dkn; float* drnorm;
   const int* nq_dev;           // device count of valid word rows (<= NQ) or null
   int* err;
-  int dbg_flags;               // perf experiments only (xmc_internal_set_debug_dump): 2 = skip the dK reduce
+  int dbg_flags;               // + 16 (tests): fill TMEM with NaNs first               // perf experiments only (xmc_internal_set_debug_dump): 2 = skip the dK reduce
   long long* trace;            // perf experiments only: flag 4 = clock64 timeline of CTA 0, [4 roles][64 chunks][4];
                                // flag 8 = per-CTA {start ns, end ns, segments, images} after it
 };
@@ -741,6 +760,8 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     mbar_init(dk_full, 1); mbar_init(dk_empty, 128); mbar_init(dq_full, 1); mbar_init(dq_empty, 256);
     fence_barrier_init();
   }
+  // region-norm slots past a chunk's rows are never loaded: make them finite (they multiply weights that are 0)
+  for (int i = threadIdx.x; i < 2 * CH; i += kBwdThreads) rn_s[i] = 0.f;
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_c); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_dq); }
   tc_fence_before();
@@ -750,6 +771,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   // column 0; using the literal keeps every TMEM address an immediate for the MMA issue path.
   constexpr uint32_t tmem = 0;
   if (threadIdx.x == 0 && *tmem_slot != 0) { *abort_flag = 1; if (p.err) atomicExch(p.err, 999); }
+  if ((p.dbg_flags & 16) && warp >= 12) poison_tmem(warp & 3);
   __syncthreads();
 
   // Running counters used by every role (never reset across segments): x = chunk index (region stage
@@ -976,10 +998,11 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
                     const int j = j4 * 4 + u;
-                    const float s = __uint_as_float(sv[j]);
-                    const float w = __uint_as_float(wv[j]);
-                    float al = ex2_approx(fmaf(c1, s, -c1)) * inv_l;                       // alpha
-                    if (!kFull) al = (r0 + hf * 16 + j) < p.R ? al : 0.f;                  // padded region rows: alpha = 0 zeroes X, Y, z
+                    // padded region rows: s = w = alpha = 0 zeroes X, Y, z (columns past the MMA's N hold stale TMEM bits)
+                    const bool valid = kFull || (r0 + hf * 16 + j) < p.R;
+                    const float s = valid ? __uint_as_float(sv[j]) : 0.f;
+                    const float w = valid ? __uint_as_float(wv[j]) : 0.f;
+                    const float al = valid ? ex2_approx(fmaf(c1, s, -c1)) * inv_l : 0.f;   // alpha
                     const float alp = al * mrv[u];                                         // alpha' = alpha * ||v_r||
                     const float dap = fmaf(ngrl, w, gam * s);                              // d loss / d alpha'
                     xv[u] = alp * fmaf(p.rho1, dap, gam);                                  // dS + gamma*alpha'
