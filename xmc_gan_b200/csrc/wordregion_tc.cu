@@ -145,6 +145,16 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// columns [c0, c0 + n) of this warp's lane quadrant <- 0: score columns beyond a narrow chunk's N are never
+// written by the MMAs but are read (and multiplied by a zero weight), so they must hold finite bits
+__device__ __forceinline__ void zero_tmem(int quadrant, int c0, int n) {
+  uint32_t v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0u;
+  for (int c = 0; c < n; c += 16) tmem_st16((static_cast<uint32_t>(quadrant * 32) << 16) + c0 + c, v);
+  tmem_wait_st();
+  tc_fence_before();
+}
 // tests only: every TMEM column of this warp's lane quadrant <- quiet NaNs
 __device__ __forceinline__ void poison_tmem(int quadrant) {
   uint32_t v[16];
@@ -205,7 +215,10 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
   // column 0; using the literal keeps every TMEM address an immediate for the MMA issue path.
   constexpr uint32_t tmem = 0;
   if (threadIdx.x == 0 && *tmem_slot != 0) { *abort_flag = 1; if (p.err) atomicExch(p.err, 999); }
-  if (p.poison && warp >= 12) poison_tmem(warp & 3);
+  if (warp >= 12) {
+    if (p.poison) poison_tmem(warp & 3);
+    zero_tmem(warp & 3, Cfg::kColS0, 2 * CH);
+  }
   __syncthreads();
 
   {
@@ -372,13 +385,11 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
                   pv[2 * j2 + 1] = ex2_approx(arg.y);
                 }
               }
-              if (r0 + 32 > p.R) {                            // ragged tail of the image: padded columns weigh 0;
-#pragma unroll                                                // columns past the MMA's N hold stale TMEM bits (maybe NaN)
-                for (int j = 0; j < 32; ++j) {
-                  const bool valid = (r0 + j) < p.R;
-                  pv[j] = valid ? pv[j] : 0.f;
-                  sv[j] = valid ? sv[j] : 0u;
-                }
+              if (r0 + 32 > p.R) {
+                // ragged tail of the image: padded columns weigh 0.  The scores of columns the MMA never wrote are
+                // finite (the S buffers are zeroed at kernel start and only ever hold cosines after that)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) pv[j] = (r0 + j) < p.R ? pv[j] : 0.f;
               }
               if (threadIdx.x == 128) XMC_TRACE(3, x, 0);
               // phase 2: l += p, p' = p * ||v_r||, a += p' s, pack (packed fp32x2, two chains each)
@@ -771,7 +782,10 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   // column 0; using the literal keeps every TMEM address an immediate for the MMA issue path.
   constexpr uint32_t tmem = 0;
   if (threadIdx.x == 0 && *tmem_slot != 0) { *abort_flag = 1; if (p.err) atomicExch(p.err, 999); }
-  if ((p.dbg_flags & 16) && warp >= 12) poison_tmem(warp & 3);
+  if (warp >= 12) {
+    if (p.dbg_flags & 16) poison_tmem(warp & 3);
+    zero_tmem(warp & 3, Cfg::kColS, 2 * CH);
+  }
   __syncthreads();
 
   // Running counters used by every role (never reset across segments): x = chunk index (region stage
@@ -998,11 +1012,12 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
                     const int j = j4 * 4 + u;
-                    // padded region rows: s = w = alpha = 0 zeroes X, Y, z (columns past the MMA's N hold stale TMEM bits)
-                    const bool valid = kFull || (r0 + hf * 16 + j) < p.R;
-                    const float s = valid ? __uint_as_float(sv[j]) : 0.f;
-                    const float w = valid ? __uint_as_float(wv[j]) : 0.f;
-                    const float al = valid ? ex2_approx(fmaf(c1, s, -c1)) * inv_l : 0.f;   // alpha
+                    const float s = __uint_as_float(sv[j]);
+                    const float w = __uint_as_float(wv[j]);
+                    float al = ex2_approx(fmaf(c1, s, -c1)) * inv_l;                       // alpha
+                    // padded region rows: alpha = 0 zeroes X, Y, z.  s, w of columns the MMAs never wrote are
+                    // finite: the score columns are zeroed at kernel start and only ever hold cosines after that
+                    if (!kFull) al = (r0 + hf * 16 + j) < p.R ? al : 0.f;
                     const float alp = al * mrv[u];                                         // alpha' = alpha * ||v_r||
                     const float dap = fmaf(ngrl, w, gam * s);                              // d loss / d alpha'
                     xv[u] = alp * fmaf(p.rho1, dap, gam);                                  // dS + gamma*alpha'
@@ -1107,7 +1122,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       while (it.next(sg)) {
         for (int ii = 0; ii < sg.nimg; ++ii) {
           for (int c = 0; c < nch; ++c, ++x) {
-            const int n = min(CH, p.Rpad - c * CH);
+            const int n = min(CH, p.R - c * CH);            // real regions of the chunk: padding rows get no add
             mbar_wait(dk_full, x & 1, wc, 23);
             tc_fence_after();
             if (tracer) XMC_TRACE(3, x, 0);

@@ -191,7 +191,7 @@ class WordLossFn(torch.autograd.Function):
             m_all = comm.all_gather_cat(mask.detach().to(torch.uint8).contiguous())
         else:
             m_all = None
-        Rpad = _ceil_to(R, 16)
+        Rpad = _ceil_to(R, 16)                                     # zero rows up to the MMA's N granularity
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         use_tc_bwd = path == _lib.PATH_BF16_TCGEN05 and D in TC_BACKWARD_DIMS
         # Padding words never contribute (excluded from the log-sum-exp, zero gradient): on the tcgen05
