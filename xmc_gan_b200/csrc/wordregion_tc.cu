@@ -1003,29 +1003,36 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               }
               auto elementwise = [&](auto full_tag) {
                 constexpr bool kFull = decltype(full_tag)::value;   // every column is a real region: no predicates
+                const float2 cc = make_float2(c1, c1), ncc = make_float2(-c1, -c1);
+                const float2 il2 = make_float2(inv_l, inv_l), gam2 = make_float2(gam, gam);
+                const float2 ng2 = make_float2(ngrl, ngrl), rho2v = make_float2(p.rho1, p.rho1);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                   float4 mr = make_float4(1.f, 1.f, 1.f, 1.f);
                   if (has_rn) mr = *reinterpret_cast<const float4*>(wsm + hf * 16 + j4 * 4);
-                  const float mrv[4] = {mr.x, mr.y, mr.z, mr.w};
-                  float xv[4], yv[4];
+                  const float2 mr2[2] = {make_float2(mr.x, mr.y), make_float2(mr.z, mr.w)};
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const int j = j4 * 4 + u;
-                    const float s = __uint_as_float(sv[j]);
-                    const float w = __uint_as_float(wv[j]);
-                    float al = ex2_approx(fmaf(c1, s, -c1)) * inv_l;                       // alpha
+                  for (int u = 0; u < 2; ++u) {               // packed fp32x2 arithmetic on column pairs
+                    const int j = j4 * 4 + 2 * u;
+                    const float2 s2 = make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
+                    const float2 w2 = make_float2(__uint_as_float(wv[j]), __uint_as_float(wv[j + 1]));
+                    const float2 arg = __ffma2_rn(s2, cc, ncc);
+                    float2 al = __fmul2_rn(make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), il2);   // alpha
                     // padded region rows: alpha = 0 zeroes X, Y, z.  s, w of columns the MMAs never wrote are
                     // finite: the score columns are zeroed at kernel start and only ever hold cosines after that
-                    if (!kFull) al = (r0 + hf * 16 + j) < p.R ? al : 0.f;
-                    const float alp = al * mrv[u];                                         // alpha' = alpha * ||v_r||
-                    const float dap = fmaf(ngrl, w, gam * s);                              // d loss / d alpha'
-                    xv[u] = alp * fmaf(p.rho1, dap, gam);                                  // dS + gamma*alpha'
-                    yv[u] = ngrl * alp;
-                    z[hf * 16 + j] = al * dap;
+                    if (!kFull) {
+                      al.x = (r0 + hf * 16 + j) < p.R ? al.x : 0.f;
+                      al.y = (r0 + hf * 16 + j + 1) < p.R ? al.y : 0.f;
+                    }
+                    const float2 alp = __fmul2_rn(al, mr2[u]);                             // alpha' = alpha * ||v_r||
+                    const float2 dap = __ffma2_rn(ng2, w2, __fmul2_rn(gam2, s2));          // d loss / d alpha'
+                    const float2 xv = __fmul2_rn(alp, __ffma2_rn(rho2v, dap, gam2));       // dS + gamma*alpha'
+                    const float2 yv = __fmul2_rn(ng2, alp);
+                    const float2 zz = __fmul2_rn(al, dap);
+                    z[hf * 16 + j] = zz.x; z[hf * 16 + j + 1] = zz.y;
+                    xp[hf * 8 + j4 * 2 + u] = pack_bf16(xv.x, xv.y);
+                    yp[hf * 8 + j4 * 2 + u] = pack_bf16(yv.x, yv.y);
                   }
-                  xp[hf * 8 + j4 * 2 + 0] = pack_bf16(xv[0], xv[1]); xp[hf * 8 + j4 * 2 + 1] = pack_bf16(xv[2], xv[3]);
-                  yp[hf * 8 + j4 * 2 + 0] = pack_bf16(yv[0], yv[1]); yp[hf * 8 + j4 * 2 + 1] = pack_bf16(yv[2], yv[3]);
                 }
               };
               if (r0 + 32 <= p.R) elementwise(std::true_type{}); else elementwise(std::false_type{});
