@@ -968,18 +968,28 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         float inv_l = 1.f, gam = 0.f, ngrl = 0.f;
         uint32_t xp[16], yp[16];
         float colsum = 0.f;
+        // per-(image, word row) statistics of the NEXT image are fetched one image ahead: at the first chunk of
+        // an image the elementwise warps are on the critical path (the pipeline drains at image boundaries)
+        float pf_l = 1.f, pf_cn = 1.f, pf_g = 0.f, pf_rel = 0.f;
+        auto fetch_stats = [&](int ii_) {
+          if (grow < NQ && ii_ < sg.nimg) {
+            const size_t o = (size_t)(sg.img0 + ii_ * sg.stride) * p.NQ + grow;
+            pf_l = __ldg(p.lsum + o); pf_cn = __ldg(p.cnorm + o); pf_g = __ldg(p.grel + o); pf_rel = __ldg(p.rel + o);
+          }
+        };
+        fetch_stats(0);
         auto arithmetic = [&]() {
           if (cm == 0) {
             inv_l = 1.f; gam = 0.f; ngrl = 0.f;
             if (grow < NQ) {
-              const size_t o = (size_t)(sg.img0 + iim * sg.stride) * p.NQ + grow;
-              const float inv_cn = 1.f / fmaxf(__ldg(p.cnorm + o), kEps);
-              inv_l = 1.f / __ldg(p.lsum + o);
-              gam = __ldg(p.grel + o) * inv_cn;
+              const float inv_cn = 1.f / fmaxf(pf_cn, kEps);
+              inv_l = 1.f / pf_l;
+              gam = pf_g * inv_cn;
               // the saved context is the unscaled sum C = l c (not the unit vector): W = C K^T and the
               // Chat^T Y term both carry 1 / (l ||c||), folded into the coefficient that multiplies them
-              ngrl = -gam * __ldg(p.rel + o) * inv_cn * inv_l;
+              ngrl = -gam * pf_rel * inv_cn * inv_l;
             }
+            fetch_stats(iim + 1);
           }
           const int n = min(CH, p.Rpad - cm * CH);
           const int r0 = cm * CH + col0;
