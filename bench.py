@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=B_LOCAL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -209,57 +210,145 @@ def main():
             ms = float(t)
         return ms
 
-    # ---- device-resident throughput ---------------------------------------------------------
+    # ---- per-kernel CUDA-event times (eager launches; feeds the roofline) --------------------
     for _ in range(W):
         step(devin)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     l0 = ops.launches
     ops.enable_timing(True)
-    ms = timed(lambda: step(devin), K)
+    ms_eager = timed(lambda: step(devin), K)
     kern = ops.kernel_ms()
     ops.enable_timing(False)
     launches = (ops.launches - l0) // K
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step(devin)
+    host_ms = (time.perf_counter() - t0) / K * 1e3            # host time to ENQUEUE one step (python + launches)
+    torch.cuda.synchronize()
+
+    # ---- the step as a CUDA graph -----------------------------------------------------------------
+    # The same public-API calls (make_labels / sent_loss / img_loss / word_loss + backward), captured once with
+    # torch.cuda.graph and replayed: a step is ~35 launches of 2-700 us kernels and the host needs about as
+    # long to enqueue them as the GPU needs to run them, so an eager loop measures the host.  Nothing in the
+    # path synchronises with the host (the compacted word-row count stays on the device), which is what makes
+    # the capture possible.  --no-graph (or a failed capture) falls back to eager launches.
+    def capture(x_static):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step(x_static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss, grads = step(x_static)
+        return g, loss, grads
+
+    graphs = None
+    mode = "eager"
+    # Single GPU only: with N > 1 the per-rank work doubles with N while the host time stays, so eager launches
+    # are GPU-bound there (and a 2-rank capture with the NCCL collectives inside hung in a replay on this pool).
+    if not args.no_graph and world == 1:
+        try:
+            sets = [devin, {k: v.clone() for k, v in devin.items()}]
+            graphs = [capture(x) for x in sets]
+            for g, _, _ in graphs:
+                g.replay()
+            torch.cuda.synchronize()
+            ref_loss, ref_grads = step(devin)                   # the replay must reproduce the eager step
+            for g_loss, g_grads in ((graphs[0][1], graphs[0][2]), (graphs[1][1], graphs[1][2])):
+                ok = abs(float(g_loss.detach()) - float(ref_loss.detach())) <= 1e-4 * abs(float(ref_loss.detach()))
+                for a, b in zip(g_grads, ref_grads):
+                    ok = ok and float((a.float() - b.float()).norm()) <= 1e-2 * float(b.float().norm())   # atomic summation order
+                if not ok:
+                    raise RuntimeError("graph replay does not reproduce the eager step")
+            mode = "cuda-graph"
+        except Exception as e:                                  # noqa: BLE001 - any capture problem: measure eagerly
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+            graphs = None
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if graphs is not None:
+        for _ in range(W):
+            graphs[0][0].replay()
+        ms = timed(graphs[0][0].replay, K)
+    else:
+        ms = timed(lambda: step(devin), K)
     clocks = sampler.summary()
 
     # ---- end to end: pinned host -> device, loss -> host -------------------------------------
-    # Every step copies ITS inputs from pinned host memory (copy stream, issued one step ahead: what a
-    # DataLoader with pinned memory and non_blocking copies does) and its loss is copied back to pinned
-    # host memory; the host waits for a loss one step late, so the launch of step k+1 overlaps the
-    # execution of step k.  No L2 flush here: the inputs arrive by DMA each step.
+    # Every step copies ITS inputs from pinned host memory (copy stream, issued one step ahead into the other
+    # of two input sets: what a DataLoader with pinned memory and non_blocking copies does) and its loss is
+    # copied back to pinned host memory; the host reads a loss one step late, so enqueueing step k+1 overlaps
+    # the execution of step k.  No L2 flush here: the inputs arrive by DMA each step.
     h2d = sum(v.numel() * v.element_size() for v in pinned.values())
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
 
-    def issue_h2d():
-        with torch.cuda.stream(copy_stream):
-            x = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return x, ev
+    if graphs is not None:
+        def e2e_loop(steps):
+            consumed = [None, None]                             # event: the replay that read input set i has finished
+            copied = [None, None]
 
-    def e2e_loop(steps):
-        pending = issue_h2d()
-        done = [None, None]
-        out = 0.0
-        for k in range(steps):
-            x, ev = pending
+            def issue_h2d(i):
+                with torch.cuda.stream(copy_stream):
+                    if consumed[i] is not None:
+                        copy_stream.wait_event(consumed[i])
+                    for k, v in pinned.items():
+                        sets[i][k].copy_(v, non_blocking=True)
+                    copied[i] = torch.cuda.Event()
+                    copied[i].record(copy_stream)
+
+            issue_h2d(0)
+            done = [None, None]
+            for k in range(steps):
+                i = k & 1
+                if k + 1 < steps:
+                    issue_h2d(i ^ 1)
+                main_stream.wait_event(copied[i])
+                graphs[i][0].replay()
+                consumed[i] = torch.cuda.Event()
+                consumed[i].record(main_stream)
+                loss_host[i].copy_(graphs[i][1].detach().float(), non_blocking=True)   # D2H read of the result
+                done[i] = torch.cuda.Event()
+                done[i].record(main_stream)
+                if done[i ^ 1] is not None:
+                    done[i ^ 1].synchronize()
+                    float(loss_host[i ^ 1])
+            done[(steps - 1) & 1].synchronize()
+            return float(loss_host[(steps - 1) & 1])
+    else:
+        def issue_h2d():
+            with torch.cuda.stream(copy_stream):
+                x = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return x, ev
+
+        def e2e_loop(steps):
             pending = issue_h2d()
-            main_stream.wait_event(ev)
-            for t in x.values():
-                t.record_stream(main_stream)
-            loss, _ = step(x)
-            slot = k & 1
-            loss_host[slot].copy_(loss.detach().float(), non_blocking=True)   # D2H read of the result
-            d = torch.cuda.Event()
-            d.record(main_stream)
-            if done[slot ^ 1] is not None:                                    # the previous step's loss is on the host
-                done[slot ^ 1].synchronize()
-                out = float(loss_host[slot ^ 1])
-            done[slot] = d
-        done[(steps - 1) & 1].synchronize()
-        return float(loss_host[(steps - 1) & 1])
+            done = [None, None]
+            for k in range(steps):
+                x, ev = pending
+                pending = issue_h2d()
+                main_stream.wait_event(ev)
+                for t in x.values():
+                    t.record_stream(main_stream)
+                loss, _ = step(x)
+                slot = k & 1
+                loss_host[slot].copy_(loss.detach().float(), non_blocking=True)   # D2H read of the result
+                d = torch.cuda.Event()
+                d.record(main_stream)
+                if done[slot ^ 1] is not None:                                    # the previous step's loss is on the host
+                    done[slot ^ 1].synchronize()
+                    float(loss_host[slot ^ 1])
+                done[slot] = d
+            done[(steps - 1) & 1].synchronize()
+            return float(loss_host[(steps - 1) & 1])
 
     e2e_loop(3)
     K_e2e = max(5, K)
@@ -318,13 +407,16 @@ def main():
             "global_batch": Bg, "pairs_per_s": B * Bg * world / (ms * 1e-3), "rho": RHO,
             "parallelism": "single GPU" if world == 1 else f"rows local, columns all-gathered over NCCL x{world}",
             "l2": "256 MiB buffer written between timed steps (untimed) to flush the 126 MB L2",
+            "launch": mode, "eager_ms_per_step": ms_eager, "host_enqueue_ms_per_step": host_ms,
+            "scaling_note": "global negatives: per-rank work grows with the global batch (rows local, columns "
+                            "gathered), so samples/s stays flat with N while pairs/s grows ~N",
         },
         "clocks": clocks,
         "e2e": {"value": Bg / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": K_e2e,
-                "how": "public API (train_gan.make_labels / sent_loss / img_loss / word_loss + backward); pinned-host "
+                "how": "public API (train_gan.make_labels / sent_loss / img_loss / word_loss + backward, %s); pinned-host "
                        "inputs copied H2D every step on a copy stream one step ahead, loss copied D2H to pinned memory "
-                       "every step and read by the host one step late"},
+                       "every step and read by the host one step late" % mode},
         "gpu_launches": launches,
         "roofline": roofline,
     }
