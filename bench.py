@@ -163,6 +163,7 @@ def main():
     torch.cuda.set_device(local_rank)
     group = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         group = dist.group.WORLD
     dev = torch.device("cuda", local_rank)
