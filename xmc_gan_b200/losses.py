@@ -230,6 +230,10 @@ class WordLossFn(torch.autograd.Function):
                                  comm.rank * nloc, nloc)
         loss3 = comm.all_reduce_sum(loss3)
 
+        # the backward's zero-filled accumulators are prepared now, beside the forward (tcgen05 path)
+        ctx.bufs = None
+        if need_grad and use_tc_bwd and chat is not None and hasattr(ops, "backward_buffers"):
+            ctx.bufs = ops.backward_buffers(path, Bc * T, Bi, R, Rpad, D, reg.device, rn is not None)
         ctx.comm, ctx.ops = comm, ops
         ctx.meta = (path, R, T, float(rho1), float(rho2), float(rho3), diag, num_pos, rows_total, Bc,
                     tuple(regions.shape), regions.dtype, words.dtype)
@@ -256,6 +260,7 @@ class WordLossFn(torch.autograd.Function):
         need_reg, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_reg or need_w):
             return (None,) * 12
+        bufs, ctx.bufs = ctx.bufs, None           # single use: the kernels accumulate into them
         go = grad_out.detach().to(torch.float32).contiguous()
         dscores = ops.infonce_grad(scores, lab, diag, rho3, row_stats, col_stats, row_div, col_div, num_pos,
                                    rows_total, Bc, go)
@@ -264,7 +269,7 @@ class WordLossFn(torch.autograd.Function):
             nq_dev = cap_ptr[Bc:]
             grel = ops.word_scores_backward(rel, m_all, scores, dscores, T, rho2, cap_ptr=cap_ptr)
             dqn, dkn, drnorm = ops.wordregion_backward(path, qn.view(-1, D), kn, rnorm if has_rn else None, R, rho1,
-                                                       lsum, cnorm, rel, grel, chat, nq_dev=nq_dev)
+                                                       lsum, cnorm, rel, grel, chat, nq_dev=nq_dev, bufs=bufs)
         else:
             grel = ops.word_scores_backward(rel, m_all, scores, dscores, T, rho2)
             if path == _lib.PATH_BF16_TCGEN05 and not has_chat:
@@ -274,7 +279,8 @@ class WordLossFn(torch.autograd.Function):
                                                            rnorm if has_rn else None, R, rho1, lsum, cnorm, rel, grel)
             else:
                 dqn, dkn, drnorm = ops.wordregion_backward(path, qn.view(-1, D), kn, rnorm if has_rn else None, R, rho1,
-                                                           lsum, cnorm, rel, grel, chat if has_chat else None)
+                                                           lsum, cnorm, rel, grel, chat if has_chat else None,
+                                                           **({"bufs": bufs} if bufs is not None else {}))
         dreg = dwords = None
         if need_reg:
             dreg = ops.normalize_transpose_backward(kn, rnorm, dkn, drnorm, R, reg_dtype).view(reg_shape)

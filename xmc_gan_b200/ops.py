@@ -242,15 +242,48 @@ class CudaOps:
         self.launches += 1
         return lsum, cnorm, rel, chat
 
-    def wordregion_backward(self, path, qn, kn, rnorm, R, rho1, lsum, cnorm, rel, grel, chat=None, nq_dev=None):
+    def backward_buffers(self, path, NQ, Bi, R, Rpad, D, dev, has_rnorm):
+        """Zero-filled gradient accumulators + workspace of wordregion_backward, filled on a side stream
+        (the 80 MB fill of dkn then runs beside the forward instead of in front of the backward kernel).
+        -> (dqn, dkn, drnorm, ws, ws_bytes, event)."""
+        cur = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        side.wait_stream(cur)                     # the allocator may hand out blocks the current stream still uses
+        with torch.cuda.stream(side):
+            dqn = torch.zeros(NQ, D, device=dev, dtype=torch.float32)
+            dkn = torch.zeros(Bi, Rpad, D, device=dev, dtype=torch.float32)
+            drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if has_rnorm else None
+            ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        for t in (dqn, dkn, drnorm, ws):
+            if t is not None:
+                t.record_stream(cur)
+        return dqn, dkn, drnorm, ws, n, ev
+
+    def _side_stream(self, dev):
+        key = (dev.type, dev.index)
+        if not hasattr(self, "_sides"):
+            self._sides = {}
+        if key not in self._sides:
+            self._sides[key] = torch.cuda.Stream(device=dev)
+        return self._sides[key]
+
+    def wordregion_backward(self, path, qn, kn, rnorm, R, rho1, lsum, cnorm, rel, grel, chat=None, nq_dev=None,
+                            bufs=None):
         _cuda(qn, kn, grel)
         NQ, D = qn.shape
         Bi, Rpad, _ = kn.shape
         dev = qn.device
-        dqn = torch.zeros(NQ, D, device=dev, dtype=torch.float32)
-        dkn = torch.zeros(Bi, Rpad, D, device=dev, dtype=torch.float32)
-        drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if rnorm is not None else None
-        ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
+        if bufs is not None:
+            dqn, dkn, drnorm, ws, n, ev = bufs
+            torch.cuda.current_stream(dev).wait_event(ev)
+            self.last_workspace = ws
+        else:
+            dqn = torch.zeros(NQ, D, device=dev, dtype=torch.float32)
+            dkn = torch.zeros(Bi, Rpad, D, device=dev, dtype=torch.float32)
+            drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if rnorm is not None else None
+            ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
         with torch.cuda.device_of(qn), self._timed("wordregion_bwd"):
             _lib.check(self.L.xmc_wordregion_backward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
                                                       _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(grel), _p(dqn), _p(dkn),
