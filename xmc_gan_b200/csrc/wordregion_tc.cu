@@ -999,18 +999,21 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           if (col0 < n) {                               // warp-uniform: this warpgroup has columns in the chunk
             const float* wsm = rn_s + (xm & 1) * CH + col0;
             float z[32];
-            // two halves of 16 columns (register budget); S,W are released after the second load
+            // S and W of the warpgroup's 32 columns -> registers, then they are released at once (the next scores
+            // may overwrite them while the arithmetic below runs); the arithmetic goes in two halves of 16 columns
+            uint32_t svv[2][16], wvv[2][16];
+            tmem_ld16(lane_base + Cfg::kColS + col0, svv[0]);
+            tmem_ld16(lane_base + Cfg::kColW + col0, wvv[0]);
+            tmem_ld16(lane_base + Cfg::kColS + col0 + 16, svv[1]);
+            tmem_ld16(lane_base + Cfg::kColW + col0 + 16, wvv[1]);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(sw_consumed);
+            if (tracer) XMC_TRACE(1, xm, 1);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-              uint32_t sv[16], wv[16];
-              tmem_ld16(lane_base + Cfg::kColS + col0 + hf * 16, sv);
-              tmem_ld16(lane_base + Cfg::kColW + col0 + hf * 16, wv);
-              tmem_wait_ld();
-              if (hf == 1) {
-                tc_fence_before();
-                mbar_arrive(sw_consumed);
-                if (tracer) XMC_TRACE(1, xm, 1);
-              }
+              const uint32_t (&sv)[16] = svv[hf];
+              const uint32_t (&wv)[16] = wvv[hf];
               auto elementwise = [&](auto full_tag) {
                 constexpr bool kFull = decltype(full_tag)::value;   // every column is a real region: no predicates
                 const float2 cc = make_float2(c1, c1), ncc = make_float2(-c1, -c1);
