@@ -967,7 +967,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         int cm = 0, iim = 0;                      // chunk-in-image / image-in-segment of the arithmetic chunk
         float inv_l = 1.f, gam = 0.f, ngrl = 0.f;
         uint32_t xp[16], yp[16];
-        float colsum = 0.f;
+        float z[32];                              // alpha * d alpha' of the chunk: column-summed into drnorm after X, Y left
         // per-(image, word row) statistics of the NEXT image are fetched one image ahead: at the first chunk of
         // an image the elementwise warps are on the critical path (the pipeline drains at image boundaries)
         float pf_l = 1.f, pf_cn = 1.f, pf_g = 0.f, pf_rel = 0.f;
@@ -998,7 +998,6 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           if (tracer) XMC_TRACE(1, xm, 0);
           if (col0 < n) {                               // warp-uniform: this warpgroup has columns in the chunk
             const float* wsm = rn_s + (xm & 1) * CH + col0;
-            float z[32];
             // S and W of the warpgroup's 32 columns -> registers, then they are released at once (the next scores
             // may overwrite them while the arithmetic below runs); the arithmetic goes in two halves of 16 columns
             uint32_t svv[2][16], wvv[2][16];
@@ -1048,9 +1047,11 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                   }
                 }
               };
-              if (r0 + 32 <= p.R) elementwise(std::true_type{}); else elementwise(std::false_type{});
+              // With raw values the padded region rows carry norm 0 (and never-loaded norm slots / never-written
+              // score columns are zeroed at kernel start): alpha' = alpha * 0 and s = w = 0 already make X, Y, z
+              // exact zeros there, so the predicate-free path serves every chunk.
+              if (has_rn || r0 + 32 <= p.R) elementwise(std::true_type{}); else elementwise(std::false_type{});
             }
-            if (has_rn) colsum = warp_transpose_sum32(z, lane);      // column (r0 + lane) over this warp's 32 rows
           } else {
             tc_fence_before();
             mbar_arrive(sw_consumed);
@@ -1080,7 +1081,11 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           fence_proxy_async_smem();
           mbar_arrive(xy_full);
           if (tracer) XMC_TRACE(2, x, 0);
-          if (active && has_rn && r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
+          // off the critical path (X, Y are already with the tensor pipe): column sums of z -> drnorm
+          if (active && has_rn) {
+            const float colsum = warp_transpose_sum32(z, lane);      // column (r0 + lane) over this warp's 32 rows
+            if (r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
+          }
           // ---- arithmetic of chunk g+1 while dQ(g), dK^T(g) run on the tensor pipe ----
           if (g + 1 < G) arithmetic();
           if (tracer) XMC_TRACE(2, x, 1);
