@@ -247,6 +247,16 @@ class CudaOps:
         (the 80 MB fill of dkn then runs beside the forward instead of in front of the backward kernel).
         -> (dqn, dkn, drnorm, ws, ws_bytes, event)."""
         cur = torch.cuda.current_stream(dev)
+        if torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture a forked stream must rejoin before the capture ends, which is not
+            # guaranteed here (the backward may never run): fill on the capturing stream
+            dqn = torch.zeros(NQ, D, device=dev, dtype=torch.float32)
+            dkn = torch.zeros(Bi, Rpad, D, device=dev, dtype=torch.float32)
+            drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if has_rnorm else None
+            ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            return dqn, dkn, drnorm, ws, n, ev
         side = self._side_stream(dev)
         side.wait_stream(cur)                     # the allocator may hand out blocks the current stream still uses
         with torch.cuda.stream(side):
