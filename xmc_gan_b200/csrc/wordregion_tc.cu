@@ -1,23 +1,27 @@
-// wordregion_tc.cu — word–region attention statistics on the 5th-gen tensor cores (sm_100a):
-// bf16 operands, fp32 accumulation in TMEM, region tiles streamed by TMA.
+// wordregion_tc.cu — word–region attention statistics and their fused backward on the 5th-gen tensor
+// cores (sm_100a): bf16 operands, fp32 accumulation in TMEM, region tiles streamed by TMA.
 //
-// Tile = (128 consecutive word rows of the flattened [Bc*T, D] unit-word matrix) x (one image).
-// A CTA keeps its 128 word rows resident in TMEM as the A operand (bf16, D/2 columns) and walks
-// over a contiguous range of images; the regions of an image arrive in chunks of 64 rows
-// ([64 x D] bf16, four 128B-swizzled TMA boxes) through an NS-stage mbarrier ring.
+// Forward.  Work item = (128 consecutive rows of the compacted unit-word matrix [NQ, D]) x (one image).
+// One persistent CTA per SM walks its share of the items (SegIter below); it keeps the 128 word rows
+// resident in TMEM as the A operand (bf16, D/2 columns) while it stays on a word tile; the regions of
+// an image arrive in chunks of 64 rows ([64 x D] bf16, 128B-swizzled TMA boxes) through a 4-stage
+// mbarrier ring.
 //
 //   GEMM1 (TS)  S[128 x 64]  = Q(tmem) . Khat_chunk^T        B = K-major  smem descriptor
 //   softmax warps: P' = exp2(c1 (S-1)) * ||v_r||  -> bf16, written over S in TMEM;  l += P, a += P' S
 //   GEMM2 (TS)  C[128 x D] += P'(tmem) . Khat_chunk           B = MN-major smem descriptor (same bytes)
-//   epilogue: ||C|| from TMEM  ->  lsum, cnorm, rel  (per image, per word row)
+//   epilogue warpgroup: C -> bf16 -> swizzled smem boxes -> TMA store (saved for the backward);
+//                       ||C||, lsum, cnorm, rel  (per image, per word row)
 //
 // The key and the value of the attention are the SAME smem tile (raw values are folded into P' as a
 // per-column scale), cosines are bounded so the softmax uses the constant shift rho1 (no running
 // max, no rescale of C), and the [Bi,Bc,T,R] score tensor lives only in TMEM.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
-// allocator, warps 4-7 = softmax/epilogue warpgroup (thread = TMEM lane = word row).
+// Warp roles (512 threads): warp 0 = TMA producer and warp 1 = MMA issuer (one elected thread each runs
+// the whole role), warp 2 = TMEM allocator, warps 4-11 = two softmax warpgroups (thread = TMEM lane =
+// word row, 32 chunk columns each), warps 12-15 = epilogue warpgroup.
 // TMEM map (512 columns): C [0,D) | Q [D, D+D/2) | S0 | S1 (64 columns each, P' aliases S).
+// The backward kernel is described in front of its code.
 #include <algorithm>
 #include <type_traits>
 
