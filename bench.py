@@ -371,15 +371,17 @@ def main():
             done[(steps - 1) & 1].synchronize()
             return float(loss_host[(steps - 1) & 1])
 
-    e2e_loop(3)
+    e2e_loop(5)
     K_e2e = max(5, K)
-    barrier()
-    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ea.record()
-    e2e_loop(K_e2e)
-    eb.record()
-    barrier()
-    ms_e2e = ea.elapsed_time(eb) / K_e2e
+    ms_e2e = float("inf")
+    for _ in range(2):                      # best of two passes of K_e2e steps (host-side jitter: PCIe, first-touch)
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        e2e_loop(K_e2e)
+        eb.record()
+        barrier()
+        ms_e2e = min(ms_e2e, ea.elapsed_time(eb) / K_e2e)
     if world > 1:
         t = torch.tensor([ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
@@ -437,7 +439,7 @@ def main():
         },
         "clocks": clocks,
         "e2e": {"value": Bg / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": K_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": K_e2e, "passes": "best of 2",
                 "how": "public API (train_gan.make_labels / sent_loss / img_loss / word_loss + backward, %s); pinned-host "
                        "inputs copied H2D every step on a copy stream one step ahead, loss copied D2H to pinned memory "
                        "every step and read by the host one step late" % mode},

@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# every tcgen05 launch made by the tests is followed by a check of the kernel's error word (a bounded
+# mbarrier wait that timed out would otherwise only show as wrong numbers)
+os.environ.setdefault("XMC_CHECK_ERRORS", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

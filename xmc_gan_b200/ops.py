@@ -9,6 +9,8 @@ the product never does that.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -212,6 +214,14 @@ class CudaOps:
         self.launches += 1
         return dx
 
+    def _check_error_word(self, ws, what):
+        """XMC_CHECK_ERRORS=1 (tests): synchronise and raise if a bounded mbarrier wait of the tcgen05 kernel
+        timed out (word 0 of its workspace).  Off by default: the product path never synchronises."""
+        if ws is not None and os.environ.get("XMC_CHECK_ERRORS") and not torch.cuda.is_current_stream_capturing():
+            code = int(ws[:4].view(torch.int32)[0])
+            if code != 0:
+                raise RuntimeError(f"{what}: pipeline wait timed out inside the kernel (code {code})")
+
     def _workspace(self, path, NQ, Bi, R, Rpad, D, dev):
         """Caller-owned scratch of the tcgen05 path; word 0 is its error flag (0 = ok), so zero-filled."""
         n = self.L.xmc_wordregion_workspace_bytes(path, NQ, Bi, R, Rpad, D)
@@ -240,6 +250,7 @@ class CudaOps:
                                                      _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(nq_dev), _p(ws), n,
                                                      _stream()))
         self.launches += 1
+        self._check_error_word(ws, "wordregion_forward")
         return lsum, cnorm, rel, chat
 
     def backward_buffers(self, path, NQ, Bi, R, Rpad, D, dev, has_rnorm):
@@ -299,6 +310,7 @@ class CudaOps:
                                                       _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(grel), _p(dqn), _p(dkn),
                                                       _p(drnorm), _p(nq_dev), _p(ws), n, _stream()))
         self.launches += 1
+        self._check_error_word(ws, "wordregion_backward")
         return dqn, dkn, drnorm
 
     def word_scores(self, rel, mask_u8, Bc, T, rho2, cap_ptr=None):
