@@ -1065,38 +1065,44 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           if (++cm == nch) { cm = 0; ++iim; }
         };
 
-        arithmetic();                                   // first chunk of the segment
+        // One call site for the arithmetic (the code of this role is large: every copy costs instruction cache):
+        // iteration g = -1 only does the arithmetic of chunk 0.
         int c = 0, ii = 0;
-        for (int g = 0; g < G; ++g, ++x) {
-          const int img = sg.img0 + ii * sg.stride;
-          const int n = min(CH, p.Rpad - c * CH);
-          const bool active = col0 < n;
-          const int r0 = c * CH + col0;
-          // ---- X,Y(g) -> smem.  Safe: dk_full of the previous chunk was waited for below, so the MMAs that read X,Y are done.
-          if (active) {
-            // row `row` of the [128 x 64] bf16 tiles, 16-byte chunks XOR-swizzled by (row & 7)
+        for (int g = -1; g < G; ++g) {
+          if (g >= 0) {
+            const int img = sg.img0 + ii * sg.stride;
+            const int n = min(CH, p.Rpad - c * CH);
+            const bool active = col0 < n;
+            const int r0 = c * CH + col0;
+            // ---- X,Y(g) -> smem.  Safe: dk_full of the previous chunk was waited for below, so the MMAs that read X,Y are done.
+            if (active) {
+              // row `row` of the [128 x 64] bf16 tiles, 16-byte chunks XOR-swizzled by (row & 7)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int phys = ((col0 >> 3) + u) ^ (row & 7);
-              *reinterpret_cast<uint4*>(Xs + row * 128 + phys * 16) = make_uint4(xp[4 * u], xp[4 * u + 1], xp[4 * u + 2], xp[4 * u + 3]);
-              *reinterpret_cast<uint4*>(Ys + row * 128 + phys * 16) = make_uint4(yp[4 * u], yp[4 * u + 1], yp[4 * u + 2], yp[4 * u + 3]);
+              for (int u = 0; u < 4; ++u) {
+                const int phys = ((col0 >> 3) + u) ^ (row & 7);
+                *reinterpret_cast<uint4*>(Xs + row * 128 + phys * 16) = make_uint4(xp[4 * u], xp[4 * u + 1], xp[4 * u + 2], xp[4 * u + 3]);
+                *reinterpret_cast<uint4*>(Ys + row * 128 + phys * 16) = make_uint4(yp[4 * u], yp[4 * u + 1], yp[4 * u + 2], yp[4 * u + 3]);
+              }
             }
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(xy_full);
-          if (tracer) XMC_TRACE(2, x, 0);
-          // off the critical path (X, Y are already with the tensor pipe): column sums of z -> drnorm
-          if (active && has_rn) {
-            const float colsum = warp_transpose_sum32(z, lane);      // column (r0 + lane) over this warp's 32 rows
-            if (r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
+            fence_proxy_async_smem();
+            mbar_arrive(xy_full);
+            if (tracer) XMC_TRACE(2, x, 0);
+            // off the critical path (X, Y are already with the tensor pipe): column sums of z -> drnorm
+            if (active && has_rn) {
+              const float colsum = warp_transpose_sum32(z, lane);      // column (r0 + lane) over this warp's 32 rows
+              if (r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
+            }
           }
           // ---- arithmetic of chunk g+1 while dQ(g), dK^T(g) run on the tensor pipe ----
           if (g + 1 < G) arithmetic();
-          if (tracer) XMC_TRACE(2, x, 1);
-          // ---- X,Y(g) stay live until dQ(g), dK^T(g) have executed ----
-          mbar_wait(dk_full, x & 1, wc, 21);
-          if (tracer) XMC_TRACE(2, x, 2);
-          if (++c == nch) { c = 0; ++ii; }
+          if (g >= 0) {
+            if (tracer) XMC_TRACE(2, x, 1);
+            // ---- X,Y(g) stay live until dQ(g), dK^T(g) have executed ----
+            mbar_wait(dk_full, x & 1, wc, 21);
+            if (tracer) XMC_TRACE(2, x, 2);
+            if (++c == nch) { c = 0; ++ii; }
+            ++x;
+          }
         }
         // ---- dQ of this segment's word tile (summed over its images): TMEM -> swizzled fp32 boxes in the
         //      (now dead) X|Y bytes -> TMA reduce-add into dqn; warpgroup h owns columns [128h, 128h+128) ----
