@@ -41,6 +41,7 @@ class CpuOps:
 
     def __init__(self):
         self.launches = 0
+        self.compactions = 0
 
     # -- similarity losses --
     def cosine_scores(self, a, b):
@@ -95,16 +96,46 @@ class CpuOps:
         return labels, (labels > 0).sum(1).float()
 
     # -- word-region --
-    def normalize_transpose(self, x, Lpad, out_dtype):
+    supports_compaction = True
+
+    def word_rows_compact(self, mask_u8):
+        """xmc_word_rows_compact: caption-major exclusive scan of the valid words."""
+        self.compactions += 1
+        Bc, T = mask_u8.shape
+        valid = (mask_u8 == 0).flatten()
+        excl = torch.cumsum(valid.int(), 0) - valid.int()
+        row_of = torch.where(valid, excl, torch.full_like(excl, -1)).to(torch.int32)
+        per_cap = valid.view(Bc, T).sum(1)
+        cap_ptr = torch.zeros(Bc + 1, dtype=torch.int32)
+        cap_ptr[1:] = torch.cumsum(per_cap, 0)
+        return row_of, cap_ptr
+
+    def normalize_transpose(self, x, Lpad, out_dtype, row_of=None):
         B, D, L = x.shape
         norm = x.norm(dim=1).clamp_min(EPS)                      # [B, L]
         xn = torch.zeros(B, Lpad, D, dtype=x.dtype)
-        xn[:, :L] = (x / norm[:, None, :]).transpose(1, 2)
         n = torch.zeros(B, Lpad, dtype=x.dtype)
+        if row_of is not None:                                   # valid rows packed to the front of [B*L, D]
+            assert Lpad == L
+            keep = row_of >= 0
+            dst = row_of[keep].long()
+            xn.view(B * L, D)[dst] = (x / norm[:, None, :]).transpose(1, 2).reshape(B * L, D)[keep]
+            n.view(B * L)[dst] = norm.reshape(B * L)[keep]
+            return xn, n
+        xn[:, :L] = (x / norm[:, None, :]).transpose(1, 2)
         n[:, :L] = norm
         return xn, n
 
-    def normalize_transpose_backward(self, xn, norm, dxn, dnorm, L, out_dtype):
+    def normalize_transpose_backward(self, xn, norm, dxn, dnorm, L, out_dtype, row_of=None):
+        if row_of is not None:                                   # dropped (padding) words get a zero gradient
+            B, Lp, D = xn.shape
+            assert Lp == L and dnorm is None
+            keep = row_of >= 0
+            src = row_of.clamp_min(0).long()
+            xh, g, n = xn.view(B * L, D)[src], dxn.reshape(B * L, D)[src], norm.view(B * L)[src]
+            dx = (g - xh * (g * xh).sum(-1, keepdim=True)) / n.clamp_min(EPS)[:, None]
+            dx = torch.where(keep[:, None], dx, torch.zeros_like(dx))
+            return dx.view(B, L, D).transpose(1, 2).contiguous()
         xh, g, n = xn[:, :L], dxn[:, :L], norm[:, :L]
         dx = (g - xh * (g * xh).sum(-1, keepdim=True)) / n[..., None]
         if dnorm is not None:
@@ -122,11 +153,24 @@ class CpuOps:
         rel = (qn[None] * ctx).sum(-1) / cnorm.clamp_min(EPS)
         return lsum, cnorm, rel
 
-    def wordregion_forward(self, path, qn, kn, rnorm, R, rho1, save_context=False):
+    def wordregion_forward(self, path, qn, kn, rnorm, R, rho1, save_context=False, nq_dev=None):
         lsum, cnorm, rel = self._wr(qn, kn, rnorm, R, rho1)
-        return lsum, cnorm, rel, None
+        chat = None
+        if nq_dev is not None:                # rows beyond the device-side count are never written by the kernel:
+            dead = torch.arange(qn.shape[0]) >= int(nq_dev[0])            # poison them so a consumer would notice
+            lsum, cnorm, rel = (torch.where(dead[None], torch.full_like(t, float('nan')), t) for t in (lsum, cnorm, rel))
+        if save_context:                      # stands for the saved attended contexts; only its presence matters here
+            chat = torch.zeros(1)
+        return lsum, cnorm, rel, chat
 
-    def wordregion_backward(self, path, qn, kn, rnorm, R, rho1, lsum, cnorm, rel, grel, chat=None):
+    def wordregion_backward(self, path, qn, kn, rnorm, R, rho1, lsum, cnorm, rel, grel, chat=None, nq_dev=None,
+                            bufs=None):
+        if nq_dev is not None:                # the kernel visits only the first nq rows
+            nq = int(nq_dev[0])
+            dq, dk, drn = self.wordregion_backward(path, qn[:nq], kn, rnorm, R, rho1, None, None, None, grel[:, :nq])
+            dq_full = torch.zeros_like(qn)
+            dq_full[:nq] = dq
+            return dq_full, dk, drn
         with torch.enable_grad():            # we are inside an autograd backward: grad mode is off
             q = qn.detach().clone().requires_grad_()
             k = kn.detach().clone().requires_grad_()
@@ -135,7 +179,22 @@ class CpuOps:
             (r * grel).sum().backward()
         return q.grad, k.grad, (rn.grad if rn is not None else None)
 
-    def word_scores(self, rel, mask_u8, Bc, T, rho2):
+    @staticmethod
+    def _dense(rel, Bc, T, cap_ptr, fill):
+        """compact [Bi, NQs] -> caption-padded [Bi, Bc, T] plus the validity mask of its slots."""
+        Bi = rel.shape[0]
+        cnt = (cap_ptr[1:] - cap_ptr[:-1]).long()
+        slot = torch.arange(T)[None, :] < cnt[:, None]                         # [Bc, T]
+        src = (cap_ptr[:-1].long()[:, None] + torch.arange(T)[None, :]).clamp_max(rel.shape[1] - 1)
+        z = torch.where(slot[None], rel[:, src], torch.full((), fill, dtype=rel.dtype))
+        return z, slot, src
+
+    def word_scores(self, rel, mask_u8, Bc, T, rho2, cap_ptr=None):
+        if cap_ptr is not None:
+            z, slot, _ = self._dense(rel, Bc, T, cap_ptr, float('-inf'))
+            empty = ~slot.any(1)
+            z = torch.where(empty.view(1, -1, 1), torch.zeros_like(z), rho2 * z)
+            return torch.where(empty.view(1, -1), torch.zeros_like(z[..., 0]), torch.logsumexp(z, -1) / rho2)
         z = rho2 * rel.view(rel.shape[0], Bc, T)
         if mask_u8 is not None:
             m = mask_u8.bool()
@@ -145,8 +204,15 @@ class CpuOps:
             return torch.where(empty.view(1, -1), torch.zeros_like(z[..., 0]), torch.logsumexp(z, -1) / rho2)
         return torch.logsumexp(z, -1) / rho2
 
-    def word_scores_backward(self, rel, mask_u8, scores, dscores, T, rho2):
+    def word_scores_backward(self, rel, mask_u8, scores, dscores, T, rho2, cap_ptr=None):
         Bi, Bc = scores.shape
+        if cap_ptr is not None:
+            z, slot, src = self._dense(rel, Bc, T, cap_ptr, 0.0)
+            w = torch.where(slot[None], torch.exp(rho2 * (z - scores[..., None])), torch.zeros_like(z))
+            g = dscores[..., None] * w                                          # [Bi, Bc, T]
+            grel = torch.zeros_like(rel)
+            grel[:, src[slot]] = g[:, slot]
+            return grel
         w = torch.exp(rho2 * (rel.view(Bi, Bc, T) - scores[..., None]))
         if mask_u8 is not None:
             w = w.masked_fill(mask_u8.bool()[None], 0.0)

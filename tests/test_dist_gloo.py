@@ -40,7 +40,7 @@ def _data(seed, Bg, D, Dw, T_, R):
     return d
 
 
-def _worker(rank, port, b_global, smooth, out):
+def _worker(rank, port, b_global, smooth, precision, Dw, out):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -51,7 +51,7 @@ def _worker(rank, port, b_global, smooth, out):
         torch.set_num_threads(1)
         T.cfg.TRAIN.SMOOTH.GLOBAL = smooth
         ops = CpuOps()
-        B, D, Dw, T_, R = 6, 16, 8, 5, 7
+        B, D, T_, R = 6, 16, 5, 7
         d = _data(0, B * WORLD, D, Dw, T_, R)
         sl = slice(rank * B, (rank + 1) * B)
         leaf = lambda x: x[sl].clone().requires_grad_()
@@ -61,22 +61,26 @@ def _worker(rank, port, b_global, smooth, out):
         loss = (T.sent_loss(img, sent, labels, b_global, group=group, _ops=ops)
                 + T.img_loss(sent.detach(), img, labels, b_global, tau=0.5, group=group, _ops=ops)
                 + T.word_loss(regions, words, d["mask"][sl], labels, b_global, rho1=4.0, rho2=5.0, rho3=6.0,
-                              group=group, _ops=ops))
+                              precision=precision, group=group, _ops=ops))
         loss.backward()
+        assert ops.compactions == (1 if precision == "bf16" else 0)
         out[rank] = dict(loss=loss.detach(), labels=labels.detach().clone(),
                          grads=[t.grad.clone() for t in (img, sent, words, regions)])
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("b_global,smooth", [(False, 0.5), (True, 0.5), (True, 0.0)])
-def test_two_rank_global_negatives_match_single_process_oracle(b_global, smooth):
+# precision "bf16" selects the tcgen05-path host flow (padding words compacted away, device-side row
+# count, gradients scattered back through row_of); the checker backend still computes in fp64.
+@pytest.mark.parametrize("b_global,smooth,precision,Dw", [(False, 0.5, None, 8), (True, 0.5, None, 8), (True, 0.0, None, 8),
+                                                          (True, 0.5, "bf16", 128), (False, 0.5, "bf16", 128)])
+def test_two_rank_global_negatives_match_single_process_oracle(b_global, smooth, precision, Dw):
     import oracle
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(_free_port(), b_global, smooth, out), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(_free_port(), b_global, smooth, precision, Dw, out), nprocs=WORLD, join=True)
 
-    B, D, Dw, T_, R = 6, 16, 8, 5, 7
+    B, D, T_, R = 6, 16, 5, 7
     Bg = B * WORLD
     d = _data(0, Bg, D, Dw, T_, R)
     leaf = lambda x: x.clone().requires_grad_()
@@ -93,7 +97,7 @@ def test_two_rank_global_negatives_match_single_process_oracle(b_global, smooth)
         sl = slice(rank * B, (rank + 1) * B)
         r = out[rank]
         assert torch.equal(r["labels"], labels[sl]), f"rank {rank} label rows"
-        assert abs(float(r["loss"]) - float(loss)) < 1e-6 * abs(float(loss)), (float(r["loss"]), float(loss))
+        assert abs(float(r["loss"]) - float(loss.detach())) < 1e-6 * abs(float(loss.detach())), (float(r["loss"]), float(loss.detach()))
         for got, ref in zip(r["grads"], (img.grad, sent.grad, words.grad, regions.grad)):
             err = float((got - ref[sl]).norm() / ref[sl].norm())
             assert err < 1e-6, (rank, err)
