@@ -6,6 +6,8 @@
 // The tensor-core kernels want unit rows with D contiguous, so one HBM-bound pass does
 // F.normalize (train_gan.py:88-89 convention) + transpose + optional bf16 cast through a padded
 // shared-memory tile (reads coalesced along L, writes coalesced along D).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace xmc {
@@ -165,6 +167,177 @@ __global__ void __launch_bounds__(256) norm_tr_bwd_kernel(const TX* __restrict__
     for (int d = warp; d < D; d += 8) st1(dx + ((size_t)b * D + d) * L + l, tile[d * (kLT + 1) + lane]);
 }
 
+// ---- bf16 fast paths (D = 128 or 256: the shapes of the tcgen05 word-region kernels) ----------------------
+// Same arithmetic, in the same order, as the generic kernels above (results are bit-identical); what changes
+// is how the bytes move: every global load of a thread is issued before the first use (16 two-byte loads /
+// four rows of 128-bit loads in flight), the staging tile holds bf16 with an odd 32-bit-word pitch so both
+// the l-major and the d-major side are bank-conflict-free, and rows leave as 4-byte (bf16x2) stores, one
+// full 128-byte line per warp instruction.
+
+__device__ __forceinline__ float bf16_bits_to_float(unsigned short h) { return __uint_as_float((uint32_t)h << 16); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) norm_tr_bf16_kernel(const __nv_bfloat16* __restrict__ x, int L, int Lpad,
+                                                            const int* __restrict__ row_of,
+                                                            __nv_bfloat16* __restrict__ xn, float* __restrict__ norm) {
+  constexpr int kW = D / 2 + 1;                   // tile row pitch in 32-bit words (odd)
+  constexpr int kPer = D / 8;                     // d values per thread
+  constexpr int kBatch = 16;
+  __shared__ uint32_t tile[kLT * kW];             // [l][d] raw bf16 inputs
+  __shared__ float part[8][kLT];
+  __shared__ float inv_sh[kLT];
+  unsigned short* tile16 = reinterpret_cast<unsigned short*>(tile);
+  const int b = blockIdx.y, l0 = blockIdx.x * kLT;
+  const int lx = threadIdx.x & 31, dy = threadIdx.x >> 5;
+  const int l = l0 + lx;
+  const bool in = l < L;
+  // lanes beyond L read the last valid column (no predicated loads); their tile rows are never stored
+  const unsigned short* src = reinterpret_cast<const unsigned short*>(x) + ((size_t)b * D + dy) * L + (in ? l : L - 1);
+  unsigned long long addr = reinterpret_cast<unsigned long long>(src);
+  const unsigned long long step = 16ull * (unsigned)L;          // bytes between the d values of a thread
+  float ss = 0.f;
+#pragma unroll
+  for (int i0 = 0; i0 < kPer; i0 += kBatch) {
+    unsigned short v[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {          // opaque pointer bump: two integer ops per load, not five
+      asm volatile("ld.global.nc.u16 %0, [%1];\n\tadd.u64 %1, %1, %2;" : "=h"(v[i]), "+l"(addr) : "l"(step));
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const float f = bf16_bits_to_float(v[i]);
+      tile16[lx * (2 * kW) + dy + 8 * (i0 + i)] = v[i];
+      ss = fmaf(f, f, ss);
+    }
+  }
+  part[dy][lx] = ss;
+  __syncthreads();
+  if (dy == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lx];
+    float n = fmaxf(sqrtf(t), kEps);
+    inv_sh[lx] = 1.f / n;
+    if (l < Lpad) norm[(size_t)b * Lpad + l] = in ? n : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kLT / 8; ++k) {
+    const int r = dy + 8 * k;
+    const int lr = l0 + r;
+    if (lr >= Lpad) break;
+    const float inv = inv_sh[r];
+    long long orow = (long long)b * Lpad + lr;
+    if (row_of) {
+      orow = row_of[orow];
+      if (orow < 0) continue;
+    }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(xn + (size_t)orow * D);
+    const bool pad_row = lr >= L;                 // zero rows up to Lpad
+#pragma unroll
+    for (int j = 0; j < D / 64; ++j) {
+      const uint32_t w = tile[r * kW + lx + 32 * j];
+      dst[lx + 32 * j] = pad_row ? 0u : pack_bf16x2(__uint_as_float(w << 16) * inv, __uint_as_float(w & 0xffff0000u) * inv);
+    }
+  }
+}
+
+template <typename TO> struct BwdTile;
+template <> struct BwdTile<__nv_bfloat16> {      // bf16 tile, odd word pitch
+  static constexpr int kWordsPerD2 = 1;           // tile words = kLT * (D * kWordsPerD2 / 2 + 1)
+  template <int D> static __device__ __forceinline__ void put4(uint32_t* t, int r, int d, float a, float b, float c, float e) {
+    t[r * (D / 2 + 1) + d / 2] = pack_bf16x2(a, b);
+    t[r * (D / 2 + 1) + d / 2 + 1] = pack_bf16x2(c, e);
+  }
+  template <int D> static __device__ __forceinline__ __nv_bfloat16 get(const uint32_t* t, int r, int d) {
+    return reinterpret_cast<const __nv_bfloat16*>(t)[r * (D + 2) + d];
+  }
+};
+template <> struct BwdTile<float> {              // fp32 tile, odd word pitch
+  static constexpr int kWordsPerD2 = 2;
+  template <int D> static __device__ __forceinline__ void put4(uint32_t* t, int r, int d, float a, float b, float c, float e) {
+    float* f = reinterpret_cast<float*>(t) + r * (D + 1) + d;
+    f[0] = a; f[1] = b; f[2] = c; f[3] = e;
+  }
+  template <int D> static __device__ __forceinline__ float get(const uint32_t* t, int r, int d) {
+    return reinterpret_cast<const float*>(t)[r * (D + 1) + d];
+  }
+};
+
+template <int D, typename TO>
+__global__ void __launch_bounds__(256, 3) norm_tr_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ xn, const float* __restrict__ norm,
+                                                                const float* __restrict__ dxn, const float* __restrict__ dnorm,
+                                                                int L, int Lpad, const int* __restrict__ row_of,
+                                                                TO* __restrict__ dx) {
+  constexpr int kC = D / 128;                     // 128-bit groups per lane and row
+  constexpr int kRows = kLT / 8;                  // rows per warp
+  using Tile = BwdTile<TO>;
+  __shared__ uint32_t tile[kLT * (D * Tile::kWordsPerD2 / 2 + 1)];   // [l][d] finished dx values
+  const int b = blockIdx.y, l0 = blockIdx.x * kLT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 xh[kRows][kC], g[kRows][kC];
+  float n[kRows], dn[kRows];
+  bool live[kRows];
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    const int l = l0 + warp + 8 * k;
+    long long irow = (long long)b * Lpad + l;
+    if (l < L && row_of) irow = row_of[irow];
+    live[k] = l < L && irow >= 0;
+    const size_t row = live[k] ? (size_t)irow * D : 0;
+    n[k] = live[k] ? norm[(size_t)b * Lpad + l] : 1.f;
+    dn[k] = (live[k] && dnorm) ? dnorm[(size_t)b * Lpad + l] : 0.f;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+      const int d = c * 128 + lane * 4;
+      if (live[k]) {
+        xh[k][c] = ld4_nc(xn + row + d);
+        g[k][c] = __ldg(reinterpret_cast<const float4*>(dxn + row + d));
+      } else {
+        xh[k][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g[k][c] = xh[k][c];
+      }
+    }
+  }
+  float proj[kRows];
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    proj[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) proj[k] += dot4(xh[k][c], g[k][c]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) proj[k] += __shfl_xor_sync(0xffffffffu, proj[k], o);
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    const int r = warp + 8 * k;
+    const bool clamped = n[k] <= kEps;            // x/eps is linear: no projection, no norm path
+    const float inv = 1.f / n[k];
+    const float pj = clamped ? 0.f : proj[k];
+    const float dnk = clamped ? 0.f : dn[k];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+      const float4 X = xh[k][c], G = g[k][c];
+      Tile::template put4<D>(tile, r, c * 128 + lane * 4,
+                             (G.x - X.x * pj) * inv + dnk * X.x, (G.y - X.y * pj) * inv + dnk * X.y,
+                             (G.z - X.z * pj) * inv + dnk * X.z, (G.w - X.w * pj) * inv + dnk * X.w);
+    }
+  }
+  __syncthreads();
+  const int l = l0 + lane;
+  if (l < L) {
+    TO* out = dx + ((size_t)b * D + warp) * L + l;
+#pragma unroll 8
+    for (int i = 0; i < D / 8; ++i) out[(size_t)i * 8 * L] = Tile::template get<D>(tile, lane, warp + 8 * i);
+  }
+}
+
 // scores[i,c] = (1/rho2) log sum_{t unmasked} exp(rho2 rel[i, row(c,t)]);   one thread per (i,c).
 // Dense rows: row(c,t) = c*T+t with the padding mask; compact rows: caption c owns rows [cap_ptr[c], cap_ptr[c+1]).
 __global__ void __launch_bounds__(256) word_scores_kernel(const float* __restrict__ rel, const uint8_t* __restrict__ mask,
@@ -205,10 +378,23 @@ __global__ void __launch_bounds__(256) word_scores_bwd_kernel(const float* __res
   }
 }
 
+static int g_prep_generic = 0;   // tests / A-B timing only: 1 = always take the generic kernels
+
 template <typename TI>
 static int launch_norm_tr(const void* x, int B, int D, int L, int Lpad, int out_dtype, const int* row_of, void* xn, float* norm, cudaStream_t st) {
   dim3 grid((Lpad + kLT - 1) / kLT, B);
+  if (std::is_same<TI, __nv_bfloat16>::value && out_dtype == XMC_BF16 && (D == 128 || D == 256) && !g_prep_generic) {
+    auto* xi = static_cast<const __nv_bfloat16*>(x);
+    auto* xo = static_cast<__nv_bfloat16*>(xn);
+    if (D == 128) norm_tr_bf16_kernel<128><<<grid, 256, 0, st>>>(xi, L, Lpad, row_of, xo, norm);
+    else norm_tr_bf16_kernel<256><<<grid, 256, 0, st>>>(xi, L, Lpad, row_of, xo, norm);
+    return cuda_fail(cudaGetLastError(), "norm_tr_bf16_kernel launch");
+  }
   size_t smem = (size_t)D * (kLT + 1) * sizeof(float);
+  if (smem > 48 * 1024) {   // D > 360: opt in to the large dynamic shared-memory carve-out
+    XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(norm_tr_kernel<TI, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(norm_tr_kernel<TI, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   if (out_dtype == XMC_F32)
     norm_tr_kernel<TI, float><<<grid, 256, smem, st>>>(static_cast<const TI*>(x), D, L, Lpad, row_of, static_cast<float*>(xn), norm);
   else
@@ -220,7 +406,24 @@ template <typename TX>
 static int launch_norm_tr_bwd(const void* xn, const float* norm, const float* dxn, const float* dnorm, int B, int D, int L,
                               int Lpad, int out_dtype, const int* row_of, void* dx, cudaStream_t st) {
   dim3 grid((L + kLT - 1) / kLT, B);
+  if (std::is_same<TX, __nv_bfloat16>::value && (D == 128 || D == 256) && !g_prep_generic) {
+    auto* xi = static_cast<const __nv_bfloat16*>(xn);
+    if (out_dtype == XMC_F32) {
+      auto* o = static_cast<float*>(dx);
+      if (D == 128) norm_tr_bwd_bf16_kernel<128, float><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, o);
+      else norm_tr_bwd_bf16_kernel<256, float><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, o);
+    } else {
+      auto* o = static_cast<__nv_bfloat16*>(dx);
+      if (D == 128) norm_tr_bwd_bf16_kernel<128, __nv_bfloat16><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, o);
+      else norm_tr_bwd_bf16_kernel<256, __nv_bfloat16><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, o);
+    }
+    return cuda_fail(cudaGetLastError(), "norm_tr_bwd_bf16_kernel launch");
+  }
   size_t smem = (size_t)D * (kLT + 1) * sizeof(float);
+  if (smem > 48 * 1024) {
+    XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(norm_tr_bwd_kernel<TX, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(norm_tr_bwd_kernel<TX, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   if (out_dtype == XMC_F32)
     norm_tr_bwd_kernel<TX, float><<<grid, 256, smem, st>>>(static_cast<const TX*>(xn), norm, dxn, dnorm, D, L, Lpad, row_of, static_cast<float*>(dx));
   else
@@ -239,6 +442,8 @@ static int check_nt(const void* a, const void* b, int B, int D, int L, int Lpad,
 }  // namespace xmc
 
 using namespace xmc;
+
+extern "C" void xmc_internal_set_prep_generic(int on) { xmc::g_prep_generic = on; }
 
 extern "C" int xmc_word_rows_compact(const uint8_t* mask, int Bc, int T, int* row_of, int* cap_ptr, void* stream) {
   XMC_REQUIRE(mask && row_of && cap_ptr, XMC_ERR_INVALID_ARG, "null pointer");
