@@ -13,6 +13,7 @@ Reference behaviour reproduced (citations into /root/reference/xmc_gan/train_gan
 """
 from __future__ import annotations
 
+import contextlib
 import math
 
 import torch
@@ -158,6 +159,28 @@ class SimLossFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # word–region attention contrastive loss
 # ------------------------------------------------------------------------------------------------
+@contextlib.contextmanager
+def _side_scope(ops, dev):
+    """Fork onto the backend's side stream if it has one (the CPU checker backend of the tests has none)."""
+    scope = getattr(ops, "side_scope", None)
+    if scope is None:
+        yield lambda: None
+    else:
+        with scope(dev) as mark:
+            yield mark
+
+
+def _wait_mark(ops, dev, ev):
+    if ev is not None:
+        ops.wait_mark(dev, ev)
+
+
+def _join_side(ops, dev, *tensors):
+    if getattr(ops, "join_side", None) is not None:
+        ops.join_side(dev, *tensors)
+
+
+
 TC_BACKWARD_DIMS = (128, 256)   # D handled by the tcgen05 backward kernel (others: fp32 kernel)
 
 
@@ -200,13 +223,23 @@ class WordLossFn(torch.autograd.Function):
         compact = (m_all is not None and path == _lib.PATH_BF16_TCGEN05 and (use_tc_bwd or not need_grad)
                    and getattr(ops, "supports_compaction", False))
         row_of = cap_ptr = nq_dev = None
-        if compact:
-            row_of, cap_ptr = ops.word_rows_compact(m_all)
-            nq_dev = cap_ptr[Bc:]
-            qn, qnorm = ops.normalize_transpose(w_all, T, op_dtype, row_of=row_of)   # compact rows of [Bc_g*T, D]
-        else:
-            qn, qnorm = ops.normalize_transpose(w_all, T, op_dtype)                  # [Bc_g, T, D]
+        rn_used = not normalize_values
+        dev = reg.device
+        # The word-side prologue and the zero fill of the backward's accumulators are independent of the
+        # region prologue and of the forward kernel: they go to a side stream and are joined below.
+        with _side_scope(ops, dev) as mark:
+            if compact:
+                row_of, cap_ptr = ops.word_rows_compact(m_all)
+                nq_dev = cap_ptr[Bc:]
+                qn, qnorm = ops.normalize_transpose(w_all, T, op_dtype, row_of=row_of)   # compact rows of [Bc_g*T, D]
+            else:
+                qn, qnorm = ops.normalize_transpose(w_all, T, op_dtype)                  # [Bc_g, T, D]
+            words_ready = mark()
+            ctx.bufs = None
+            if need_grad and use_tc_bwd and hasattr(ops, "backward_buffers"):
+                ctx.bufs = ops.backward_buffers(path, Bc * T, Bi, R, Rpad, D, dev, rn_used)
         kn, rnorm = ops.normalize_transpose(reg, Rpad, op_dtype)   # [Bi, Rpad, D]
+        _wait_mark(ops, dev, words_ready)
         qn2 = qn.view(Bc * T, D)
         rn = None if normalize_values else rnorm
         if compact:
@@ -230,10 +263,9 @@ class WordLossFn(torch.autograd.Function):
                                  comm.rank * nloc, nloc)
         loss3 = comm.all_reduce_sum(loss3)
 
-        # the backward's zero-filled accumulators are prepared now, beside the forward (tcgen05 path)
-        ctx.bufs = None
-        if need_grad and use_tc_bwd and chat is not None and hasattr(ops, "backward_buffers"):
-            ctx.bufs = ops.backward_buffers(path, Bc * T, Bi, R, Rpad, D, reg.device, rn is not None)
+        _join_side(ops, dev, qn, qnorm, row_of, cap_ptr, *(ctx.bufs[:4] if ctx.bufs is not None else ()))
+        if chat is None:
+            ctx.bufs = None
         ctx.comm, ctx.ops = comm, ops
         ctx.meta = (path, R, T, float(rho1), float(rho2), float(rho3), diag, num_pos, rows_total, Bc,
                     tuple(regions.shape), regions.dtype, words.dtype)
@@ -281,14 +313,15 @@ class WordLossFn(torch.autograd.Function):
                 dqn, dkn, drnorm = ops.wordregion_backward(path, qn.view(-1, D), kn, rnorm if has_rn else None, R, rho1,
                                                            lsum, cnorm, rel, grel, chat if has_chat else None,
                                                            **({"bufs": bufs} if bufs is not None else {}))
-        dreg = dwords = None
+        dreg = dwords = dw_all = None
+        dev = kn.device
+        if need_w:                                 # the two layout epilogues are independent: words on the side stream
+            with _side_scope(ops, dev):
+                dw_all = ops.normalize_transpose_backward(qn, qnorm, dqn.view(qn.shape), None, T, torch.float32,
+                                                          **({"row_of": row_of} if compact else {}))
         if need_reg:
             dreg = ops.normalize_transpose_backward(kn, rnorm, dkn, drnorm, R, reg_dtype).view(reg_shape)
         if need_w:
-            if compact:
-                dw_all = ops.normalize_transpose_backward(qn, qnorm, dqn.view(qn.shape), None, T, torch.float32,
-                                                          row_of=row_of)
-            else:
-                dw_all = ops.normalize_transpose_backward(qn, qnorm, dqn.view(qn.shape), None, T, torch.float32)
+            _join_side(ops, dev, dw_all)
             dwords = comm.reduce_scatter_sum(dw_all).to(w_dtype)
         return (dreg, dwords) + (None,) * 10

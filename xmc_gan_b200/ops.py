@@ -9,6 +9,7 @@ the product never does that.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import torch
@@ -254,33 +255,42 @@ class CudaOps:
         return lsum, cnorm, rel, chat
 
     def backward_buffers(self, path, NQ, Bi, R, Rpad, D, dev, has_rnorm):
-        """Zero-filled gradient accumulators + workspace of wordregion_backward, filled on a side stream
-        (the 80 MB fill of dkn then runs beside the forward instead of in front of the backward kernel).
-        -> (dqn, dkn, drnorm, ws, ws_bytes, event)."""
+        """Zero-filled gradient accumulators + workspace of wordregion_backward, allocated and filled on the
+        CURRENT stream.  The word loss calls this inside ``side_scope`` so that the 80 MB fill of dkn runs beside
+        the forward kernel instead of in front of the backward kernel.  -> (dqn, dkn, drnorm, ws, ws_bytes)."""
+        dqn = torch.zeros(NQ, D, device=dev, dtype=torch.float32)
+        dkn = torch.zeros(Bi, Rpad, D, device=dev, dtype=torch.float32)
+        drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if has_rnorm else None
+        ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
+        return dqn, dkn, drnorm, ws, n
+
+    # A fork/join pair for independent pieces of one autograd function (capture-safe: the join happens
+    # before the function returns, so a CUDA-graph capture never ends with a dangling forked stream).
+    @contextlib.contextmanager
+    def side_scope(self, dev):
+        """Body runs on the side stream, ordered after what the current stream holds so far.  Yields a
+        function ``mark()`` -> event recorded on the side stream at that point."""
         cur = torch.cuda.current_stream(dev)
-        if torch.cuda.is_current_stream_capturing():
-            # inside a CUDA-graph capture a forked stream must rejoin before the capture ends, which is not
-            # guaranteed here (the backward may never run): fill on the capturing stream
-            dqn = torch.zeros(NQ, D, device=dev, dtype=torch.float32)
-            dkn = torch.zeros(Bi, Rpad, D, device=dev, dtype=torch.float32)
-            drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if has_rnorm else None
-            ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            return dqn, dkn, drnorm, ws, n, ev
         side = self._side_stream(dev)
-        side.wait_stream(cur)                     # the allocator may hand out blocks the current stream still uses
+        side.wait_stream(cur)
         with torch.cuda.stream(side):
-            dqn = torch.zeros(NQ, D, device=dev, dtype=torch.float32)
-            dkn = torch.zeros(Bi, Rpad, D, device=dev, dtype=torch.float32)
-            drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if has_rnorm else None
-            ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
-            ev = torch.cuda.Event()
-            ev.record(side)
-        for t in (dqn, dkn, drnorm, ws):
+            def mark():
+                ev = torch.cuda.Event()
+                ev.record(side)
+                return ev
+            yield mark
+
+    def wait_mark(self, dev, ev):
+        torch.cuda.current_stream(dev).wait_event(ev)
+
+    def join_side(self, dev, *tensors):
+        """Current stream waits for everything on the side stream; ``tensors`` (allocated there) are marked
+        as used by the current stream for the caching allocator."""
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_stream(self._side_stream(dev))
+        for t in tensors:
             if t is not None:
                 t.record_stream(cur)
-        return dqn, dkn, drnorm, ws, n, ev
 
     def _side_stream(self, dev):
         key = (dev.type, dev.index)
@@ -297,8 +307,7 @@ class CudaOps:
         Bi, Rpad, _ = kn.shape
         dev = qn.device
         if bufs is not None:
-            dqn, dkn, drnorm, ws, n, ev = bufs
-            torch.cuda.current_stream(dev).wait_event(ev)
+            dqn, dkn, drnorm, ws, n = bufs         # zero-filled beside the forward (WordLossFn)
             self.last_workspace = ws
         else:
             dqn = torch.zeros(NQ, D, device=dev, dtype=torch.float32)
