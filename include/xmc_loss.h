@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define XMC_ABI_VERSION 2
+#define XMC_ABI_VERSION 3
 
 typedef enum {
   XMC_OK = 0,
@@ -201,6 +201,17 @@ int xmc_word_scores(const float* rel, const uint8_t* mask, const int* cap_ptr, i
 int xmc_word_scores_backward(const float* rel, const uint8_t* mask, const int* cap_ptr,
                              const float* scores, const float* dscores, int Bi, int Bc, int T,
                              int NQs, float rho2, float* grel, void* stream);
+
+/* xmc_infonce_grad followed by xmc_word_scores_backward in one launch (same arithmetic, no dscores
+ * round trip): grel[i, row(c,t)] = dLoss/dS_word(i,c) * softmax_t(rho2 rel)[t].  Arguments as in the
+ * two calls it replaces; col_stats must already be the statistics over ALL rows. */
+int xmc_word_scores_infonce_backward(const float* rel, const uint8_t* mask, const int* cap_ptr,
+                                     const float* scores, int Bi, int Bc, int T, int NQs, float rho2,
+                                     const float* labels, int diag_offset, float scale,
+                                     const float* row_stats, const float* col_stats,
+                                     const float* row_div, const float* col_div, float num_pos,
+                                     int rows_total, int cols_total, const float* grad_out,
+                                     float* grel, void* stream);
 
 #ifdef __cplusplus
 }

@@ -351,12 +351,17 @@ __global__ void __launch_bounds__(256) word_scores_kernel(const float* __restric
   const float* r = rel + i * NQs;
   const uint8_t* mk = (mask && !cap_ptr) ? mask : nullptr;
   float m = -INFINITY;
-  for (int q = lo; q < hi; ++q)
-    if (!mk || !mk[q]) m = fmaxf(m, rho2 * r[q]);
+  for (int q0 = lo; q0 < hi; q0 += 8) {            // eight loads in flight
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (q0 + u < hi && (!mk || !mk[q0 + u])) ? rho2 * __ldg(r + q0 + u) : -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m = fmaxf(m, v[u]);
+  }
   if (m == -INFINITY) { scores[k] = 0.f; return; }  // fully padded caption
   float s = 0.f;
   for (int q = lo; q < hi; ++q)
-    if (!mk || !mk[q]) s += __expf(rho2 * r[q] - m);
+    if (!mk || !mk[q]) s += __expf(rho2 * __ldg(r + q) - m);
   scores[k] = (m + logf(s)) / rho2;
 }
 
@@ -372,9 +377,16 @@ __global__ void __launch_bounds__(256) word_scores_bwd_kernel(const float* __res
   const int lo = cap_ptr ? cap_ptr[c] : c * T, hi = cap_ptr ? cap_ptr[c + 1] : c * T + T;
   const uint8_t* mk = (mask && !cap_ptr) ? mask : nullptr;
   const float sc = scores[k], ds = dscores[k];
-  for (int q = lo; q < hi; ++q) {
-    const bool pad = mk && mk[q];
-    grel[i * NQs + q] = pad ? 0.f : ds * __expf(rho2 * (rel[i * NQs + q] - sc));
+  for (int q0 = lo; q0 < hi; q0 += 8) {            // eight loads in flight
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (q0 + u < hi) ? __ldg(rel + i * NQs + q0 + u) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (q0 + u >= hi) break;
+      const bool pad = mk && mk[q0 + u];
+      grel[i * NQs + q0 + u] = pad ? 0.f : ds * __expf(rho2 * (v[u] - sc));
+    }
   }
 }
 

@@ -332,6 +332,8 @@ struct TailParams {
   const float* grad_out;
   float* out;
   int n_row_blocks;
+  // fused word-score backward (tail_grad_words_kernel)
+  const float* rel; const uint8_t* mask; const int* cap_ptr; int T, NQs; float rho2;
 };
 
 __global__ void __launch_bounds__(256) tail_stats_kernel(TailParams p) {
@@ -340,8 +342,15 @@ __global__ void __launch_bounds__(256) tail_stats_kernel(TailParams p) {
     const int i = blockIdx.x * 8 + warp;
     if (i >= p.Bq) return;
     Stat st; st.init();
-    for (int j = lane; j < p.Bk; j += 32)
-      st.add(p.scale * __ldg(p.scores + (size_t)i * p.Bk + j), label_at(p.labels, p.Bk, i, j, p.diag));
+    const float* row = p.scores + (size_t)i * p.Bk;
+    for (int j0 = lane; j0 < p.Bk; j0 += 4 * 32) {   // four loads in flight, consumed in index order
+      float z[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) z[u] = (j0 + 32 * u < p.Bk) ? __ldg(row + j0 + 32 * u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + 32 * u < p.Bk) st.add(p.scale * z[u], label_at(p.labels, p.Bk, i, j0 + 32 * u, p.diag));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) st.merge(shfl_xor_stat(st, o));
     if (lane == 0) {
@@ -354,8 +363,14 @@ __global__ void __launch_bounds__(256) tail_stats_kernel(TailParams p) {
     const int j = (blockIdx.x - p.n_row_blocks) * 32 + lane;
     Stat st; st.init();
     if (j < p.Bk)
-      for (int i = warp; i < p.Bq; i += 8)
-        st.add(p.scale * __ldg(p.scores + (size_t)i * p.Bk + j), label_at(p.labels, p.Bk, i, j, p.diag));
+      for (int i0 = warp; i0 < p.Bq; i0 += 4 * 8) {
+        float z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) z[u] = (i0 + 8 * u < p.Bq) ? __ldg(p.scores + (size_t)(i0 + 8 * u) * p.Bk + j) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + 8 * u < p.Bq) st.add(p.scale * z[u], label_at(p.labels, p.Bk, i0 + 8 * u, j, p.diag));
+      }
     sh[warp][lane] = st;
     __syncthreads();
     if (warp == 0 && j < p.Bk) {
@@ -404,6 +419,36 @@ __global__ void __launch_bounds__(256) tail_grad_kernel(TailParams p) {
     const float inv_nc = p.inv_cols_total / (p.col_div ? p.col_div[j] : p.num_pos);
     p.out[k] = go * dscore(z, lab, p.row_stats[i], p.row_stats[p.Bq + i], inv_nr,
                            p.col_stats[j], p.col_stats[p.Bk + j], inv_nc);
+  }
+}
+
+// tail_grad followed by the backward of the per-caption log-sum-exp, in one pass: thread (i,c) forms
+// dS_word(i,c) as tail_grad_kernel does and spreads it over the caption's word rows,
+// grel[i, row(c,t)] = dS(i,c) * exp(rho2 * (rel[i,row] - S_word(i,c)))   (0 for padding words).
+__global__ void __launch_bounds__(256) tail_grad_words_kernel(TailParams p) {
+  const size_t k = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (k >= (size_t)p.Bq * p.Bk) return;
+  const int i = (int)(k / p.Bk), c = (int)(k % p.Bk);
+  const float sc = p.scores[k];
+  const float go = __ldg(p.grad_out) * p.scale;
+  const float inv_nr = p.inv_rows_total / (p.row_div ? p.row_div[i] : p.num_pos);
+  const float inv_nc = p.inv_cols_total / (p.col_div ? p.col_div[c] : p.num_pos);
+  const float ds = go * dscore(p.scale * sc, label_at(p.labels, p.Bk, i, c, p.diag), p.row_stats[i], p.row_stats[p.Bq + i],
+                               inv_nr, p.col_stats[c], p.col_stats[p.Bk + c], inv_nc);
+  const int lo = p.cap_ptr ? p.cap_ptr[c] : c * p.T, hi = p.cap_ptr ? p.cap_ptr[c + 1] : c * p.T + p.T;
+  const uint8_t* mk = (p.mask && !p.cap_ptr) ? p.mask : nullptr;
+  const float* r = p.rel + (size_t)i * p.NQs;
+  float* g = p.out + (size_t)i * p.NQs;
+  for (int q0 = lo; q0 < hi; q0 += 8) {            // eight loads in flight
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (q0 + u < hi) ? __ldg(r + q0 + u) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (q0 + u >= hi) break;
+      const bool pad = mk && mk[q0 + u];
+      g[q0 + u] = pad ? 0.f : ds * __expf(p.rho2 * (v[u] - sc));
+    }
   }
 }
 
@@ -597,6 +642,29 @@ extern "C" int xmc_infonce_grad(const float* scores, int Bq, int Bk, const float
   int grid = (int)((n + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
   tail_grad_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
   return cuda_fail(cudaGetLastError(), "tail_grad_kernel launch");
+}
+
+extern "C" int xmc_word_scores_infonce_backward(const float* rel, const uint8_t* mask, const int* cap_ptr,
+                                                const float* scores, int Bi, int Bc, int T, int NQs, float rho2,
+                                                const float* labels, int diag_offset, float scale,
+                                                const float* row_stats, const float* col_stats,
+                                                const float* row_div, const float* col_div, float num_pos,
+                                                int rows_total, int cols_total, const float* grad_out,
+                                                float* grel, void* stream) {
+  if (int rc = check_tail(scores, Bi, Bc)) return rc;
+  XMC_REQUIRE(rel && row_stats && col_stats && grad_out && grel, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(T > 0 && NQs >= Bc && rho2 > 0.f, XMC_ERR_INVALID_ARG, "bad shape / rho2");
+  XMC_REQUIRE(rows_total > 0 && cols_total > 0 && num_pos > 0.f, XMC_ERR_INVALID_ARG, "bad totals / num_pos");
+  TailParams p{};
+  p.scores = scores; p.Bq = Bi; p.Bk = Bc; p.labels = labels; p.diag = diag_offset; p.scale = scale;
+  p.row_stats = row_stats; p.col_stats = col_stats;
+  p.row_div = row_div; p.col_div = col_div; p.num_pos = num_pos;
+  p.inv_rows_total = 1.f / rows_total; p.inv_cols_total = 1.f / cols_total;
+  p.grad_out = grad_out; p.out = grel;
+  p.rel = rel; p.mask = mask; p.cap_ptr = cap_ptr; p.T = T; p.NQs = NQs; p.rho2 = rho2;
+  const size_t n = (size_t)Bi * Bc;
+  tail_grad_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(p);
+  return cuda_fail(cudaGetLastError(), "tail_grad_words_kernel launch");
 }
 
 extern "C" int xmc_make_labels(const float* sim, int B, float p, float smooth_global,

@@ -294,16 +294,20 @@ class WordLossFn(torch.autograd.Function):
             return (None,) * 12
         bufs, ctx.bufs = ctx.bufs, None           # single use: the kernels accumulate into them
         go = grad_out.detach().to(torch.float32).contiguous()
-        dscores = ops.infonce_grad(scores, lab, diag, rho3, row_stats, col_stats, row_div, col_div, num_pos,
-                                   rows_total, Bc, go)
+        cap = {"cap_ptr": cap_ptr} if compact else {}
+        if hasattr(ops, "word_scores_infonce_backward"):     # d loss / d rel in one launch
+            grel = ops.word_scores_infonce_backward(rel, m_all, scores, T, rho2, lab, diag, rho3, row_stats, col_stats,
+                                                    row_div, col_div, num_pos, rows_total, Bc, go, **cap)
+        else:
+            dscores = ops.infonce_grad(scores, lab, diag, rho3, row_stats, col_stats, row_div, col_div, num_pos,
+                                       rows_total, Bc, go)
+            grel = ops.word_scores_backward(rel, m_all, scores, dscores, T, rho2, **cap)
         D = qn.shape[2]
         if compact:
             nq_dev = cap_ptr[Bc:]
-            grel = ops.word_scores_backward(rel, m_all, scores, dscores, T, rho2, cap_ptr=cap_ptr)
             dqn, dkn, drnorm = ops.wordregion_backward(path, qn.view(-1, D), kn, rnorm if has_rn else None, R, rho1,
                                                        lsum, cnorm, rel, grel, chat, nq_dev=nq_dev, bufs=bufs)
         else:
-            grel = ops.word_scores_backward(rel, m_all, scores, dscores, T, rho2)
             if path == _lib.PATH_BF16_TCGEN05 and not has_chat:
                 # D outside the tcgen05 backward kernel's set: run the fp32 CUDA-core backward kernel on the
                 # (bf16-rounded) operands the forward used.  Still libxmcloss, never PyTorch.

@@ -179,6 +179,7 @@ class CudaOps:
 
     # -- word-region --------------------------------------------------------------------------
     supports_compaction = True     # the tcgen05 kernels visit only the non-padding word rows
+    use_side_stream = True         # word-side prologue / zero fills / word epilogue beside the main stream
 
     def word_rows_compact(self, mask_u8):
         """mask [Bc, T] (non-zero = padding) -> row_of [Bc*T] int32 (-1 = dropped), cap_ptr [Bc+1] int32."""
@@ -270,9 +271,13 @@ class CudaOps:
     def side_scope(self, dev):
         """Body runs on the side stream, ordered after what the current stream holds so far.  Yields a
         function ``mark()`` -> event recorded on the side stream at that point."""
+        if getattr(self, "events", None) is not None or not self.use_side_stream:
+            yield lambda: None                 # per-kernel timing (enable_timing): one stream, clean event pairs
+            return
         cur = torch.cuda.current_stream(dev)
         side = self._side_stream(dev)
         side.wait_stream(cur)
+        self._forked = True
         with torch.cuda.stream(side):
             def mark():
                 ev = torch.cuda.Event()
@@ -286,6 +291,9 @@ class CudaOps:
     def join_side(self, dev, *tensors):
         """Current stream waits for everything on the side stream; ``tensors`` (allocated there) are marked
         as used by the current stream for the caching allocator."""
+        if not getattr(self, "_forked", False):
+            return
+        self._forked = False
         cur = torch.cuda.current_stream(dev)
         cur.wait_stream(self._side_stream(dev))
         for t in tensors:
@@ -340,6 +348,21 @@ class CudaOps:
         with torch.cuda.device_of(rel):
             _lib.check(self.L.xmc_word_scores_backward(_p(rel), _p(mask_u8), _p(cap_ptr), _p(scores), _p(dscores),
                                                        Bi, Bc, T, NQs, float(rho2), _p(grel), _stream()))
+        self.launches += 1
+        return grel
+
+    def word_scores_infonce_backward(self, rel, mask_u8, scores, T, rho2, labels, diag, scale, row_stats, col_stats,
+                                     row_div, col_div, num_pos, rows_total, cols_total, grad_out, cap_ptr=None):
+        """infonce_grad + word_scores_backward in one launch -> grel [Bi, NQs]."""
+        _cuda(rel, scores, grad_out)
+        Bi, Bc = scores.shape
+        NQs = rel.shape[1]
+        grel = torch.empty_like(rel)
+        with torch.cuda.device_of(rel):
+            _lib.check(self.L.xmc_word_scores_infonce_backward(
+                _p(rel), _p(mask_u8), _p(cap_ptr), _p(scores), Bi, Bc, T, NQs, float(rho2), _p(labels), diag,
+                float(scale), _p(row_stats), _p(col_stats), _p(row_div), _p(col_div), float(num_pos), rows_total,
+                cols_total, _p(grad_out), _p(grel), _stream()))
         self.launches += 1
         return grel
 
