@@ -14,7 +14,7 @@ kn, rnorm = ops.normalize_transpose(regions, 304, torch.bfloat16)
 qn = qn.view(B * T, D)
 for _ in range(2):
     ops.wordregion_forward(1, qn, kn, rnorm, R, 5.0, save_context=True)
-hook(4)
+hook(4 | (int(sys.argv[1]) if len(sys.argv) > 1 else 0))
 ops.wordregion_forward(1, qn, kn, rnorm, R, 5.0, save_context=True)
 torch.cuda.synchronize()
 hook(0)
@@ -30,3 +30,5 @@ print("image | c_full ready, C in registers (c_empty), stores issued")
 for ii in range(0, 6):
     e = [int(v) - t0 for v in tr[2, ii]]
     print(f"{ii:3d} | {e[0]:7d} {e[1]:7d} {e[3]:7d} | read={e[1]-e[0]} rest={e[3]-e[1]}")
+clk, ns, nimg = (int(v) for v in tr[2, 63, :3])
+print(f"CTA 0 main loop: {clk} SM cycles in {ns} ns over {nimg} images = {clk / max(ns, 1) * 1e3:.0f} MHz effective SM clock")

@@ -141,6 +141,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -443,6 +448,8 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
       const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
       const bool issuer = (threadIdx.x == 384);
       int ic = 0;
+      long long clk0 = 0, ns0 = 0;                   // trace only: SM cycles vs wall time of this CTA's main loop
+      if (p.trace && issuer && blockIdx.x == 0) { clk0 = clock64(); ns0 = global_timer_ns(); }
       SegIter it = seg_iter(NQ, p.Bi);
       Seg sg;
       while (it.next(sg)) {
@@ -534,6 +541,10 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
         }
       }
       if (issuer) bulk_wait<0>();                             // all context stores performed before exit
+      if (p.trace && issuer && blockIdx.x == 0) {
+        long long* t = p.trace + (2 * 64 + 63) * 4;
+        t[0] = clock64() - clk0; t[1] = global_timer_ns() - ns0; t[2] = ic;
+      }
     }
   }
   tc_fence_before();
