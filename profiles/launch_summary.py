@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv): the launches of the LAST
-bench step (between the last two word-region backward kernels) with their share of that step.
+"""Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv): the launches of ONE eager
+bench step (the shortest run of launches between two consecutive word-region backward kernels; longer
+runs contain the bench's own bookkeeping, e.g. the graph-replay validation) with their share of that step.
     python profiles/launch_summary.py gpurun_out/launches.csv"""
 import csv
 import sys
@@ -11,7 +12,7 @@ hdr = rows[hi]
 ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
 seq = [(r[ki], float(r[vi].replace(',', '')) / 1000.0) for r in rows[hi + 2:] if len(r) > vi]
 idx = [i for i, (k, v) in enumerate(seq) if 'wr_bwd' in k]
-a, b = idx[-2] + 1, idx[-1] + 1
+a, b = min(((i + 1, j + 1) for i, j in zip(idx, idx[1:])), key=lambda ab: ab[1] - ab[0])
 # the step's trailing kernels (after the last word-region backward) belong to it as well: take the same
 # number of launches that followed the previous one before the next step began
 step = seq[a:b]
