@@ -36,8 +36,33 @@ def _cuda(*ts):
             raise RuntimeError("xmc_gan_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """cudaStream_t of the current stream of the current device (one C call: this runs ~25 times per step)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
+
+
+class _on:
+    """``with _on(t):`` makes t's device current for the launch — a no-op (one C call) when it already is,
+    which is the case in a one-process-per-GPU job; torch.cuda.device_of costs ~15 us per use."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, t):
+        self.idx = t.device.index
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.idx is not None and self.idx != self.prev:
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.idx is not None and self.idx != self.prev:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _f32c(t):
@@ -71,6 +96,7 @@ class CudaOps:
         self.launches = 0      # kernels launched through this backend (bench.py's gpu_launches)
         self.events = None     # name -> [(start, stop)] CUDA events when kernel timing is on
         self.last_workspace = None
+        self.check_errors = bool(os.environ.get("XMC_CHECK_ERRORS"))   # tests: read the kernels' error word back
 
     def enable_timing(self, on=True):
         """Record CUDA events (current stream) around the named hot kernels; see kernel_ms()."""
@@ -91,7 +117,7 @@ class CudaOps:
         Bq, D = a.shape
         Bk = b.shape[0]
         scores = torch.empty(Bq, Bk, device=a.device, dtype=torch.float32)
-        with torch.cuda.device_of(a):
+        with _on(a):
             _lib.check(self.L.xmc_cosine_scores(_p(a), _p(b), Bq, Bk, D, _dt(a), _p(scores), None, None, _stream()))
         self.launches += 1
         return scores
@@ -106,7 +132,7 @@ class CudaOps:
         inv_b = torch.empty(Bk, device=dev, dtype=torch.float32)
         row_stats = torch.empty(3, Bq, device=dev, dtype=torch.float32)
         col_stats = torch.empty(3, Bk, device=dev, dtype=torch.float32)
-        with torch.cuda.device_of(a), self._timed("simloss_fwd"):
+        with _on(a), self._timed("simloss_fwd"):
             _lib.check(self.L.xmc_simloss_forward(_p(a), _p(b), Bq, Bk, D, _dt(a), _p(labels), diag, scale,
                                                   _p(scores), _p(inv_a), _p(inv_b), _p(row_stats), _p(col_stats),
                                                   _stream()))
@@ -122,7 +148,7 @@ class CudaOps:
         db = torch.empty_like(b) if need_b else None
         if not (need_a or need_b):
             return None, None
-        with torch.cuda.device_of(a), self._timed("simloss_bwd"):
+        with _on(a), self._timed("simloss_bwd"):
             _lib.check(self.L.xmc_simloss_backward(
                 _p(a), _p(b), Bq, Bk, D, _dt(a), _p(scores), _p(inv_a), _p(inv_b), _p(labels), diag, scale,
                 _p(row_stats), _p(col_stats), _p(row_div), _p(col_div), float(num_pos), rows_total, cols_total,
@@ -136,7 +162,7 @@ class CudaOps:
         Bq, Bk = scores.shape
         row_stats = torch.empty(3, Bq, device=scores.device, dtype=torch.float32)
         col_stats = torch.empty(3, Bk, device=scores.device, dtype=torch.float32)
-        with torch.cuda.device_of(scores):
+        with _on(scores):
             _lib.check(self.L.xmc_infonce_stats(_p(scores), Bq, Bk, _p(labels), diag, scale,
                                                 _p(row_stats), _p(col_stats), _stream()))
         self.launches += 1
@@ -146,7 +172,7 @@ class CudaOps:
                      col_begin, col_count):
         _cuda(row_stats, col_stats)
         out = torch.empty(3, device=row_stats.device, dtype=torch.float32)
-        with torch.cuda.device_of(row_stats):
+        with _on(row_stats):
             _lib.check(self.L.xmc_infonce_loss(_p(row_stats), _p(col_stats), row_stats.shape[1], col_stats.shape[1],
                                                _p(row_div), _p(col_div), float(num_pos), rows_total, cols_total,
                                                col_begin, col_count, _p(out), _stream()))
@@ -158,7 +184,7 @@ class CudaOps:
         _cuda(scores, grad_out)
         Bq, Bk = scores.shape
         ds = torch.empty_like(scores)
-        with torch.cuda.device_of(scores):
+        with _on(scores):
             _lib.check(self.L.xmc_infonce_grad(_p(scores), Bq, Bk, _p(labels), diag, scale, _p(row_stats),
                                                _p(col_stats), _p(row_div), _p(col_div), float(num_pos),
                                                rows_total, cols_total, _p(grad_out), _p(ds), _stream()))
@@ -171,7 +197,7 @@ class CudaOps:
         labels = torch.empty(B, B, device=sim.device, dtype=torch.float32)
         row_count = torch.empty(B, device=sim.device, dtype=torch.float32)
         tmp = torch.empty(B, device=sim.device, dtype=torch.float32)
-        with torch.cuda.device_of(sim):
+        with _on(sim):
             _lib.check(self.L.xmc_make_labels(_p(sim), B, float(p), float(smooth_global), _p(labels),
                                               _p(row_count), _p(tmp), _stream()))
         self.launches += 2
@@ -187,7 +213,7 @@ class CudaOps:
         Bc, T = mask_u8.shape
         row_of = torch.empty(Bc * T, device=mask_u8.device, dtype=torch.int32)
         cap_ptr = torch.empty(Bc + 1, device=mask_u8.device, dtype=torch.int32)
-        with torch.cuda.device_of(mask_u8):
+        with _on(mask_u8):
             _lib.check(self.L.xmc_word_rows_compact(_p(mask_u8), Bc, T, _p(row_of), _p(cap_ptr), _stream()))
         self.launches += 1
         return row_of, cap_ptr
@@ -200,7 +226,7 @@ class CudaOps:
         else:
             xn = torch.empty(B, Lpad, D, device=x.device, dtype=out_dtype)
         norm = torch.empty(B, Lpad, device=x.device, dtype=torch.float32)
-        with torch.cuda.device_of(x):
+        with _on(x):
             _lib.check(self.L.xmc_normalize_transpose(_p(x), B, D, L, Lpad, _dt(x), _DT[out_dtype], _p(row_of),
                                                       _p(xn), _p(norm), _stream()))
         self.launches += 1
@@ -210,7 +236,7 @@ class CudaOps:
         _cuda(xn, dxn)
         B, Lpad, D = xn.shape
         dx = torch.empty(B, D, L, device=xn.device, dtype=out_dtype)
-        with torch.cuda.device_of(xn):
+        with _on(xn):
             _lib.check(self.L.xmc_normalize_transpose_backward(_p(xn), _p(norm), _p(dxn), _p(dnorm), B, D, L, Lpad,
                                                                _dt(xn), _DT[out_dtype], _p(row_of), _p(dx), _stream()))
         self.launches += 1
@@ -219,7 +245,7 @@ class CudaOps:
     def _check_error_word(self, ws, what):
         """XMC_CHECK_ERRORS=1 (tests): synchronise and raise if a bounded mbarrier wait of the tcgen05 kernel
         timed out (word 0 of its workspace).  Off by default: the product path never synchronises."""
-        if ws is not None and os.environ.get("XMC_CHECK_ERRORS") and not torch.cuda.is_current_stream_capturing():
+        if ws is not None and self.check_errors and not torch.cuda.is_current_stream_capturing():
             code = int(ws[:4].view(torch.int32)[0])
             if code != 0:
                 raise RuntimeError(f"{what}: pipeline wait timed out inside the kernel (code {code})")
@@ -247,7 +273,7 @@ class CudaOps:
         if save_context and path == _lib.PATH_BF16_TCGEN05:
             chat = torch.empty(Bi, NQ, D, device=dev, dtype=torch.bfloat16)
         ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
-        with torch.cuda.device_of(qn), self._timed("wordregion_fwd"):
+        with _on(qn), self._timed("wordregion_fwd"):
             _lib.check(self.L.xmc_wordregion_forward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
                                                      _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(nq_dev), _p(ws), n,
                                                      _stream()))
@@ -322,7 +348,7 @@ class CudaOps:
             dkn = torch.zeros(Bi, Rpad, D, device=dev, dtype=torch.float32)
             drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if rnorm is not None else None
             ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
-        with torch.cuda.device_of(qn), self._timed("wordregion_bwd"):
+        with _on(qn), self._timed("wordregion_bwd"):
             _lib.check(self.L.xmc_wordregion_backward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
                                                       _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(grel), _p(dqn), _p(dkn),
                                                       _p(drnorm), _p(nq_dev), _p(ws), n, _stream()))
@@ -334,7 +360,7 @@ class CudaOps:
         _cuda(rel, mask_u8)
         Bi, NQs = rel.shape
         scores = torch.empty(Bi, Bc, device=rel.device, dtype=torch.float32)
-        with torch.cuda.device_of(rel):
+        with _on(rel):
             _lib.check(self.L.xmc_word_scores(_p(rel), _p(mask_u8), _p(cap_ptr), Bi, Bc, T, NQs, float(rho2),
                                               _p(scores), _stream()))
         self.launches += 1
@@ -345,7 +371,7 @@ class CudaOps:
         Bi, Bc = scores.shape
         NQs = rel.shape[1]
         grel = torch.empty_like(rel)
-        with torch.cuda.device_of(rel):
+        with _on(rel):
             _lib.check(self.L.xmc_word_scores_backward(_p(rel), _p(mask_u8), _p(cap_ptr), _p(scores), _p(dscores),
                                                        Bi, Bc, T, NQs, float(rho2), _p(grel), _stream()))
         self.launches += 1
@@ -358,7 +384,7 @@ class CudaOps:
         Bi, Bc = scores.shape
         NQs = rel.shape[1]
         grel = torch.empty_like(rel)
-        with torch.cuda.device_of(rel):
+        with _on(rel):
             _lib.check(self.L.xmc_word_scores_infonce_backward(
                 _p(rel), _p(mask_u8), _p(cap_ptr), _p(scores), Bi, Bc, T, NQs, float(rho2), _p(labels), diag,
                 float(scale), _p(row_stats), _p(col_stats), _p(row_div), _p(col_div), float(num_pos), rows_total,
