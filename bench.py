@@ -217,7 +217,13 @@ def main():
         """Per-step CUDA events on the current stream, L2 flushed (untimed) between steps."""
         evs = []
         barrier()
-        for _ in range(steps):
+        for i in range(steps):
+            # Keep the host at most two steps ahead of the GPU, as a training loop that reads its loss does.
+            # Unbounded, the eager N > 1 loop runs ~17 steps ahead (launch-queue depth) and the caching
+            # allocator answers the growing set of in-flight buffers with cudaMalloc/cudaFree stalls of
+            # ~100 ms (profiles/exp_n2_steps.py); the GPU never idles with two steps queued.
+            if i >= 2:
+                evs[i - 2][1].synchronize()
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record()
@@ -240,10 +246,11 @@ def main():
     ops.enable_timing(False)
     launches = (ops.launches - l0) // K
     ms_eager = timed(lambda: step(devin), K)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(K):
+    for _ in range(min(K, 8)):                                # few enough that the launch queue never fills
         step(devin)
-    host_ms = (time.perf_counter() - t0) / K * 1e3            # host time to ENQUEUE one step (python + launches)
+    host_ms = (time.perf_counter() - t0) / min(K, 8) * 1e3    # host time to ENQUEUE one step (python + launches)
     torch.cuda.synchronize()
 
     # ---- the step as a CUDA graph -----------------------------------------------------------------

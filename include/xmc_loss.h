@@ -85,6 +85,11 @@ int xmc_simloss_forward(const void* a, const void* b, int Bq, int Bk, int D, int
 int xmc_infonce_stats(const float* scores, int Bq, int Bk, const float* labels, int diag_offset,
                       float scale, float* row_stats, float* col_stats, void* stream);
 
+/* Row-sharded score matrix (one process per GPU): merge the column statistics of `world` shards,
+ * gathered as [world][3][Bk] (rank order irrelevant), into the statistics over all rows:
+ * col_stats[0] = log-sum-exp over shards of their log-sum-exps, [1], [2] = sums of the label sums. */
+int xmc_infonce_combine_stats(const float* gathered, int world, int Bk, float* col_stats, void* stream);
+
 /* Loss from statistics — train_gan.py:104-113 (s0 = column direction, s1 = row direction).
  * row_div[Bq] / col_div[Bk]: per-row / per-column divisor ("num_pos" when it is the
  * (labels>0).sum(1) vector, :99); NULL means the scalar num_pos (1 or 2, :94-97).

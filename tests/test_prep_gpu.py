@@ -157,3 +157,19 @@ def test_fused_word_tail_backward_equals_the_two_calls(compact, dense_labels, di
     n = int(cap_ptr[Bc]) if compact else Bc * T          # compact: columns beyond the valid rows are never written
     assert torch.equal(one[:, :n], two[:, :n])
     assert two[:, :n].abs().sum() > 0
+
+
+@pytest.mark.parametrize("world,Bk", [(2, 512), (8, 2048), (3, 37)])
+def test_combine_col_stats_matches_torch(world, Bk):
+    """xmc_infonce_combine_stats == logsumexp over shards (row 0) and sums (rows 1-2)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(world * 1000 + Bk)
+    gathered = (torch.randn(world, 3, Bk, generator=g) * 5).cuda()
+    gathered[:, 0, 3] = float("-inf")                      # a column no shard has seen
+    gathered[0, 0, 5] = float("-inf")                      # ... and one a single shard has not
+    out = ops.combine_col_stats(gathered)
+    ref0 = torch.logsumexp(gathered[:, 0].double(), dim=0)
+    assert torch.equal(torch.isinf(out[0]), torch.isinf(ref0)) and bool((out[0][torch.isinf(out[0])] < 0).all())
+    fin = ~torch.isinf(ref0)
+    assert torch.allclose(out[0][fin].double(), ref0[fin], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(out[1:].double(), gathered[:, 1:].double().sum(0), rtol=1e-6, atol=1e-5)

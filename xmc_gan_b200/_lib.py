@@ -51,6 +51,7 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "xmc_word_scores": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "xmc_word_scores_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "xmc_infonce_combine_stats": (_i, [_vp, _i, _i, _vp, _vp]),
     "xmc_word_scores_infonce_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _i, _f, _vp, _vp, _vp, _vp, _f,
                                               _i, _i, _vp, _vp, _vp]),
 }

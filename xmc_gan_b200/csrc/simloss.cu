@@ -384,6 +384,26 @@ __global__ void __launch_bounds__(256) tail_stats_kernel(TailParams p) {
   }
 }
 
+// Column statistics of `world` row shards -> statistics over all rows: log-sum-exp of the shards'
+// log-sum-exps, sums of the label sums.  gathered: [world][3][Bk], out: [3][Bk]; one thread per column.
+__global__ void __launch_bounds__(256) combine_stats_kernel(const float* __restrict__ g, int world, int Bk,
+                                                             float* __restrict__ out) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= Bk) return;
+  float m = -INFINITY, sl = 0.f, slz = 0.f;
+  for (int w = 0; w < world; ++w) m = fmaxf(m, g[(size_t)w * 3 * Bk + j]);
+  float s = 0.f;
+  for (int w = 0; w < world; ++w) {
+    const float* gw = g + (size_t)w * 3 * Bk;
+    s += (m == -INFINITY) ? 0.f : expf(gw[j] - m);
+    sl += gw[Bk + j];
+    slz += gw[2 * Bk + j];
+  }
+  out[j] = (m == -INFINITY) ? -INFINITY : m + logf(s);
+  out[Bk + j] = sl;
+  out[2 * Bk + j] = slz;
+}
+
 // loss_out[0] = s0_part + s1_part, [1] = s0_part (columns), [2] = s1_part (rows); single CTA.
 __global__ void __launch_bounds__(256) tail_loss_kernel(TailParams p) {
   float s0 = 0.f, s1 = 0.f;
@@ -606,6 +626,13 @@ extern "C" int xmc_infonce_stats(const float* scores, int Bq, int Bk, const floa
   int grid = p.n_row_blocks + (Bk + 31) / 32;
   tail_stats_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
   return cuda_fail(cudaGetLastError(), "tail_stats_kernel launch");
+}
+
+extern "C" int xmc_infonce_combine_stats(const float* gathered, int world, int Bk, float* col_stats, void* stream) {
+  XMC_REQUIRE(gathered && col_stats, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(world > 0 && Bk > 0, XMC_ERR_INVALID_ARG, "bad sizes world=%d Bk=%d", world, Bk);
+  combine_stats_kernel<<<(Bk + 255) / 256, 256, 0, as_stream(stream)>>>(gathered, world, Bk, col_stats);
+  return cuda_fail(cudaGetLastError(), "combine_stats_kernel launch");
 }
 
 extern "C" int xmc_infonce_loss(const float* row_stats, const float* col_stats, int Bq, int Bk,

@@ -168,6 +168,16 @@ class CudaOps:
         self.launches += 1
         return row_stats, col_stats
 
+    def combine_col_stats(self, gathered):
+        """[world, 3, Bk] per-shard column statistics -> [3, Bk] statistics over all rows (one launch)."""
+        _cuda(gathered)
+        world, _, Bk = gathered.shape
+        out = torch.empty(3, Bk, device=gathered.device, dtype=torch.float32)
+        with _on(gathered):
+            _lib.check(self.L.xmc_infonce_combine_stats(_p(gathered), world, Bk, _p(out), _stream()))
+        self.launches += 1
+        return out
+
     def infonce_loss(self, row_stats, col_stats, row_div, col_div, num_pos, rows_total, cols_total,
                      col_begin, col_count):
         _cuda(row_stats, col_stats)
