@@ -257,3 +257,44 @@ def test_never_written_tmem_columns_are_not_read(B, D, T_, R):
     (l0, r0, w0), (l1, r1, w1) = out
     assert torch.isfinite(l1) and torch.isfinite(r1).all() and torch.isfinite(w1).all()
     assert lerr(l1, l0) <= 1e-6 and nerr(r1, r0) <= 2e-3 and nerr(w1, w0) <= 2e-3
+
+
+def test_word_loss_is_cuda_graph_capturable():
+    """The whole word loss (side-stream prologue, device-side row count, fused tail backward) can be captured
+    with torch.cuda.graph and replayed: nothing in it synchronises with the host, and the side stream it
+    forks is joined before the autograd function returns.  Replays must reproduce the eager result."""
+    from util import word_inputs
+    from xmc_gan_b200 import train_gan as T
+    B, D, T_, R = 24, 128, 9, 70
+    words, regions, mask = word_inputs(B, D, T_, R, seed=11)
+    r = regions.bfloat16().cuda().requires_grad_()
+    w = words.bfloat16().cuda().requires_grad_()
+    m = mask.cuda()
+    labels = T.make_labels(B, torch.randn(B, 16).cuda(), False)
+
+    def step():
+        r.grad = None; w.grad = None
+        loss = T.word_loss(r, w, m, labels, False, precision="bf16")
+        loss.backward()
+        return loss
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    ref_loss = float(step().detach())
+    ref_r, ref_w = r.grad.clone(), w.grad.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        loss = step()
+    for _ in range(3):
+        r.grad.zero_(); w.grad.zero_()       # the captured backward ACCUMULATES into the captured .grad tensors
+        g.replay()
+    torch.cuda.synchronize()
+    assert abs(float(loss.detach()) - ref_loss) <= 1e-5 * abs(ref_loss)
+    # fp32 atomics: summation order differs from run to run
+    assert float((r.grad.float() - ref_r.float()).norm() / ref_r.float().norm()) < 1e-2
+    assert float((w.grad.float() - ref_w.float()).norm() / ref_w.float().norm()) < 1e-2
