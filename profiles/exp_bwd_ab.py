@@ -1,0 +1,31 @@
+"""Same-box A/B of the backward kernel's context-tile hand-over (debug flag 64 = whole tile, as before the
+split into feature halves): word_loss fwd+bwd at COCO-256 with the bench masks, kernel times from CUDA
+events around the launches, L2 flushed between runs."""
+import sys, torch
+sys.path.insert(0, '.')
+import bench
+from xmc_gan_b200 import _lib, train_gan as T
+from xmc_gan_b200.ops import default_ops
+ops = default_ops()
+inp = {k: v.cuda() for k, v in bench.make_inputs(256, 1000, torch.bfloat16).items()}
+labels = T.make_labels(256, inp["sent"], False)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+hook = _lib.lib().xmc_internal_set_debug_dump
+def run(flag, n=20):
+    hook(flag)
+    def step():
+        v = inp["regions"].detach().requires_grad_(); w = inp["words"].detach().requires_grad_()
+        loss = T.word_loss(v, w, inp["mask"], labels, False, rho1=5., rho2=5., rho3=10., precision="bf16")
+        loss.backward()
+        return loss, v.grad
+    for _ in range(3): step()
+    ops.enable_timing(True)
+    for _ in range(n):
+        flush.zero_()
+        loss, g = step()
+    k = ops.kernel_ms()
+    ops.enable_timing(False)
+    hook(0)
+    return round(k["wordregion_bwd"][1] * 1e3, 1), round(float(loss), 6), round(float(g.float().norm()), 5)
+for rnd in range(3):
+    print({"halves": run(0), "whole": run(64)}, flush=True)

@@ -758,8 +758,6 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   float* rn_s = reinterpret_cast<float*>(smem + Cfg::kOffRn);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* ch_full = bars + 1;
-  uint64_t* ch_empty = bars + 2;
   uint64_t* kv_full = bars + 3;    // [2]
   uint64_t* kv_empty = bars + 5;   // [2]
   uint64_t* sw_full = bars + 7;
@@ -769,7 +767,13 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint64_t* dk_empty = bars + 11;
   uint64_t* dq_full = bars + 12;   // per segment: every MMA of the segment has executed
   uint64_t* dq_empty = bars + 13;  // per segment: dQ has been read out of TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  // The context tile is handed over in kCH feature halves (one per M-tile of dK^T): at the end of an image the
+  // half that dK^T's first M-tile has finished with is refilled while the second M-tile still runs, and the
+  // next image's W starts on the first half while the second is in flight.
+  constexpr int kCH = Cfg::kTilesD;
+  uint64_t* ch_full = bars + 14;   // [kCH]
+  uint64_t* ch_empty = bars + 16;  // [kCH]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   int* abort_flag = reinterpret_cast<int*>(tmem_slot + 1);
   const WaitCtx wc{abort_flag, p.err};
 
@@ -780,7 +784,8 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   if (threadIdx.x == 0) {
     *abort_flag = 0;
-    mbar_init(q_full, 1); mbar_init(ch_full, 1); mbar_init(ch_empty, 1);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(ch_full + s, 1); mbar_init(ch_empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
     mbar_init(sw_full, 1); mbar_init(sw_consumed, 256); mbar_init(xy_full, 256);
     mbar_init(dk_full, 1); mbar_init(dk_empty, 128); mbar_init(dq_full, 1); mbar_init(dq_empty, 256);
@@ -835,11 +840,16 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 tma_load_3d(kv + st * Cfg::kKvStage + kb * Cfg::kKvBlock, &tm_k, kb * 64, c * CH, img, kv_full + st);
               if (has_rn) bulk_load_1d(rn_s + st * CH, p.rnorm + (size_t)img * p.Rpad + c * CH, n * 4, kv_full + st);
               if (c == 0) {
-                mbar_wait(ch_empty, (ic & 1) ^ 1, wc, 12);
-                mbar_expect_tx(ch_full, Cfg::kQBytes);
+                if (p.dbg_flags & 64)                      // A/B timing only: hand the tile over whole
+                  for (int hh = 0; hh < kCH; ++hh) mbar_wait(ch_empty + hh, (ic & 1) ^ 1, wc, 12);
 #pragma unroll
-                for (int kb = 0; kb < D / 64; ++kb)
-                  tma_load_3d(Cs + kb * Cfg::kQBlock, &tm_c, kb * 64, m0, img, ch_full);
+                for (int hh = 0; hh < kCH; ++hh) {
+                  mbar_wait(ch_empty + hh, (ic & 1) ^ 1, wc, 12);
+                  mbar_expect_tx(ch_full + hh, Cfg::kQBytes / kCH);
+#pragma unroll
+                  for (int kb = hh * (D / 64 / kCH); kb < (hh + 1) * (D / 64 / kCH); ++kb)
+                    tma_load_3d(Cs + kb * Cfg::kQBlock, &tm_c, kb * 64, m0, img, ch_full + hh);
+                }
               }
               // the next image's contexts come from HBM and are needed the moment this image ends (the single
               // buffer cannot be refilled earlier): pull them into L2 shortly before
@@ -863,13 +873,28 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const Desc kv_k = make_desc(smem_u32(kv), 16, 1024), kv_mn = make_desc(smem_u32(kv), Cfg::kKvBlock, 1024);
         const Desc x_k = make_desc(smem_u32(Xs), 16, 1024), x_mn = make_desc(smem_u32(Xs), Cfg::kXBytes, 1024);
         const Desc y_mn = make_desc(smem_u32(Ys), Cfg::kXBytes, 1024);
-        auto issue_scores = [&](int st, int n, Desc a_k, uint32_t d_col) {   // [128 x n] = A[128 x D] . Khat_chunk^T
-          const uint32_t idesc = idesc_bf16(TM, n, false, false);
+        auto issue_scores_part = [&](int st, int n, Desc a_k, uint32_t d_col, int part, int parts) {
+          const uint32_t idesc = idesc_bf16(TM, n, false, false);   // [128 x n] = A[128 x D] . Khat_chunk^T, k-steps of one part
           const Desc b_k = kv_k + ((uint32_t)(st * Cfg::kKvStage) >> 4);
+          const int k0 = part * (D / 16 / parts);
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k)
+          for (int kk = 0; kk < D / 16 / parts; ++kk) {
+            const int k = k0 + kk;
             mma_ss(tmem + d_col, a_k + (((k >> 2) * Cfg::kQBlock + (k & 3) * 32) >> 4),
                    b_k + (((k >> 2) * Cfg::kKvBlock + (k & 3) * 32) >> 4), idesc, k > 0);
+          }
+        };
+        auto issue_scores = [&](int st, int n, Desc a_k, uint32_t d_col) { issue_scores_part(st, n, a_k, d_col, 0, 1); };
+        // W of the FIRST chunk of an image: each feature half of the context tile as it lands
+        auto issue_w_arriving = [&](int st, int n, int parity) {
+          if (p.dbg_flags & 64)                            // A/B timing only
+            for (int hh = 0; hh < kCH; ++hh) mbar_wait(ch_full + hh, parity, wc, 15);
+#pragma unroll
+          for (int hh = 0; hh < kCH; ++hh) {
+            mbar_wait(ch_full + hh, parity, wc, 15);
+            tc_fence_after();
+            issue_scores_part(st, n, c_k, Cfg::kColW, hh, kCH);
+          }
         };
         int x = 0, ic = 0, seg = 0;
         SegIter it = seg_iter(NQ, p.Bi);
@@ -880,9 +905,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           mbar_wait(kv_full + (x & 1), (x >> 1) & 1, wc, 14);
           tc_fence_after();
           issue_scores(x & 1, min(CH, p.Rpad), q_k, Cfg::kColS);
-          mbar_wait(ch_full, ic & 1, wc, 15);
-          tc_fence_after();
-          issue_scores(x & 1, min(CH, p.Rpad), c_k, Cfg::kColW);
+          issue_w_arriving(x & 1, min(CH, p.Rpad), ic & 1);
           mma_commit(sw_full);
           int c = 0;
           for (int g = 0; g < G; ++g, ++x) {
@@ -921,12 +944,12 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
                 for (int kt = 0; kt < TM / 16; ++kt)
                   mma_ss(tmem + Cfg::kColDK + h * CH, c_mn + ((2 * h * Cfg::kQBlock + kt * 2048) >> 4), y_mn + ((kt * 2048) >> 4), idesc_dk, kt > 0);
+                if (last_chunk) mma_commit(ch_empty + h);   // this feature half of the context tile is free
               }
             };
             if (last_chunk) {
               // end of the image: release the context buffer first, the refill overlaps dQ and the Q part of dK^T
               issue_dk_c();
-              mma_commit(ch_empty);
               issue_dq();
             } else {
               // inside the image: release the region stage first, the next chunk's load overlaps dK^T
@@ -942,9 +965,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             mma_commit(dk_full);          // X / Y are dead once this fires
             XMC_TRACE(0, x, 2);
             if (has_next && last_chunk) {
-              mbar_wait(ch_full, (ic + 1) & 1, wc, 15);
-              tc_fence_after();
-              issue_scores(st ^ 1, n1, c_k, Cfg::kColW);
+              issue_w_arriving(st ^ 1, n1, (ic + 1) & 1);
               mma_commit(sw_full);
             }
             XMC_TRACE(0, x, 3);
