@@ -87,7 +87,9 @@ int xmc_infonce_stats(const float* scores, int Bq, int Bk, const float* labels, 
 
 /* Row-sharded score matrix (one process per GPU): merge the column statistics of `world` shards,
  * gathered as [world][3][Bk] (rank order irrelevant), into the statistics over all rows:
- * col_stats[0] = log-sum-exp over shards of their log-sum-exps, [1], [2] = sums of the label sums. */
+ * col_stats[0] = log-sum-exp over shards of their log-sum-exps, [1], [2] = sums of the label sums.
+ * Replaces nothing in the reference (single GPU): it is the cross-rank half of the column-direction
+ * log_softmax(dim=0) of train_gan.py:103-105 / 127-129 when the rows of the logits live on different GPUs. */
 int xmc_infonce_combine_stats(const float* gathered, int world, int Bk, float* col_stats, void* stream);
 
 /* Loss from statistics — train_gan.py:104-113 (s0 = column direction, s1 = row direction).
@@ -209,7 +211,8 @@ int xmc_word_scores_backward(const float* rel, const uint8_t* mask, const int* c
 
 /* xmc_infonce_grad followed by xmc_word_scores_backward in one launch (same arithmetic, no dscores
  * round trip): grel[i, row(c,t)] = dLoss/dS_word(i,c) * softmax_t(rho2 rel)[t].  Arguments as in the
- * two calls it replaces; col_stats must already be the statistics over ALL rows. */
+ * two calls it replaces; col_stats must already be the statistics over ALL rows.  Reference: the autograd
+ * of train_gan.py:103-113 composed with the word-score log-sum-exp of the word loss (:220-222, 267-269). */
 int xmc_word_scores_infonce_backward(const float* rel, const uint8_t* mask, const int* cap_ptr,
                                      const float* scores, int Bi, int Bc, int T, int NQs, float rho2,
                                      const float* labels, int diag_offset, float scale,
