@@ -1,5 +1,5 @@
-"""Same-box A/B of the backward kernel's context-tile hand-over (debug flag 64 = whole tile, as before the
-split into feature halves): word_loss fwd+bwd at COCO-256 with the bench masks, kernel times from CUDA
+"""Same-box A/B of the backward kernel's operand hand-over in feature halves (debug flag 64 = context tile
+handed over whole, flag 128 = S waits for the whole region stage): word_loss fwd+bwd at COCO-256 with the bench masks, kernel times from CUDA
 events around the launches, L2 flushed between runs."""
 import sys, torch
 sys.path.insert(0, '.')
@@ -27,5 +27,12 @@ def run(flag, n=20):
     ops.enable_timing(False)
     hook(0)
     return round(k["wordregion_bwd"][1] * 1e3, 1), round(float(loss), 6), round(float(g.float().norm()), 5)
-for rnd in range(3):
-    print({"halves": run(0), "whole": run(64)}, flush=True)
+variants = [("all_on", 0), ("whole_context_tile", 64), ("whole_region_stage", 128)]
+tot = {k: 0.0 for k, _ in variants}
+R = 6
+for rnd in range(R):                      # rotate the order: the box drifts (clocks, temperature) within a run
+    order = variants[rnd % 3:] + variants[:rnd % 3]
+    res = {k: run(f, n=10) for k, f in order}
+    for k in tot: tot[k] += res[k][0]
+    print({k: res[k] for k, _ in variants}, flush=True)
+print("mean us:", {k: round(v / R, 1) for k, v in tot.items()})

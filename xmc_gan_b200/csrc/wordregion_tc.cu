@@ -773,7 +773,10 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   constexpr int kCH = Cfg::kTilesD;
   uint64_t* ch_full = bars + 14;   // [kCH]
   uint64_t* ch_empty = bars + 16;  // [kCH]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  // A region stage lands in two feature halves as well (kv_full: features [0, D/2) and the region norms,
+  // kv_full_b: features [D/2, D)): S starts on the first half while the second is in flight
+  uint64_t* kv_full_b = bars + 18; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   int* abort_flag = reinterpret_cast<int*>(tmem_slot + 1);
   const WaitCtx wc{abort_flag, p.err};
 
@@ -785,7 +788,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (threadIdx.x == 0) {
     *abort_flag = 0;
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(ch_full + s, 1); mbar_init(ch_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(ch_full + s, 1); mbar_init(ch_empty + s, 1); mbar_init(kv_full_b + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
     mbar_init(sw_full, 1); mbar_init(sw_consumed, 256); mbar_init(xy_full, 256);
     mbar_init(dk_full, 1); mbar_init(dk_empty, 128); mbar_init(dq_full, 1); mbar_init(dq_empty, 256);
@@ -834,10 +837,12 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               const int st = x & 1;
               const int n = min(CH, p.Rpad - c * CH);
               mbar_wait(kv_empty + st, ((x >> 1) & 1) ^ 1, wc, 11);
-              mbar_expect_tx(kv_full + st, Cfg::kKvStage + (has_rn ? n * 4 : 0));
+              mbar_expect_tx(kv_full + st, Cfg::kKvStage / 2 + (has_rn ? n * 4 : 0));
+              mbar_expect_tx(kv_full_b + st, Cfg::kKvStage / 2);
 #pragma unroll
               for (int kb = 0; kb < D / 64; ++kb)
-                tma_load_3d(kv + st * Cfg::kKvStage + kb * Cfg::kKvBlock, &tm_k, kb * 64, c * CH, img, kv_full + st);
+                tma_load_3d(kv + st * Cfg::kKvStage + kb * Cfg::kKvBlock, &tm_k, kb * 64, c * CH, img,
+                            (kb < D / 128 ? kv_full : kv_full_b) + st);
               if (has_rn) bulk_load_1d(rn_s + st * CH, p.rnorm + (size_t)img * p.Rpad + c * CH, n * 4, kv_full + st);
               if (c == 0) {
                 if (p.dbg_flags & 64)                      // A/B timing only: hand the tile over whole
@@ -885,6 +890,17 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           }
         };
         auto issue_scores = [&](int st, int n, Desc a_k, uint32_t d_col) { issue_scores_part(st, n, a_k, d_col, 0, 1); };
+        // S of a chunk whose region stage may still be landing: each feature half as it arrives
+        auto issue_s_arriving = [&](int st, int n, int parity) {
+          const bool whole = (p.dbg_flags & 128) != 0;     // A/B timing only: wait for the whole stage first
+          if (whole) mbar_wait(kv_full_b + st, parity, wc, 18);
+          mbar_wait(kv_full + st, parity, wc, 18);
+          tc_fence_after();
+          issue_scores_part(st, n, q_k, Cfg::kColS, 0, 2);
+          mbar_wait(kv_full_b + st, parity, wc, 18);
+          tc_fence_after();
+          issue_scores_part(st, n, q_k, Cfg::kColS, 1, 2);
+        };
         // W of the FIRST chunk of an image: each feature half of the context tile as it lands
         auto issue_w_arriving = [&](int st, int n, int parity) {
           if (p.dbg_flags & 64)                            // A/B timing only
@@ -902,9 +918,7 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         while (it.next(sg)) {
           const int G = sg.nimg * nch;
           mbar_wait(q_full, seg & 1, wc, 13);
-          mbar_wait(kv_full + (x & 1), (x >> 1) & 1, wc, 14);
-          tc_fence_after();
-          issue_scores(x & 1, min(CH, p.Rpad), q_k, Cfg::kColS);
+          issue_s_arriving(x & 1, min(CH, p.Rpad), (x >> 1) & 1);
           issue_w_arriving(x & 1, min(CH, p.Rpad), ic & 1);
           mma_commit(sw_full);
           int c = 0;
@@ -916,10 +930,8 @@ wr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (has_next) {
               // S,W(g) are in the elementwise warps' registers: the next scores may overwrite them now
               mbar_wait(sw_consumed, x & 1, wc, 16);
-              mbar_wait(kv_full + (st ^ 1), ((x + 1) >> 1) & 1, wc, 18);
-              tc_fence_after();
               XMC_TRACE(0, x, 0);
-              issue_scores(st ^ 1, n1, q_k, Cfg::kColS);
+              issue_s_arriving(st ^ 1, n1, ((x + 1) >> 1) & 1);
               if (!last_chunk) {
                 issue_scores(st ^ 1, n1, c_k, Cfg::kColW);
                 mma_commit(sw_full);
