@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import contextlib
 import os
+import threading
 
 import torch
 
@@ -97,6 +98,7 @@ class CudaOps:
         self.events = None     # name -> [(start, stop)] CUDA events when kernel timing is on
         self.last_workspace = None
         self.check_errors = bool(os.environ.get("XMC_CHECK_ERRORS"))   # tests: read the kernels' error word back
+        self._tls = threading.local()   # fork state of side_scope: forward runs on the caller's thread, backward on autograd's
 
     def enable_timing(self, on=True):
         """Record CUDA events (current stream) around the named hot kernels; see kernel_ms()."""
@@ -313,7 +315,7 @@ class CudaOps:
         cur = torch.cuda.current_stream(dev)
         side = self._side_stream(dev)
         side.wait_stream(cur)
-        self._forked = True
+        self._tls.forked = True
         with torch.cuda.stream(side):
             def mark():
                 ev = torch.cuda.Event()
@@ -327,9 +329,9 @@ class CudaOps:
     def join_side(self, dev, *tensors):
         """Current stream waits for everything on the side stream; ``tensors`` (allocated there) are marked
         as used by the current stream for the caching allocator."""
-        if not getattr(self, "_forked", False):
+        if not getattr(self._tls, "forked", False):
             return
-        self._forked = False
+        self._tls.forked = False
         cur = torch.cuda.current_stream(dev)
         cur.wait_stream(self._side_stream(dev))
         for t in tensors:
