@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define XMC_ABI_VERSION 3
+#define XMC_ABI_VERSION 4
 
 typedef enum {
   XMC_OK = 0,
@@ -220,6 +220,22 @@ int xmc_word_scores_infonce_backward(const float* rel, const uint8_t* mask, cons
                                      const float* row_div, const float* col_div, float num_pos,
                                      int rows_total, int cols_total, const float* grad_out,
                                      float* grel, void* stream);
+
+/* ---- matching-aware gradient penalty (MA-GP) reduction: SURVEY §8(f) N4 ---------------------------
+ * Replaces xmc_gan/train_gan.py:244-249:
+ *     grad = torch.cat((grads[0].view(B,-1), grads[1].view(B,-1)), dim=1)
+ *     d_loss = weight * torch.mean(torch.sqrt(torch.sum(grad ** 2, dim=1)) ** power)      (weight 2.0, power 6)
+ * g0 [B, n0] and g1 [B, n1] are the two gradient tensors as they are (contiguous rows; either may be
+ * empty), dtype XMC_F32 or XMC_BF16.  One pass over HBM, no concatenation.  `slices` CTAs share a row
+ * (caller picks it; partial is [B * slices] scratch); sumsq [B] is kept for the backward; loss [1].
+ * Backward (first order): d0/d1 = grad_out * weight/B * power * sumsq^(power/2 - 1) * g0/g1, either may be
+ * NULL.  The double backward through the discriminator stays with autograd. */
+int xmc_gradnorm_penalty_forward(const void* g0, long long n0, const void* g1, long long n1, int B, int dtype,
+                                 float power, float weight, int slices, float* partial, float* sumsq,
+                                 float* loss, void* stream);
+int xmc_gradnorm_penalty_backward(const void* g0, long long n0, const void* g1, long long n1, int B, int dtype,
+                                  float power, float weight, int slices, const float* sumsq,
+                                  const float* grad_out, void* d0, void* d1, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,10 @@ Parity status
   ``tests/golden/make_golden.py`` in the build container; the resulting
   input/output vectors are committed under ``tests/golden/`` and re-checked by
   ``tests/test_oracle.py`` everywhere (the GPU box has no ``/root/reference``).
+* ``magp_penalty``: restatement of the MA-GP reduction ``xmc_gan/train_gan.py:244-249`` (inline
+  statements of ``train()``).  PINNED the same way: ``load_reference.load_reference_magp`` lifts those six
+  assignments out of the reference's ``train`` with ``ast`` and runs them; vectors in
+  ``tests/golden/ref_magp_*.npz``.
 * ``word_scores`` / ``word_loss``: PARITY UNPINNED.  The reference names
   ``word_loss`` (``xmc_gan/train_gan.py:220-222, 267-269``) but only raises
   ``NotImplementedError``; the restatement here follows the XMC-GAN paper's
@@ -21,6 +25,6 @@ Parity status
   ``oracle/word_region.py``).
 """
 from .ref_losses import (  # noqa: F401
-    cosine_scores, make_labels, infonce_tail, sent_loss, img_loss, num_pos_of,
+    cosine_scores, make_labels, infonce_tail, sent_loss, img_loss, num_pos_of, magp_penalty,
 )
 from .word_region import word_scores, word_loss  # noqa: F401

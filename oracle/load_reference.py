@@ -50,3 +50,31 @@ def cuda_is_identity():
         yield
     finally:
         torch.Tensor.cuda = saved
+
+
+_MAGP_TARGETS = ("grad0", "grad1", "grad", "grad_l2norm", "d_loss_gp", "d_loss")
+
+
+def load_reference_magp():
+    """The reference's MA-GP reduction (``train_gan.py:244-249``) as a callable ``grads -> d_loss``.
+
+    The six assignments are statements inside ``train()`` (under ``if cfg.TRAIN.MAGP:``), not a function:
+    they are lifted out of the parsed file by their target names, in source order, and executed with
+    ``grads`` bound — unmodified, nothing copied."""
+    with open(REFERENCE_FILE, "r") as f:
+        tree = ast.parse(f.read(), REFERENCE_FILE)
+    train = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "train")
+    stmts = []
+    for node in ast.walk(train):
+        if isinstance(node, ast.If) and "MAGP" in ast.unparse(node.test):
+            stmts = [st for st in node.body if isinstance(st, ast.Assign) and len(st.targets) == 1
+                     and isinstance(st.targets[0], ast.Name) and st.targets[0].id in _MAGP_TARGETS]
+            break
+    assert [st.targets[0].id for st in stmts] == list(_MAGP_TARGETS), "reference layout changed"
+    code = compile(ast.Module(body=stmts, type_ignores=[]), REFERENCE_FILE, "exec")
+
+    def d_loss(grads):
+        ns = {"torch": torch, "grads": grads}
+        exec(code, ns)
+        return ns["d_loss"]
+    return d_loss

@@ -83,3 +83,13 @@ def img_loss(real_imgs, fake_imgs, labels, b_global, smooth_global: float = 0.5)
     """Real–fake image InfoNCE, rows = real, cols = fake (train_gan.py:117-139)."""
     return infonce_tail(cosine_scores(real_imgs, fake_imgs), labels,
                         num_pos_of(labels, b_global, smooth_global))
+
+
+def magp_penalty(grad_img: torch.Tensor, grad_sent: torch.Tensor, power: float = 6.0, weight: float = 2.0) -> torch.Tensor:
+    """MA-GP reduction, ``xmc_gan/train_gan.py:244-249`` (grad0/grad1 views :244-245, cat :246,
+    L2 norm :247, mean of the 6th power :248, factor 2 :249)."""
+    grad0 = grad_img.reshape(grad_img.size(0), -1)
+    grad1 = grad_sent.reshape(grad_sent.size(0), -1)
+    grad = torch.cat((grad0, grad1), dim=1)
+    grad_l2norm = torch.sqrt(torch.sum(grad ** 2, dim=1))
+    return weight * torch.mean(grad_l2norm ** power)

@@ -95,6 +95,22 @@ def word_case(name, B, D, T, R, seed, rho=(5.0, 5.0, 10.0), normalize_values=Fal
     print(f"word_{name}: loss={float(loss.detach()):.12f}")
 
 
+def magp_case(name, B, shape_img, D, seed, scale):
+    """The reference's own six statements (train_gan.py:244-249) on synthetic gradients."""
+    g = torch.Generator().manual_seed(seed)
+    ref = LR.load_reference_magp()
+    gi = torch.randn(B, *shape_img, generator=g) * scale
+    gs = torch.randn(B, D, generator=g) * scale
+    out = {}
+    for dt, tag in ((torch.float32, "32"), (torch.float64, "64")):
+        a = gi.to(dt).clone().requires_grad_(); b = gs.to(dt).clone().requires_grad_()
+        loss = ref((a, b))
+        loss.backward()
+        out["loss" + tag] = loss.detach().numpy(); out["d0_" + tag] = a.grad.numpy(); out["d1_" + tag] = b.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, f"ref_magp_{name}.npz"), g0=gi.numpy(), g1=gs.numpy(), **out)
+    print(f"ref_magp_{name}: loss={float(out['loss64']):.12f}")
+
+
 if __name__ == "__main__":
     assert LR.reference_available(), "needs /root/reference"
     torch.set_num_threads(1)
@@ -104,6 +120,8 @@ if __name__ == "__main__":
     sim_case("sent_b88_d256_id", "sent", 88, 256, False, 0.0, 4, need=(True, False))
     sim_case("img_b16_d512_id", "img", 16, 512, False, 0.5, 5, need=(False, True))
     sim_case("img_b40_d512_soft05", "img", 40, 512, True, 0.5, 6, need=(False, True))
+    magp_case("b6_3x8x8_d16", 6, (3, 8, 8), 16, 21, 0.08)
+    magp_case("b5_3x7x9_d10", 5, (3, 7, 9), 10, 22, 0.11)        # row lengths not multiples of 4
     word_case("b6_d64_t7_r20", 6, 64, 7, 20, 11)
     word_case("b4_d256_t18_r289", 4, 256, 18, 289, 12, lean=0.15)
     word_case("b6_d128_t12_r64_nv", 6, 128, 12, 64, 13, normalize_values=True)

@@ -19,7 +19,7 @@ def _t(x, dtype=None):
 
 
 def _ref_cases(golden_dir):
-    return sorted(glob.glob(os.path.join(golden_dir, "ref_*.npz")))
+    return sorted(p for p in glob.glob(os.path.join(golden_dir, "ref_*.npz")) if "ref_magp_" not in p)
 
 
 def test_golden_files_present(golden_dir):
@@ -156,3 +156,39 @@ def test_word_oracle_properties():
     assert (S2[:, 2] == 0).all()
     S2.sum().backward()
     assert torch.isfinite(wq.grad).all() and (wq.grad[2] == 0).all()
+
+
+# ---- MA-GP reduction (train_gan.py:244-249) ---------------------------------------------------------
+def _magp_cases(golden_dir):
+    return sorted(glob.glob(os.path.join(golden_dir, "ref_magp_*.npz")))
+
+
+@pytest.mark.parametrize("dtype,tag,tol", [(torch.float32, "32", 2e-6), (torch.float64, "64", 1e-12)])
+def test_magp_oracle_matches_reference_golden(golden_dir, dtype, tag, tol):
+    cases = _magp_cases(golden_dir)
+    assert len(cases) >= 2
+    for path in cases:
+        z = np.load(path)
+        a = torch.from_numpy(z["g0"]).to(dtype).requires_grad_()
+        b = torch.from_numpy(z["g1"]).to(dtype).requires_grad_()
+        loss = oracle.magp_penalty(a, b)
+        loss.backward()
+        assert abs(float(loss) - float(z["loss" + tag])) <= tol * abs(float(z["loss" + tag])), path
+        for got, ref in ((a.grad, z["d0_" + tag]), (b.grad, z["d1_" + tag])):
+            ref = torch.from_numpy(ref)
+            assert float((got - ref).norm() / ref.norm()) <= 10 * tol, path
+
+
+@pytest.mark.skipif(not LR.reference_available(), reason="/root/reference only exists in the build container")
+def test_magp_oracle_matches_reference_live():
+    ref = LR.load_reference_magp()
+    g = torch.Generator().manual_seed(3)
+    a = (torch.randn(7, 3, 5, 6, generator=g, dtype=torch.float64) * 0.1).requires_grad_()
+    b = (torch.randn(7, 12, generator=g, dtype=torch.float64) * 0.1).requires_grad_()
+    l_ref = ref((a, b))
+    g_ref = torch.autograd.grad(l_ref, (a, b))
+    l_or = oracle.magp_penalty(a, b)
+    g_or = torch.autograd.grad(l_or, (a, b))
+    assert abs(float(l_ref) - float(l_or)) <= 1e-13 * abs(float(l_ref))
+    for x, y in zip(g_ref, g_or):
+        assert torch.allclose(x, y, rtol=1e-12, atol=0)

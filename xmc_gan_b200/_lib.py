@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 XMC_F32, XMC_BF16 = 0, 1
 PATH_FP32_SIMT, PATH_BF16_TCGEN05 = 0, 1
 
-_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_vp, _i, _f, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 
 # name -> (restype, argtypes); must list every symbol the header declares (tests check this)
 SIGNATURES = {
@@ -51,6 +51,8 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "xmc_word_scores": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "xmc_word_scores_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "xmc_gradnorm_penalty_forward": (_i, [_vp, _ll, _vp, _ll, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp]),
+    "xmc_gradnorm_penalty_backward": (_i, [_vp, _ll, _vp, _ll, _i, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "xmc_infonce_combine_stats": (_i, [_vp, _i, _i, _vp, _vp]),
     "xmc_word_scores_infonce_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _i, _f, _vp, _vp, _vp, _vp, _f,
                                               _i, _i, _vp, _vp, _vp]),

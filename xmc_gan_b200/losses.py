@@ -332,3 +332,37 @@ class WordLossFn(torch.autograd.Function):
             _join_side(ops, dev, dw_all)
             dwords = comm.reduce_scatter_sum(dw_all).to(w_dtype)
         return (dreg, dwords) + (None,) * 10
+
+
+# ------------------------------------------------------------------------------------------------
+# MA-GP reduction (train_gan.py:244-249)
+# ------------------------------------------------------------------------------------------------
+class GradNormPenaltyFn(torch.autograd.Function):
+    """loss = weight * mean_b ||cat(g0[b], g1[b])||_2 ** power, first-order differentiable in g0, g1.
+
+    The gradients fed in carry the graph of ``autograd.grad(..., create_graph=True)``; what this
+    function returns from ``backward`` flows on into that graph (the double backward through the
+    discriminator is autograd's, as in the reference)."""
+
+    @staticmethod
+    def forward(ctx, g0, g1, power, weight, ops):
+        a = g0.detach().reshape(g0.shape[0], -1).contiguous()
+        b = g1.detach().reshape(g1.shape[0], -1).contiguous()
+        if a.shape[0] != b.shape[0]:
+            raise ValueError(f"batch sizes differ: {a.shape[0]} vs {b.shape[0]}")
+        if a.dtype != b.dtype:
+            raise TypeError(f"gradient dtypes differ: {a.dtype} vs {b.dtype}")
+        loss, sumsq = ops.gradnorm_penalty_forward(a, b, power, weight)
+        ctx.save_for_backward(a, b, sumsq)
+        ctx.meta = (float(power), float(weight), tuple(g0.shape), tuple(g1.shape))
+        ctx.ops = ops
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, b, sumsq = ctx.saved_tensors
+        power, weight, s0, s1 = ctx.meta
+        go = grad_out.detach().to(torch.float32).contiguous()
+        d0, d1 = ctx.ops.gradnorm_penalty_backward(a, b, power, weight, sumsq, go, ctx.needs_input_grad[0],
+                                                   ctx.needs_input_grad[1])
+        return (d0.view(s0) if d0 is not None else None, d1.view(s1) if d1 is not None else None, None, None, None)

@@ -215,6 +215,39 @@ class CudaOps:
         self.launches += 2
         return labels, row_count
 
+    # -- MA-GP reduction ----------------------------------------------------------------------
+    @staticmethod
+    def _gp_slices(B, n0):
+        """CTAs per row: enough CTAs for every SM (148) a few times over, at least 16 K elements each."""
+        return int(max(1, min(64, (4 * 148 + B - 1) // B, max(1, n0 // 16384))))
+
+    def gradnorm_penalty_forward(self, g0, g1, power, weight):
+        """g0 [B, n0], g1 [B, n1] (contiguous, same dtype) -> (loss [] fp32, sumsq [B] fp32)."""
+        _cuda(g0, g1)
+        B, n0, n1 = g0.shape[0], g0.shape[1], g1.shape[1]
+        S = self._gp_slices(B, n0)
+        partial = torch.empty(B * S, device=g0.device, dtype=torch.float32)
+        sumsq = torch.empty(B, device=g0.device, dtype=torch.float32)
+        loss = torch.empty((), device=g0.device, dtype=torch.float32)
+        with _on(g0), self._timed("gradpen_fwd"):
+            _lib.check(self.L.xmc_gradnorm_penalty_forward(_p(g0), n0, _p(g1), n1, B, _dt(g0), float(power),
+                                                           float(weight), S, _p(partial), _p(sumsq), _p(loss), _stream()))
+        self.launches += 2
+        return loss, sumsq
+
+    def gradnorm_penalty_backward(self, g0, g1, power, weight, sumsq, grad_out, need0, need1):
+        _cuda(g0, g1, grad_out)
+        B, n0, n1 = g0.shape[0], g0.shape[1], g1.shape[1]
+        S = self._gp_slices(B, n0)
+        d0 = torch.empty_like(g0) if need0 else None
+        d1 = torch.empty_like(g1) if need1 else None
+        with _on(g0), self._timed("gradpen_bwd"):
+            _lib.check(self.L.xmc_gradnorm_penalty_backward(_p(g0), n0, _p(g1), n1, B, _dt(g0), float(power),
+                                                            float(weight), S, _p(sumsq), _p(grad_out), _p(d0), _p(d1),
+                                                            _stream()))
+        self.launches += 1
+        return d0, d1
+
     # -- word-region --------------------------------------------------------------------------
     supports_compaction = True     # the tcgen05 kernels visit only the non-padding word rows
     use_side_stream = True         # word-side prologue / zero fills / word epilogue beside the main stream

@@ -21,7 +21,7 @@ from . import losses as _L
 from .config import cfg  # noqa: F401  (re-exported: callers set cfg.TRAIN.SMOOTH.GLOBAL here)
 from .ops import default_ops
 
-__all__ = ["cfg", "make_labels", "cosine_scores", "sent_loss", "img_loss", "word_loss"]
+__all__ = ["cfg", "make_labels", "cosine_scores", "sent_loss", "img_loss", "word_loss", "magp_penalty"]
 
 
 def make_labels(batch_size, sent_embs, b_global, p=0.6, *, group=None, device=None, _ops=None):
@@ -85,3 +85,17 @@ def word_loss(imgs, words, mask, labels, b_global, *, rho1=5.0, rho2=5.0, rho3=1
     """
     return _L.WordLossFn.apply(imgs, words, mask, labels, bool(b_global), float(rho1), float(rho2), float(rho3),
                                bool(normalize_values), precision, group, _ops or default_ops())
+
+
+def magp_penalty(grads, *, power=6.0, weight=2.0, _ops=None):
+    """Matching-aware gradient penalty reduction, ``xmc_gan/train_gan.py:244-249``.
+
+    ``grads``: the pair returned by ``torch.autograd.grad(out[0], (interpolated, sent_inter),
+    create_graph=True, ...)`` (``:237-242``) — image gradients ``[B, 3, H, W]`` and sentence
+    gradients ``[B, D]``.  Returns ``weight * mean_b(||cat(g_img[b], g_sent[b])||_2 ** power)``
+    (the reference's ``d_loss``: weight 2.0, power 6) as a 0-dim tensor; ``.backward()`` continues
+    into the double-backward graph of the discriminator exactly as the reference's expression does.
+    One pass over the gradients: no ``cat``, no ``grad ** 2`` temporary.
+    """
+    g0, g1 = grads
+    return _L.GradNormPenaltyFn.apply(g0, g1, float(power), float(weight), _ops or default_ops())
