@@ -45,3 +45,27 @@ for _ in range(5):
     gi.grad = None; gs.grad = None; flush.zero_()
     T.magp_penalty((gi, gs)).backward()
 print("kernel events:", {k: round(v[1] * 1e3, 1) for k, v in ops.kernel_ms().items()}, "us (two launches in fwd)")
+# The zero-fill flush leaves ~126 MB of dirty lines in L2 whose write-back shares HBM with the timed kernel;
+# flushing by READING a 512 MB buffer leaves clean lines: the kernel's own traffic only.
+big = torch.empty(512 << 20, dtype=torch.uint8, device="cuda").zero_()
+ops.enable_timing(True)
+for _ in range(8):
+    gi.grad = None; gs.grad = None
+    big.view(torch.int64).sum()
+    loss = T.magp_penalty((gi, gs))
+    big.view(torch.int64).sum()
+    loss.backward()
+k = ops.kernel_ms()
+f, b = k["gradpen_fwd"][1] * 1e3, k["gradpen_bwd"][1] * 1e3
+print(f"clean-L2 flush: fwd {f:6.1f} us = {nbytes / f / 1e3:6.0f} GB/s ({nbytes / f / 1e3 / peak:.2f})   bwd {b:6.1f} us = {2 * nbytes / b / 1e3:6.0f} GB/s ({2 * nbytes / b / 1e3 / peak:.2f})")
+ops.enable_timing(False)
+# slices-per-row sweep (kernel events, forward = sumsq + loss launches)
+from xmc_gan_b200.ops import CudaOps
+for S in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32):
+    CudaOps._gp_slices = staticmethod(lambda B, n0, S=S: S)
+    ops.enable_timing(True)
+    for _ in range(6):
+        gi.grad = None; gs.grad = None; flush.zero_()
+        T.magp_penalty((gi, gs)).backward()
+    k = ops.kernel_ms()
+    print(f"slices {S:2d}: fwd {k['gradpen_fwd'][1] * 1e3:6.1f} us  bwd {k['gradpen_bwd'][1] * 1e3:6.1f} us")
