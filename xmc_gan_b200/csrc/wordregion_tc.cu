@@ -716,7 +716,9 @@ struct TcBwdParams {
   float* dqn; float* dkn; float* drnorm;
   const int* nq_dev;           // device count of valid word rows (<= NQ) or null
   int* err;
-  int dbg_flags;               // + 16 (tests): fill TMEM with NaNs first               // perf experiments only (xmc_internal_set_debug_dump): 2 = skip the dK reduce
+  int dbg_flags;               // xmc_internal_set_debug_dump bits (tests / perf experiments only): 2 = skip the dK reduce,
+                               // 4 = clock64 trace, 8 = per-CTA timing log, 16 = fill TMEM with NaNs first (tests),
+                               // 64 = hand the context tile over whole, 128 = S waits for the whole region stage
   long long* trace;            // perf experiments only: flag 4 = clock64 timeline of CTA 0, [4 roles][64 chunks][4];
                                // flag 8 = per-CTA {start ns, end ns, segments, images} after it
 };
