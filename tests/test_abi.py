@@ -42,6 +42,15 @@ def test_argument_validation_without_gpu(built):
     assert rc == 2 and b"unsupported" in L.xmc_last_error()
     rc = L.xmc_cosine_scores(8, 16, 4, 4, 8, 0, 16, None, None, None)
     assert rc == 3
+    # MA-GP reduction: empty problem, missing outputs, power below 2
+    assert L.xmc_gradnorm_penalty_forward(None, 0, None, 0, 4, 0, 6.0, 2.0, 1, 16, 16, 16, None) == 1
+    assert L.xmc_gradnorm_penalty_forward(16, 8, None, 0, 4, 0, 6.0, 2.0, 1, None, 16, 16, None) == 1
+    assert L.xmc_gradnorm_penalty_forward(16, 8, None, 0, 4, 0, 1.0, 2.0, 1, 16, 16, 16, None) == 1
+    assert b"power" in L.xmc_last_error()
+    assert L.xmc_gradnorm_penalty_backward(16, 8, 16, 8, 4, 0, 6.0, 2.0, 1, None, 16, 16, 16, None) == 1
+    # merge of per-rank column statistics
+    assert L.xmc_infonce_combine_stats(None, 2, 8, 16, None) == 1
+    assert L.xmc_infonce_combine_stats(16, 0, 8, 16, None) == 1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
