@@ -29,9 +29,9 @@ def run(flag, n=20):
     return round(k["wordregion_bwd"][1] * 1e3, 1), round(float(loss), 6), round(float(g.float().norm()), 5)
 variants = [("all_on", 0), ("whole_context_tile", 64), ("whole_region_stage", 128)]
 tot = {k: 0.0 for k, _ in variants}
-R = 6
+R = 8
 for rnd in range(R):                      # rotate the order: the box drifts (clocks, temperature) within a run
-    order = variants[rnd % 3:] + variants[:rnd % 3]
+    order = variants[rnd % len(variants):] + variants[:rnd % len(variants)]
     res = {k: run(f, n=10) for k, f in order}
     for k in tot: tot[k] += res[k][0]
     print({k: res[k] for k, _ in variants}, flush=True)
