@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define XMC_ABI_VERSION 4
+#define XMC_ABI_VERSION 5
 
 typedef enum {
   XMC_OK = 0,
@@ -72,6 +72,13 @@ int xmc_check_device(void);
 int xmc_cosine_scores(const void* a, const void* b, int Bq, int Bk, int D, int dtype,
                       float* scores, float* inv_norm_a, float* inv_norm_b, void* stream);
 
+/* Backward of cosine_scores as autograd differentiates train_gan.py:88-90: given dscores[Bq,Bk],
+ * da = normalize-backward(dscores @ bhat), db = normalize-backward(dscores^T @ ahat); da / db may be NULL.
+ * inv_norm_*: what xmc_cosine_scores returned.  Outputs have dtype `dtype`. */
+int xmc_cosine_scores_backward(const void* a, const void* b, int Bq, int Bk, int D, int dtype,
+                               const float* inv_norm_a, const float* inv_norm_b, const float* dscores,
+                               void* da, void* db, void* stream);
+
 /* Fused forward of sent_loss / img_loss up to the statistics — train_gan.py:93-111 / 117-135:
  * L2-normalise, cosine matrix, scale (=1/tau; the reference has no temperature: 1.0),
  * log-sum-exp over rows and over columns and the label-weighted sums, ONE kernel.
@@ -92,17 +99,30 @@ int xmc_infonce_stats(const float* scores, int Bq, int Bk, const float* labels, 
  * log_softmax(dim=0) of train_gan.py:103-105 / 127-129 when the rows of the logits live on different GPUs. */
 int xmc_infonce_combine_stats(const float* gathered, int world, int Bk, float* col_stats, void* stream);
 
+/* Row-sharded score matrix, one exchange per loss.  Each rank contributes a PACKET of `stride` floats:
+ *   [0, 3*Bk)  column statistics over its rows (what xmc_simloss_forward / xmc_infonce_stats wrote),
+ *   [3*Bk]     its row-direction partial loss (xmc_infonce_loss with col_count = 0, element [0]).
+ * gathered = the packets of all ranks, [world][stride].  Writes the merged column statistics col_stats[3][Bk]
+ * (kept for the backward) and loss_out[0] = the GLOBAL loss s0 + s1 of train_gan.py:113 ([1] = s0 over all
+ * columns, [2] = s1 = sum of the ranks' partials): identical on every rank, so no all-reduce follows.  A NaN
+ * partial (error_word of xmc_infonce_loss) makes the global loss NaN on every rank. */
+int xmc_infonce_combine_loss(const float* gathered, int world, int stride, int Bk, const float* col_div,
+                             float num_pos, int cols_total, float* col_stats, float* loss_out, void* stream);
+
 /* Loss from statistics — train_gan.py:104-113 (s0 = column direction, s1 = row direction).
  * row_div[Bq] / col_div[Bk]: per-row / per-column divisor ("num_pos" when it is the
  * (labels>0).sum(1) vector, :99); NULL means the scalar num_pos (1 or 2, :94-97).
  * rows_total / cols_total are the GLOBAL matrix sizes the two means divide by (== Bq, Bk on one
  * GPU).  loss_out[0] = s0_part + s1_part, [1] = s0_part, [2] = s1_part, where s1_part sums the Bq
  * local rows and s0_part the columns [col_begin, col_begin+col_count) — all Bk columns on one
- * GPU, the rank's own columns when the matrix is sharded by rows (so that parts add up). */
+ * GPU, the rank's own columns when the matrix is sharded by rows (so that parts add up).
+ * error_word (nullable): DEVICE int, word 0 of the workspace of the xmc_wordregion_forward call that
+ * produced the scores.  If it is non-zero (a bounded pipeline wait of that kernel timed out) all three
+ * outputs are NaN — checked on the device, no host synchronisation. */
 int xmc_infonce_loss(const float* row_stats, const float* col_stats, int Bq, int Bk,
                      const float* row_div, const float* col_div, float num_pos,
                      int rows_total, int cols_total, int col_begin, int col_count,
-                     float* loss_out, void* stream);
+                     float* loss_out, const int* error_word, void* stream);
 
 /* d loss / d scores (closed form of the autograd of train_gan.py:103-113), times *grad_out
  * (device scalar) times scale.  col_stats must already be the statistics over ALL rows. */
@@ -162,11 +182,13 @@ int xmc_normalize_transpose(const void* x, int B, int D, int L, int Lpad, int in
 
 /* Backward of the above.  dxn[B,Lpad,D] fp32 is the gradient w.r.t. the unit rows; dnorm[B,Lpad]
  * (nullable) the gradient w.r.t. the norm.  dx[B,D,L] has dtype out_dtype.  With row_of the
- * rows of xn / dxn are the compact ones and dropped words get a zero gradient. */
+ * rows of xn / dxn are the compact ones and dropped words get a zero gradient.
+ * error_word (nullable): DEVICE int, word 0 of the workspace of the xmc_wordregion_backward call that
+ * accumulated dxn; non-zero (that kernel timed out) turns every element of dx into NaN. */
 int xmc_normalize_transpose_backward(const void* xn, const float* norm, const float* dxn,
                                      const float* dnorm, int B, int D, int L, int Lpad,
-                                     int xn_dtype, int out_dtype, const int* row_of, void* dx,
-                                     void* stream);
+                                     int xn_dtype, int out_dtype, const int* row_of,
+                                     const int* error_word, void* dx, void* stream);
 
 size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad, int D);
 

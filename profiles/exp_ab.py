@@ -5,8 +5,8 @@ import sys, torch
 sys.path.insert(0, '.')
 import bench
 from xmc_gan_b200 import _lib, train_gan as T
-from xmc_gan_b200.ops import CudaOps, default_ops
-ops = default_ops()
+from xmc_gan_b200.ops import CudaOps
+ops = CudaOps(lib=_lib.hooks_lib())   # -DXMC_TEST_HOOKS build: the A/B switches do not exist in the product library
 inp = {k: v.cuda() for k, v in bench.make_inputs(256, 1000, torch.bfloat16).items()}
 labels = T.make_labels(256, inp["sent"], False)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -33,7 +33,7 @@ def capture():
 fused = CudaOps.word_scores_infonce_backward
 def variant(name):
     ops.use_side_stream = name != "no_side_stream"
-    _lib.lib().xmc_internal_set_prep_generic(int(name == "generic_prep"))
+    _lib.hooks_lib().xmc_internal_set_prep_generic(int(name == "generic_prep"))
     if name == "two_call_tail":
         del CudaOps.word_scores_infonce_backward
     try:
@@ -41,7 +41,7 @@ def variant(name):
     finally:
         CudaOps.word_scores_infonce_backward = fused
         ops.use_side_stream = True
-        _lib.lib().xmc_internal_set_prep_generic(0)
+        _lib.hooks_lib().xmc_internal_set_prep_generic(0)
 
 names = ["all_on", "no_side_stream", "two_call_tail", "generic_prep"]
 graphs = {n: variant(n) for n in names}

@@ -1,10 +1,9 @@
 import ctypes, sys, torch
 sys.path.insert(0, '.')
 from xmc_gan_b200 import _lib
-from xmc_gan_b200.ops import default_ops
-ops = default_ops()
-hook = _lib.lib().xmc_internal_set_debug_dump
-hook.argtypes, hook.restype = [ctypes.c_int], None
+from xmc_gan_b200.ops import CudaOps
+ops = CudaOps(lib=_lib.hooks_lib())   # -DXMC_TEST_HOOKS build: the debug flags do not exist in the product library
+hook = _lib.hooks_lib().xmc_internal_set_debug_dump
 B, D, T, R = 256, 256, 18, 289
 g = torch.Generator().manual_seed(0)
 words = torch.randn(B, D, T, generator=g).cuda(); regions = torch.randn(B, D, R, generator=g).cuda()

@@ -5,12 +5,12 @@ import sys, torch
 sys.path.insert(0, '.')
 import bench
 from xmc_gan_b200 import _lib, train_gan as T
-from xmc_gan_b200.ops import default_ops
-ops = default_ops()
+from xmc_gan_b200.ops import CudaOps
+ops = CudaOps(lib=_lib.hooks_lib())   # -DXMC_TEST_HOOKS build: the debug flags do not exist in the product library
 inp = {k: v.cuda() for k, v in bench.make_inputs(256, 1000, torch.bfloat16).items()}
 labels = T.make_labels(256, inp["sent"], False)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-hook = _lib.lib().xmc_internal_set_debug_dump
+hook = _lib.hooks_lib().xmc_internal_set_debug_dump
 def run(flag, n=20):
     hook(flag)
     def step():

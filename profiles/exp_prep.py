@@ -3,8 +3,8 @@ generic kernels vs the bf16 fast kernels, L2 flushed before every timed launch."
 import sys, torch
 sys.path.insert(0, '.')
 from xmc_gan_b200 import _lib
-from xmc_gan_b200.ops import default_ops
-ops = default_ops()
+from xmc_gan_b200.ops import CudaOps
+ops = CudaOps(lib=_lib.hooks_lib())   # -DXMC_TEST_HOOKS build: the debug flags do not exist in the product library
 B, D, R, Rpad, T = 256, 256, 289, 304, 18
 reg = torch.randn(B, D, R, device="cuda").bfloat16()
 words = torch.randn(B, D, T, device="cuda").bfloat16()
@@ -26,7 +26,7 @@ def timed(fn, n=20):
     return tot / n * 1e3
 
 for generic in (1, 0, 1, 0):
-    _lib.lib().xmc_internal_set_prep_generic(generic)
+    _lib.hooks_lib().xmc_internal_set_prep_generic(generic)
     kn, rnorm = ops.normalize_transpose(reg, Rpad, torch.bfloat16)
     qn, qnorm = ops.normalize_transpose(words, T, torch.bfloat16, row_of=row_of)
     t = dict(
@@ -36,4 +36,4 @@ for generic in (1, 0, 1, 0):
         bwd_words=timed(lambda: ops.normalize_transpose_backward(qn, qnorm, dqn, None, T, torch.float32, row_of=row_of)),
     )
     print("generic" if generic else "fast   ", {k: round(v, 1) for k, v in t.items()}, "us", flush=True)
-_lib.lib().xmc_internal_set_prep_generic(0)
+_lib.hooks_lib().xmc_internal_set_prep_generic(0)

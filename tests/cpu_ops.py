@@ -44,17 +44,28 @@ class CpuOps:
         self.compactions = 0
 
     # -- similarity losses --
-    def cosine_scores(self, a, b):
-        an = a / a.norm(dim=1, keepdim=True).clamp_min(EPS)
-        bn = b / b.norm(dim=1, keepdim=True).clamp_min(EPS)
-        return an @ bn.t()
+    def cosine_scores(self, a, b, with_norms=False):
+        inv_a = 1 / a.norm(dim=1).clamp_min(EPS)
+        inv_b = 1 / b.norm(dim=1).clamp_min(EPS)
+        s = (a * inv_a[:, None]) @ (b * inv_b[:, None]).t()
+        return (s, inv_a, inv_b) if with_norms else s
 
-    def simloss_forward(self, a, b, labels, diag, scale):
+    def cosine_scores_backward(self, a, b, inv_a, inv_b, dscores, need_a, need_b):
+        ah, bh = a * inv_a[:, None], b * inv_b[:, None]
+        dS = dscores.to(a.dtype)
+
+        def nb(g, xh, inv):
+            return (g - xh * (g * xh).sum(1, keepdim=True)) * inv[:, None]
+        return (nb(dS @ bh, ah, inv_a) if need_a else None), (nb(dS.t() @ ah, bh, inv_b) if need_b else None)
+
+    def simloss_forward(self, a, b, labels, diag, scale, col_stats=None):
         inv_a = 1 / a.norm(dim=1).clamp_min(EPS)
         inv_b = 1 / b.norm(dim=1).clamp_min(EPS)
         scores = (a * inv_a[:, None]) @ (b * inv_b[:, None]).t()
         L = _labels(labels, a.shape[0], b.shape[0], diag, scores.dtype)
         row, col = _stats(scale * scores, L)
+        if col_stats is not None:            # the exchange packet is fp32, as on the GPU
+            col_stats.copy_(col)
         return scores, inv_a, inv_b, row, col
 
     def simloss_backward(self, a, b, scores, inv_a, inv_b, labels, diag, scale, row_stats, col_stats,
@@ -70,17 +81,35 @@ class CpuOps:
         return da, db
 
     # -- tail --
-    def infonce_stats(self, scores, labels, diag, scale):
+    def infonce_stats(self, scores, labels, diag, scale, col_stats=None):
         L = _labels(labels, scores.shape[0], scores.shape[1], diag, scores.dtype)
-        return _stats(scale * scores, L)
+        row, col = _stats(scale * scores, L)
+        if col_stats is not None:
+            col_stats.copy_(col)
+        return row, col
 
-    def infonce_loss(self, row_stats, col_stats, row_div, col_div, num_pos, rows_total, cols_total, col_begin, col_count):
+    def infonce_loss(self, row_stats, col_stats, row_div, col_div, num_pos, rows_total, cols_total, col_begin, col_count,
+                     error_word=None, out=None):
         nr = row_div if row_div is not None else float(num_pos)
         s1 = ((row_stats[0] * row_stats[1] - row_stats[2]) / nr).sum() / rows_total
         sl = slice(col_begin, col_begin + col_count)
         nc = col_div[sl] if col_div is not None else float(num_pos)
         s0 = ((col_stats[0][sl] * col_stats[1][sl] - col_stats[2][sl]) / nc).sum() / cols_total
-        return torch.stack([s0 + s1, s0, s1])
+        res = torch.stack([s0 + s1, s0, s1])
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def combine_loss(self, gathered, offset, Bk, col_div, num_pos, cols_total):
+        """xmc_infonce_combine_loss: merge the ranks' packets, evaluate the global loss."""
+        g = gathered[:, offset:offset + 3 * Bk + 1].double()
+        cs = g[:, :3 * Bk].reshape(-1, 3, Bk)
+        col = torch.stack([torch.logsumexp(cs[:, 0], 0), cs[:, 1].sum(0), cs[:, 2].sum(0)])
+        nc = col_div.double() if col_div is not None else float(num_pos)
+        s0 = ((col[0] * col[1] - col[2]) / nc).sum() / cols_total
+        s1 = g[:, 3 * Bk].sum()
+        return col, torch.stack([s0 + s1, s0, s1])
 
     def infonce_grad(self, scores, labels, diag, scale, row_stats, col_stats, row_div, col_div, num_pos,
                      rows_total, cols_total, grad_out):
@@ -126,7 +155,7 @@ class CpuOps:
         n[:, :L] = norm
         return xn, n
 
-    def normalize_transpose_backward(self, xn, norm, dxn, dnorm, L, out_dtype, row_of=None):
+    def normalize_transpose_backward(self, xn, norm, dxn, dnorm, L, out_dtype, row_of=None, error_word=None):
         if row_of is not None:                                   # dropped (padding) words get a zero gradient
             B, Lp, D = xn.shape
             assert Lp == L and dnorm is None

@@ -40,7 +40,7 @@ def _data(seed, Bg, D, Dw, T_, R):
     return d
 
 
-def _worker(rank, port, b_global, smooth, precision, Dw, out):
+def _worker(rank, port, b_global, smooth, precision, Dw, out, fused=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -58,6 +58,15 @@ def _worker(rank, port, b_global, smooth, precision, Dw, out):
         img, sent, words, regions = leaf(d["img"]), leaf(d["sent"]), leaf(d["words"]), leaf(d["regions"])
         group = dist.group.WORLD
         labels = T.make_labels(B, d["sent"][sl].float(), b_global, group=group, _ops=ops)
+        if fused:      # the three losses through ONE autograd function: grouped gather / exchange / reduce-scatter
+            real, fake = leaf(d["img"]).detach(), leaf(d["sent"])
+            l3 = T.contrastive_losses(img, sent, real, fake, regions, words, d["mask"][sl], labels, b_global,
+                                      rho1=4.0, rho2=5.0, rho3=6.0, precision=precision, group=group, _ops=ops)
+            loss = l3[0] + 0.5 * l3[1] + l3[2]
+            loss.backward()
+            out[rank] = dict(loss=loss.detach(), labels=labels.detach().clone(), parts=[x.detach() for x in l3],
+                             grads=[t.grad.clone() for t in (img, sent, words, regions, fake)])
+            return
         loss = (T.sent_loss(img, sent, labels, b_global, group=group, _ops=ops)
                 + T.img_loss(sent.detach(), img, labels, b_global, tau=0.5, group=group, _ops=ops)
                 + T.word_loss(regions, words, d["mask"][sl], labels, b_global, rho1=4.0, rho2=5.0, rho3=6.0,
@@ -101,3 +110,60 @@ def test_two_rank_global_negatives_match_single_process_oracle(b_global, smooth,
         for got, ref in zip(r["grads"], (img.grad, sent.grad, words.grad, regions.grad)):
             err = float((got - ref[sl]).norm() / ref[sl].norm())
             assert err < 1e-6, (rank, err)
+
+
+@pytest.mark.parametrize("b_global,smooth,precision,Dw", [(False, 0.5, None, 8), (True, 0.5, "bf16", 128), (True, 0.0, None, 8)])
+def test_two_rank_fused_losses_match_single_process_oracle(b_global, smooth, precision, Dw):
+    """contrastive_losses (one grouped all-gather, one packet exchange, one grouped reduce-scatter per step)
+    against the single-process oracle on the concatenated batch, every loss and every gradient."""
+    import oracle
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(_free_port(), b_global, smooth, precision, Dw, out, True), nprocs=WORLD, join=True)
+
+    B, D, T_, R = 6, 16, 5, 7
+    Bg = B * WORLD
+    d = _data(0, Bg, D, Dw, T_, R)
+    leaf = lambda x: x.clone().requires_grad_()
+    img, sent, words, regions, fake = leaf(d["img"]), leaf(d["sent"]), leaf(d["words"]), leaf(d["regions"]), leaf(d["sent"])
+    labels = oracle.make_labels(Bg, d["sent"].float(), b_global, smooth_global=smooth)
+    parts = [oracle.sent_loss(img, sent, labels, b_global, smooth),
+             oracle.img_loss(d["img"], fake, labels, b_global, smooth),
+             oracle.word_loss(regions, words, d["mask"], labels, b_global, smooth, 4.0, 5.0, 6.0)]
+    loss = parts[0] + 0.5 * parts[1] + parts[2]
+    loss.backward()
+    for rank in range(WORLD):
+        sl = slice(rank * B, (rank + 1) * B)
+        r = out[rank]
+        for got, ref in zip(r["parts"], parts):
+            assert abs(float(got) - float(ref.detach())) < 1e-6 * abs(float(ref.detach())), (rank, float(got), float(ref))
+        for got, ref in zip(r["grads"], (img.grad, sent.grad, words.grad, regions.grad, fake.grad)):
+            err = float((got - ref[sl]).norm() / ref[sl].norm())
+            assert err < 1e-6, (rank, err)
+
+
+def test_cosine_scores_is_differentiable_like_the_reference():
+    """train_gan.cosine_scores carries a gradient (the reference's is an ordinary torch expression, :85-91)."""
+    import oracle
+    sys.path.insert(0, HERE)
+    from cpu_ops import CpuOps
+    from xmc_gan_b200 import train_gan as T
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(5, 12, generator=g, dtype=torch.float64).requires_grad_()
+    b = torch.randn(7, 12, generator=g, dtype=torch.float64).requires_grad_()
+    w = torch.randn(5, 7, generator=g, dtype=torch.float64)
+    (T.cosine_scores(a, b, _ops=CpuOps()) * w).sum().backward()
+    a2, b2 = a.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    (oracle.cosine_scores(a2, b2) * w).sum().backward()
+    # the upstream gradient crosses the boundary as fp32 (the C ABI's type): 1e-6, not 1e-12
+    assert torch.allclose(a.grad, a2.grad, atol=1e-6) and torch.allclose(b.grad, b2.grad, atol=1e-6)
+
+
+def test_identity_tag_does_not_survive_an_edit():
+    """make_labels tags identity labels so the kernels skip reading them; an in-place edit voids the tag."""
+    from xmc_gan_b200 import losses as L
+    lab = L.tag_identity(torch.eye(4))
+    assert L._is_identity(lab, (4, 4))
+    assert not L._is_identity(lab, (4, 8))
+    lab[0, 1] = 0.5
+    assert not L._is_identity(lab, (4, 4))

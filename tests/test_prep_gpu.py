@@ -12,9 +12,14 @@ def _ops():
     return default_ops()
 
 
+def _hops():
+    """The hooks build: the only one in which the generic-kernel switch exists."""
+    from util import hooks_ops
+    return hooks_ops()
+
+
 def _generic(on):
-    from xmc_gan_b200 import _lib
-    _lib.lib().xmc_internal_set_prep_generic(int(on))
+    _hops().L.xmc_internal_set_prep_generic(int(on))
 
 
 def _reference(x, Lpad, row_of=None):
@@ -107,7 +112,8 @@ def test_compact_rows_forward_and_backward(B, D, T):
 @pytest.mark.parametrize("B,D,L,Lpad,compact", [(3, 256, 289, 304, False), (2, 128, 289, 304, False),
                                                 (16, 256, 18, 18, True), (5, 128, 33, 33, True), (2, 256, 31, 32, False)])
 def test_bf16_fast_kernels_are_bit_identical_to_generic(B, D, L, Lpad, compact):
-    ops = _ops()
+    ops = _hops()                                     # generic = hooks build with the switch on; fast = the same build, switch off
+    prod = _ops()
     g = torch.Generator().manual_seed(L)
     x = torch.randn(B, D, L, generator=g).bfloat16().cuda()
     x[0, :, 1] = 0
@@ -125,6 +131,11 @@ def test_bf16_fast_kernels_are_bit_identical_to_generic(B, D, L, Lpad, compact):
     finally:
         _generic(False)
     for a, b in zip(out[True], out[False]):
+        assert torch.equal(a, b)
+    # and the product library (no switch at all) takes the fast kernels: same bits again
+    xn, norm = prod.normalize_transpose(x, Lpad, torch.bfloat16, row_of=row_of)
+    d16 = prod.normalize_transpose_backward(xn, norm, dxn, dnorm, L, torch.bfloat16, row_of=row_of)
+    for a, b in zip((xn, norm, d16), out[False][:3]):
         assert torch.equal(a, b)
 
 

@@ -36,12 +36,13 @@ def _err_word(ops):
 
 
 @pytest.mark.parametrize("D", [256, 128, 64])
-def test_tmem_dump_matches_matmul(ops, D):
+def test_tmem_dump_matches_matmul(D):
+    from util import hooks_ops
     from xmc_gan_b200 import _lib
+    ops = hooks_ops()                                      # the debug dump exists only in the -DXMC_TEST_HOOKS build
     B, T_, R = 8, 18, 100
     qn, kn, rnorm, _ = _operands(ops, B, D, T_, R, seed=D)
-    hook = _lib.lib().xmc_internal_set_debug_dump
-    hook.argtypes, hook.restype = [ctypes.c_int], None
+    hook = ops.L.xmc_internal_set_debug_dump
     hook(1)
     try:
         lsum, cnorm, rel, _ = ops.wordregion_forward(_lib.PATH_BF16_TCGEN05, qn, kn, rnorm, R, 5.0)
@@ -236,10 +237,10 @@ def test_more_word_tiles_than_sms(ops):
 def test_never_written_tmem_columns_are_not_read(B, D, T_, R):
     """Chunks narrower than 64 regions leave TMEM columns the MMAs never write.  With tensor memory filled
     with NaNs first (debug flag 16) the result must not change: nothing stale may leak into the sums."""
-    from xmc_gan_b200 import _lib
+    from util import hooks_ops
     from xmc_gan_b200 import train_gan as T
-    hook = _lib.lib().xmc_internal_set_debug_dump
-    hook.argtypes, hook.restype = [ctypes.c_int], None
+    hops = hooks_ops()                                     # the NaN-poisoning flag exists only in the hooks build
+    hook = hops.L.xmc_internal_set_debug_dump
     words, regions, mask = word_inputs(B, D, T_, R, seed=B + R)
     labels = T.make_labels(B, None, False)
     out = []
@@ -248,7 +249,7 @@ def test_never_written_tmem_columns_are_not_read(B, D, T_, R):
         try:
             r = regions.bfloat16().cuda().requires_grad_()
             w = words.bfloat16().cuda().requires_grad_()
-            loss = T.word_loss(r, w, mask.cuda(), labels, False, precision="bf16")
+            loss = T.word_loss(r, w, mask.cuda(), labels, False, precision="bf16", _ops=hops)
             loss.backward()
             torch.cuda.synchronize()
             out.append((loss.detach(), r.grad.float(), w.grad.float()))

@@ -46,3 +46,18 @@ def word_inputs(B, D, T, R, seed, lean=0.3, min_len=None):
     lens = torch.randint(lo, T + 1, (B,), generator=g)
     mask = torch.arange(T).unsqueeze(0) >= lens.unsqueeze(1)
     return words, regions, mask
+
+
+_hooks_ops = None
+
+
+def hooks_ops():
+    """A CudaOps bound to libxmcloss_hooks.so — the -DXMC_TEST_HOOKS build of the same sources, which adds the
+    debug setters (TMEM dump, NaN poisoning, generic-kernel switch).  The product library has none of them."""
+    global _hooks_ops
+    if _hooks_ops is None:
+        from xmc_gan_b200 import _lib
+        from xmc_gan_b200.ops import CudaOps
+        _lib.build()
+        _hooks_ops = CudaOps(lib=_lib.hooks_lib())
+    return _hooks_ops

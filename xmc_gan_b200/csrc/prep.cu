@@ -109,8 +109,10 @@ template <typename TX, typename TO>
 __global__ void __launch_bounds__(256) norm_tr_bwd_kernel(const TX* __restrict__ xn, const float* __restrict__ norm,
                                                            const float* __restrict__ dxn, const float* __restrict__ dnorm,
                                                            int D, int L, int Lpad, const int* __restrict__ row_of,
-                                                           TO* __restrict__ dx) {
+                                                           const int* __restrict__ error_word, TO* __restrict__ dx) {
   extern __shared__ float tile[];                 // [D][kLT+1] holds the finished dx tile
+  // a kernel upstream (tcgen05 backward) timed out: its accumulators are garbage, so the gradient is NaN
+  const float poison = (error_word && __ldg(error_word) != 0) ? __int_as_float(0x7fc00000) : 0.f;
   const int b = blockIdx.y, l0 = blockIdx.x * kLT;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = warp; r < kLT; r += 8) {
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(256) norm_tr_bwd_kernel(const TX* __restrict__
   __syncthreads();
   const int l = l0 + lane;
   if (l < L)
-    for (int d = warp; d < D; d += 8) st1(dx + ((size_t)b * D + d) * L + l, tile[d * (kLT + 1) + lane]);
+    for (int d = warp; d < D; d += 8) st1(dx + ((size_t)b * D + d) * L + l, tile[d * (kLT + 1) + lane] + poison);
 }
 
 // ---- bf16 fast paths (D = 128 or 256: the shapes of the tcgen05 word-region kernels) ----------------------
@@ -272,8 +274,9 @@ template <int D, typename TO>
 __global__ void __launch_bounds__(256, 3) norm_tr_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ xn, const float* __restrict__ norm,
                                                                 const float* __restrict__ dxn, const float* __restrict__ dnorm,
                                                                 int L, int Lpad, const int* __restrict__ row_of,
-                                                                TO* __restrict__ dx) {
+                                                                const int* __restrict__ error_word, TO* __restrict__ dx) {
   constexpr int kC = D / 128;                     // 128-bit groups per lane and row
+  const float poison = (error_word && __ldg(error_word) != 0) ? __int_as_float(0x7fc00000) : 0.f;
   constexpr int kRows = kLT / 8;                  // rows per warp
   using Tile = BwdTile<TO>;
   __shared__ uint32_t tile[kLT * (D * Tile::kWordsPerD2 / 2 + 1)];   // [l][d] finished dx values
@@ -325,8 +328,8 @@ __global__ void __launch_bounds__(256, 3) norm_tr_bwd_bf16_kernel(const __nv_bfl
     for (int c = 0; c < kC; ++c) {
       const float4 X = xh[k][c], G = g[k][c];
       Tile::template put4<D>(tile, r, c * 128 + lane * 4,
-                             (G.x - X.x * pj) * inv + dnk * X.x, (G.y - X.y * pj) * inv + dnk * X.y,
-                             (G.z - X.z * pj) * inv + dnk * X.z, (G.w - X.w * pj) * inv + dnk * X.w);
+                             (G.x - X.x * pj) * inv + dnk * X.x + poison, (G.y - X.y * pj) * inv + dnk * X.y + poison,
+                             (G.z - X.z * pj) * inv + dnk * X.z + poison, (G.w - X.w * pj) * inv + dnk * X.w + poison);
     }
   }
   __syncthreads();
@@ -390,7 +393,11 @@ __global__ void __launch_bounds__(256) word_scores_bwd_kernel(const float* __res
   }
 }
 
-static int g_prep_generic = 0;   // tests / A-B timing only: 1 = always take the generic kernels
+#ifdef XMC_TEST_HOOKS
+static int g_prep_generic = 0;   // tests / A-B timing only (libxmcloss_hooks.so): 1 = always take the generic kernels
+#else
+static constexpr int g_prep_generic = 0;
+#endif
 
 template <typename TI>
 static int launch_norm_tr(const void* x, int B, int D, int L, int Lpad, int out_dtype, const int* row_of, void* xn, float* norm, cudaStream_t st) {
@@ -416,18 +423,18 @@ static int launch_norm_tr(const void* x, int B, int D, int L, int Lpad, int out_
 
 template <typename TX>
 static int launch_norm_tr_bwd(const void* xn, const float* norm, const float* dxn, const float* dnorm, int B, int D, int L,
-                              int Lpad, int out_dtype, const int* row_of, void* dx, cudaStream_t st) {
+                              int Lpad, int out_dtype, const int* row_of, const int* err, void* dx, cudaStream_t st) {
   dim3 grid((L + kLT - 1) / kLT, B);
   if (std::is_same<TX, __nv_bfloat16>::value && (D == 128 || D == 256) && !g_prep_generic) {
     auto* xi = static_cast<const __nv_bfloat16*>(xn);
     if (out_dtype == XMC_F32) {
       auto* o = static_cast<float*>(dx);
-      if (D == 128) norm_tr_bwd_bf16_kernel<128, float><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, o);
-      else norm_tr_bwd_bf16_kernel<256, float><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, o);
+      if (D == 128) norm_tr_bwd_bf16_kernel<128, float><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, err, o);
+      else norm_tr_bwd_bf16_kernel<256, float><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, err, o);
     } else {
       auto* o = static_cast<__nv_bfloat16*>(dx);
-      if (D == 128) norm_tr_bwd_bf16_kernel<128, __nv_bfloat16><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, o);
-      else norm_tr_bwd_bf16_kernel<256, __nv_bfloat16><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, o);
+      if (D == 128) norm_tr_bwd_bf16_kernel<128, __nv_bfloat16><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, err, o);
+      else norm_tr_bwd_bf16_kernel<256, __nv_bfloat16><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, L, Lpad, row_of, err, o);
     }
     return cuda_fail(cudaGetLastError(), "norm_tr_bwd_bf16_kernel launch");
   }
@@ -437,9 +444,9 @@ static int launch_norm_tr_bwd(const void* xn, const float* norm, const float* dx
     XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(norm_tr_bwd_kernel<TX, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (out_dtype == XMC_F32)
-    norm_tr_bwd_kernel<TX, float><<<grid, 256, smem, st>>>(static_cast<const TX*>(xn), norm, dxn, dnorm, D, L, Lpad, row_of, static_cast<float*>(dx));
+    norm_tr_bwd_kernel<TX, float><<<grid, 256, smem, st>>>(static_cast<const TX*>(xn), norm, dxn, dnorm, D, L, Lpad, row_of, err, static_cast<float*>(dx));
   else
-    norm_tr_bwd_kernel<TX, __nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const TX*>(xn), norm, dxn, dnorm, D, L, Lpad, row_of, static_cast<__nv_bfloat16*>(dx));
+    norm_tr_bwd_kernel<TX, __nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const TX*>(xn), norm, dxn, dnorm, D, L, Lpad, row_of, err, static_cast<__nv_bfloat16*>(dx));
   return cuda_fail(cudaGetLastError(), "norm_tr_bwd_kernel launch");
 }
 
@@ -455,7 +462,9 @@ static int check_nt(const void* a, const void* b, int B, int D, int L, int Lpad,
 
 using namespace xmc;
 
+#ifdef XMC_TEST_HOOKS
 extern "C" void xmc_internal_set_prep_generic(int on) { xmc::g_prep_generic = on; }
+#endif
 
 extern "C" int xmc_word_rows_compact(const uint8_t* mask, int Bc, int T, int* row_of, int* cap_ptr, void* stream) {
   XMC_REQUIRE(mask && row_of && cap_ptr, XMC_ERR_INVALID_ARG, "null pointer");
@@ -475,13 +484,14 @@ extern "C" int xmc_normalize_transpose(const void* x, int B, int D, int L, int L
 
 extern "C" int xmc_normalize_transpose_backward(const void* xn, const float* norm, const float* dxn,
                                                 const float* dnorm, int B, int D, int L, int Lpad,
-                                                int xn_dtype, int out_dtype, const int* row_of, void* dx, void* stream) {
+                                                int xn_dtype, int out_dtype, const int* row_of,
+                                                const int* error_word, void* dx, void* stream) {
   if (int rc = check_nt(xn, dx, B, D, L, Lpad, xn_dtype, out_dtype)) return rc;
   XMC_REQUIRE(norm && dxn, XMC_ERR_INVALID_ARG, "null pointer");
   XMC_REQUIRE(!row_of || (Lpad == L && !dnorm), XMC_ERR_INVALID_ARG, "row_of needs Lpad == L and no dnorm");
   return xn_dtype == XMC_F32
-             ? launch_norm_tr_bwd<float>(xn, norm, dxn, dnorm, B, D, L, Lpad, out_dtype, row_of, dx, as_stream(stream))
-             : launch_norm_tr_bwd<__nv_bfloat16>(xn, norm, dxn, dnorm, B, D, L, Lpad, out_dtype, row_of, dx, as_stream(stream));
+             ? launch_norm_tr_bwd<float>(xn, norm, dxn, dnorm, B, D, L, Lpad, out_dtype, row_of, error_word, dx, as_stream(stream))
+             : launch_norm_tr_bwd<__nv_bfloat16>(xn, norm, dxn, dnorm, B, D, L, Lpad, out_dtype, row_of, error_word, dx, as_stream(stream));
 }
 
 extern "C" int xmc_word_scores(const float* rel, const uint8_t* mask, const int* cap_ptr, int Bi, int Bc, int T,

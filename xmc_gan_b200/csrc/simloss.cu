@@ -33,6 +33,7 @@ struct SimParams {
   const float* grad_out;
   void* da; void* db;
   int n_a_blocks;
+  const float* ds_given;   // cosine_scores backward: d loss / d scores comes from the caller instead of the closed form
 };
 
 constexpr int kSimThreads = 256;
@@ -176,14 +177,15 @@ __global__ void __launch_bounds__(kSimThreads) sim_bwd_kernel(SimParams p) {
   __shared__ float red[ROWS][DCH * 128];
   for (int k = threadIdx.x; k < ROWS * DCH * 128; k += kSimThreads) (&red[0][0])[k] = 0.f;
 
+  const bool given = p.ds_given != nullptr;
   float x_lse[ROWS], x_sl[ROWS], x_inv_n[ROWS];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
     const int k = min(r0 + r, NX - 1);
-    x_lse[r] = xs[k]; x_sl[r] = xs[NX + k];
-    x_inv_n[r] = x_tot / (xdiv ? xdiv[k] : p.num_pos);
+    x_lse[r] = given ? 0.f : xs[k]; x_sl[r] = given ? 0.f : xs[NX + k];
+    x_inv_n[r] = given ? 0.f : x_tot / (xdiv ? xdiv[k] : p.num_pos);
   }
-  const float go = __ldg(p.grad_out) * p.scale;
+  const float go = given ? 1.f : __ldg(p.grad_out) * p.scale;
 
   float4 acc[ROWS][DCH];
 #pragma unroll
@@ -196,8 +198,10 @@ __global__ void __launch_bounds__(kSimThreads) sim_bwd_kernel(SimParams p) {
     const bool y_ok = y < NY;
     float y_lse = 0.f, y_sl = 0.f, y_inv_n = 0.f, y_inv = 0.f;
     if (y_ok) {
-      y_lse = ys[y]; y_sl = ys[NY + y];
-      y_inv_n = y_tot / (ydiv ? ydiv[y] : p.num_pos);
+      if (!given) {
+        y_lse = ys[y]; y_sl = ys[NY + y];
+        y_inv_n = y_tot / (ydiv ? ydiv[y] : p.num_pos);
+      }
       y_inv = inv_y[y];
     }
 #pragma unroll
@@ -206,10 +210,14 @@ __global__ void __launch_bounds__(kSimThreads) sim_bwd_kernel(SimParams p) {
       const int x = r0 + r;
       if (y_ok && x < NX) {
         const int i = a_side ? x : y, j = a_side ? y : x;
-        const float z = p.scale * __ldg(p.scores + (size_t)i * p.Bk + j);
-        const float lab = label_at(p.labels, p.Bk, i, j, p.diag);
-        // dscore is symmetric in (row-stat, col-stat) roles
-        v = go * dscore(z, lab, x_lse[r], x_sl[r], x_inv_n[r], y_lse, y_sl, y_inv_n) * y_inv;
+        if (given) {
+          v = __ldg(p.ds_given + (size_t)i * p.Bk + j) * y_inv;
+        } else {
+          const float z = p.scale * __ldg(p.scores + (size_t)i * p.Bk + j);
+          const float lab = label_at(p.labels, p.Bk, i, j, p.diag);
+          // dscore is symmetric in (row-stat, col-stat) roles
+          v = go * dscore(z, lab, x_lse[r], x_sl[r], x_inv_n[r], y_lse, y_sl, y_inv_n) * y_inv;
+        }
       }
       ds_sh[warp][r][lane] = v;
     }
@@ -332,6 +340,7 @@ struct TailParams {
   const float* grad_out;
   float* out;
   int n_row_blocks;
+  const int* error_word;   // tail_loss_kernel: non-zero word (a kernel upstream timed out) -> the loss is NaN
   // fused word-score backward (tail_grad_words_kernel)
   const float* rel; const uint8_t* mask; const int* cap_ptr; int T, NQs; float rho2;
 };
@@ -404,6 +413,43 @@ __global__ void __launch_bounds__(256) combine_stats_kernel(const float* __restr
   out[2 * Bk + j] = slz;
 }
 
+// Sharded problem, after the packet exchange: gathered[w * stride + ...] = rank w's packet {column statistics over its
+// rows [3][Bk], its row-direction partial loss}.  Merges the column statistics (written to col_stats for the backward)
+// and evaluates the GLOBAL loss: column direction over all Bk columns from the merged statistics, row direction as the sum
+// of the ranks' partials.  Every rank computes the same number, so no all-reduce follows.  Single CTA.
+__global__ void __launch_bounds__(1024) combine_loss_kernel(const float* __restrict__ g, int world, int stride, int Bk,
+                                                             const float* __restrict__ col_div, float num_pos,
+                                                             float inv_cols_total, float* __restrict__ col_stats,
+                                                             float* __restrict__ loss_out) {
+  float s0 = 0.f;
+  for (int j = threadIdx.x; j < Bk; j += 1024) {
+    float m = -INFINITY, sl = 0.f, slz = 0.f;
+    for (int w = 0; w < world; ++w) m = fmaxf(m, g[(size_t)w * stride + j]);
+    float s = 0.f;
+    for (int w = 0; w < world; ++w) {
+      const float* gw = g + (size_t)w * stride;
+      s += (m == -INFINITY) ? 0.f : expf(gw[j] - m);
+      sl += gw[Bk + j];
+      slz += gw[2 * Bk + j];
+    }
+    const float lse = (m == -INFINITY) ? -INFINITY : m + logf(s);
+    col_stats[j] = lse; col_stats[Bk + j] = sl; col_stats[2 * Bk + j] = slz;
+    const float n = col_div ? col_div[j] : num_pos;
+    s0 += (lse * sl - slz) / n;
+  }
+  __shared__ float sh[32];
+  s0 = warp_sum(s0);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 32; ++w) a += sh[w];
+    a *= inv_cols_total;
+    for (int w = 0; w < world; ++w) b += g[(size_t)w * stride + 3 * Bk];     // NaN if any rank's kernel timed out
+    loss_out[0] = a + b; loss_out[1] = a; loss_out[2] = b;
+  }
+}
+
 // loss_out[0] = s0_part + s1_part, [1] = s0_part (columns), [2] = s1_part (rows); single CTA.
 __global__ void __launch_bounds__(256) tail_loss_kernel(TailParams p) {
   float s0 = 0.f, s1 = 0.f;
@@ -424,6 +470,7 @@ __global__ void __launch_bounds__(256) tail_loss_kernel(TailParams p) {
     float a = 0.f, b = 0.f;
     for (int w = 0; w < 8; ++w) { a += sh0[w]; b += sh1[w]; }
     a *= p.inv_cols_total; b *= p.inv_rows_total;
+    if (p.error_word && *p.error_word != 0) a = b = __int_as_float(0x7fc00000);   // never a plausible number
     p.out[0] = a + b; p.out[1] = a; p.out[2] = b;
   }
 }
@@ -571,6 +618,18 @@ extern "C" int xmc_cosine_scores(const void* a, const void* b, int Bq, int Bk, i
   return sim_dispatch(2, p, dtype, as_stream(stream));
 }
 
+extern "C" int xmc_cosine_scores_backward(const void* a, const void* b, int Bq, int Bk, int D, int dtype,
+                                          const float* inv_norm_a, const float* inv_norm_b, const float* dscores,
+                                          void* da, void* db, void* stream) {
+  if (int rc = check_sim_args(a, b, Bq, Bk, D, dtype)) return rc;
+  XMC_REQUIRE(inv_norm_a && inv_norm_b && dscores, XMC_ERR_INVALID_ARG, "null pointer");
+  SimParams p{};
+  p.a = a; p.b = b; p.Bq = Bq; p.Bk = Bk; p.D = D;
+  p.inv_a = const_cast<float*>(inv_norm_a); p.inv_b = const_cast<float*>(inv_norm_b);
+  p.ds_given = dscores; p.da = da; p.db = db;
+  return sim_dispatch(1, p, dtype, as_stream(stream));
+}
+
 extern "C" int xmc_simloss_forward(const void* a, const void* b, int Bq, int Bk, int D, int dtype,
                                    const float* labels, int diag_offset, float scale,
                                    float* scores, float* inv_norm_a, float* inv_norm_b,
@@ -635,10 +694,20 @@ extern "C" int xmc_infonce_combine_stats(const float* gathered, int world, int B
   return cuda_fail(cudaGetLastError(), "combine_stats_kernel launch");
 }
 
+extern "C" int xmc_infonce_combine_loss(const float* gathered, int world, int stride, int Bk, const float* col_div,
+                                        float num_pos, int cols_total, float* col_stats, float* loss_out, void* stream) {
+  XMC_REQUIRE(gathered && col_stats && loss_out, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(world > 0 && Bk > 0 && stride >= 3 * Bk + 1 && cols_total > 0 && num_pos > 0.f, XMC_ERR_INVALID_ARG,
+              "bad sizes world=%d Bk=%d stride=%d", world, Bk, stride);
+  combine_loss_kernel<<<1, 1024, 0, as_stream(stream)>>>(gathered, world, stride, Bk, col_div, num_pos, 1.f / cols_total,
+                                                          col_stats, loss_out);
+  return cuda_fail(cudaGetLastError(), "combine_loss_kernel launch");
+}
+
 extern "C" int xmc_infonce_loss(const float* row_stats, const float* col_stats, int Bq, int Bk,
                                 const float* row_div, const float* col_div, float num_pos,
                                 int rows_total, int cols_total, int col_begin, int col_count,
-                                float* loss_out, void* stream) {
+                                float* loss_out, const int* error_word, void* stream) {
   XMC_REQUIRE(row_stats && col_stats && loss_out, XMC_ERR_INVALID_ARG, "null pointer");
   XMC_REQUIRE(Bq > 0 && Bk > 0 && rows_total > 0 && cols_total > 0 && num_pos > 0.f, XMC_ERR_INVALID_ARG, "bad sizes");
   XMC_REQUIRE(col_begin >= 0 && col_count >= 0 && col_begin + col_count <= Bk, XMC_ERR_INVALID_ARG, "bad column range");
@@ -646,7 +715,7 @@ extern "C" int xmc_infonce_loss(const float* row_stats, const float* col_stats, 
   p.Bq = Bq; p.Bk = Bk; p.row_stats = row_stats; p.col_stats = col_stats;
   p.row_div = row_div; p.col_div = col_div; p.num_pos = num_pos;
   p.inv_rows_total = 1.f / rows_total; p.inv_cols_total = 1.f / cols_total;
-  p.col_begin = col_begin; p.col_count = col_count; p.out = loss_out;
+  p.col_begin = col_begin; p.col_count = col_count; p.out = loss_out; p.error_word = error_word;
   tail_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(p);
   return cuda_fail(cudaGetLastError(), "tail_loss_kernel launch");
 }

@@ -552,7 +552,13 @@ wr_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant
   if (warp == 2) tmem_dealloc(*tmem_slot, 512);
 }
 
-static int g_debug_dump = 0;   // tests only: dump S chunk 0 and C of tile 0 / image 0 into the workspace
+// Debug flags (TMEM dump, NaN poisoning, clock64 traces, A/B switches).  The product library has no way to set
+// them: the setter exists only in the -DXMC_TEST_HOOKS build that tests and profiles/exp_*.py load.
+#ifdef XMC_TEST_HOOKS
+static int g_debug_dump = 0;
+#else
+static constexpr int g_debug_dump = 0;
+#endif
 
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1277,5 +1283,7 @@ int wordregion_tc_backward(const WrParams& p, int D, void* ws, size_t ws_bytes, 
 
 }  // namespace xmc
 
-// Not part of the public ABI (not in include/xmc_loss.h): test hook for the TMEM debug dump.
+#ifdef XMC_TEST_HOOKS
+// Not part of the public ABI (not in include/xmc_loss.h, not in libxmcloss.so): test hook for the debug flags.
 extern "C" void xmc_internal_set_debug_dump(int on) { xmc::g_debug_dump = on; }
+#endif

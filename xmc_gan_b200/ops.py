@@ -92,13 +92,25 @@ class CudaOps:
 
     name = "libxmcloss"
 
-    def __init__(self):
-        self.L = _lib.lib()
+    def __init__(self, lib=None):
+        self.L = lib if lib is not None else _lib.lib()   # lib: the -DXMC_TEST_HOOKS build (tests / experiments only)
         self.launches = 0      # kernels launched through this backend (bench.py's gpu_launches)
         self.events = None     # name -> [(start, stop)] CUDA events when kernel timing is on
-        self.last_workspace = None
         self.check_errors = bool(os.environ.get("XMC_CHECK_ERRORS"))   # tests: read the kernels' error word back
         self._tls = threading.local()   # fork state of side_scope: forward runs on the caller's thread, backward on autograd's
+
+    @property
+    def last_workspace(self):
+        """Workspace of the last word-region launch made by THIS thread (None: fp32 path, which has none)."""
+        return getattr(self._tls, "last_ws", None)
+
+    @last_workspace.setter
+    def last_workspace(self, ws):
+        self._tls.last_ws = ws
+
+    def _check(self, rc):
+        if rc != 0:
+            _lib.check(rc, self.L)
 
     def enable_timing(self, on=True):
         """Record CUDA events (current stream) around the named hot kernels; see kernel_ms()."""
@@ -113,18 +125,37 @@ class CudaOps:
         return _Timed(self, name)
 
     # -- similarity losses ------------------------------------------------------------------
-    def cosine_scores(self, a, b):
+    def cosine_scores(self, a, b, with_norms=False):
         _cuda(a, b)
         a, b = a.contiguous(), b.contiguous()
+        if a.dtype != b.dtype:
+            raise TypeError(f"operand dtypes differ: {a.dtype} vs {b.dtype}")
         Bq, D = a.shape
         Bk = b.shape[0]
         scores = torch.empty(Bq, Bk, device=a.device, dtype=torch.float32)
+        inv_a = torch.empty(Bq, device=a.device, dtype=torch.float32) if with_norms else None
+        inv_b = torch.empty(Bk, device=a.device, dtype=torch.float32) if with_norms else None
         with _on(a):
-            _lib.check(self.L.xmc_cosine_scores(_p(a), _p(b), Bq, Bk, D, _dt(a), _p(scores), None, None, _stream()))
+            self._check(self.L.xmc_cosine_scores(_p(a), _p(b), Bq, Bk, D, _dt(a), _p(scores), _p(inv_a), _p(inv_b), _stream()))
         self.launches += 1
-        return scores
+        return (scores, inv_a, inv_b) if with_norms else scores
 
-    def simloss_forward(self, a, b, labels, diag, scale):
+    def cosine_scores_backward(self, a, b, inv_a, inv_b, dscores, need_a, need_b):
+        _cuda(a, b, dscores)
+        if not (need_a or need_b):
+            return None, None
+        Bq, D = a.shape
+        Bk = b.shape[0]
+        da = torch.empty_like(a) if need_a else None
+        db = torch.empty_like(b) if need_b else None
+        with _on(a):
+            self._check(self.L.xmc_cosine_scores_backward(_p(a), _p(b), Bq, Bk, D, _dt(a), _p(inv_a), _p(inv_b), _p(dscores),
+                                                          _p(da), _p(db), _stream()))
+        self.launches += 1
+        return da, db
+
+    def simloss_forward(self, a, b, labels, diag, scale, col_stats=None):
+        """col_stats: optional [3, Bk] fp32 view to write the column statistics into (a slice of the exchange packet)."""
         _cuda(a, b, labels)
         Bq, D = a.shape
         Bk = b.shape[0]
@@ -133,9 +164,10 @@ class CudaOps:
         inv_a = torch.empty(Bq, device=dev, dtype=torch.float32)
         inv_b = torch.empty(Bk, device=dev, dtype=torch.float32)
         row_stats = torch.empty(3, Bq, device=dev, dtype=torch.float32)
-        col_stats = torch.empty(3, Bk, device=dev, dtype=torch.float32)
+        if col_stats is None:
+            col_stats = torch.empty(3, Bk, device=dev, dtype=torch.float32)
         with _on(a), self._timed("simloss_fwd"):
-            _lib.check(self.L.xmc_simloss_forward(_p(a), _p(b), Bq, Bk, D, _dt(a), _p(labels), diag, scale,
+            self._check(self.L.xmc_simloss_forward(_p(a), _p(b), Bq, Bk, D, _dt(a), _p(labels), diag, scale,
                                                   _p(scores), _p(inv_a), _p(inv_b), _p(row_stats), _p(col_stats),
                                                   _stream()))
         self.launches += 1
@@ -151,7 +183,7 @@ class CudaOps:
         if not (need_a or need_b):
             return None, None
         with _on(a), self._timed("simloss_bwd"):
-            _lib.check(self.L.xmc_simloss_backward(
+            self._check(self.L.xmc_simloss_backward(
                 _p(a), _p(b), Bq, Bk, D, _dt(a), _p(scores), _p(inv_a), _p(inv_b), _p(labels), diag, scale,
                 _p(row_stats), _p(col_stats), _p(row_div), _p(col_div), float(num_pos), rows_total, cols_total,
                 _p(grad_out), _p(da), _p(db), _stream()))
@@ -159,13 +191,14 @@ class CudaOps:
         return da, db
 
     # -- InfoNCE tail over a given score matrix -----------------------------------------------
-    def infonce_stats(self, scores, labels, diag, scale):
+    def infonce_stats(self, scores, labels, diag, scale, col_stats=None):
         _cuda(scores, labels)
         Bq, Bk = scores.shape
         row_stats = torch.empty(3, Bq, device=scores.device, dtype=torch.float32)
-        col_stats = torch.empty(3, Bk, device=scores.device, dtype=torch.float32)
+        if col_stats is None:
+            col_stats = torch.empty(3, Bk, device=scores.device, dtype=torch.float32)
         with _on(scores):
-            _lib.check(self.L.xmc_infonce_stats(_p(scores), Bq, Bk, _p(labels), diag, scale,
+            self._check(self.L.xmc_infonce_stats(_p(scores), Bq, Bk, _p(labels), diag, scale,
                                                 _p(row_stats), _p(col_stats), _stream()))
         self.launches += 1
         return row_stats, col_stats
@@ -176,20 +209,35 @@ class CudaOps:
         world, _, Bk = gathered.shape
         out = torch.empty(3, Bk, device=gathered.device, dtype=torch.float32)
         with _on(gathered):
-            _lib.check(self.L.xmc_infonce_combine_stats(_p(gathered), world, Bk, _p(out), _stream()))
+            self._check(self.L.xmc_infonce_combine_stats(_p(gathered), world, Bk, _p(out), _stream()))
         self.launches += 1
         return out
 
     def infonce_loss(self, row_stats, col_stats, row_div, col_div, num_pos, rows_total, cols_total,
-                     col_begin, col_count):
+                     col_begin, col_count, error_word=None, out=None):
+        """error_word: workspace of the tcgen05 forward that produced the scores (its word 0 is the kernel's
+        error flag); a non-zero flag makes the loss NaN on the device."""
         _cuda(row_stats, col_stats)
-        out = torch.empty(3, device=row_stats.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(3, device=row_stats.device, dtype=torch.float32)
         with _on(row_stats):
-            _lib.check(self.L.xmc_infonce_loss(_p(row_stats), _p(col_stats), row_stats.shape[1], col_stats.shape[1],
+            self._check(self.L.xmc_infonce_loss(_p(row_stats), _p(col_stats), row_stats.shape[1], col_stats.shape[1],
                                                _p(row_div), _p(col_div), float(num_pos), rows_total, cols_total,
-                                               col_begin, col_count, _p(out), _stream()))
+                                               col_begin, col_count, _p(out), _p(error_word), _stream()))
         self.launches += 1
         return out
+
+    def combine_loss(self, gathered, offset, Bk, col_div, num_pos, cols_total):
+        """gathered [world, P] packets, this loss's packet at float `offset` -> (col_stats [3, Bk], loss3 [3])."""
+        _cuda(gathered)
+        world, stride = gathered.shape
+        col_stats = torch.empty(3, Bk, device=gathered.device, dtype=torch.float32)
+        out = torch.empty(3, device=gathered.device, dtype=torch.float32)
+        with _on(gathered):
+            self._check(self.L.xmc_infonce_combine_loss(gathered.data_ptr() + 4 * offset, world, stride, Bk, _p(col_div),
+                                                        float(num_pos), cols_total, _p(col_stats), _p(out), _stream()))
+        self.launches += 1
+        return col_stats, out
 
     def infonce_grad(self, scores, labels, diag, scale, row_stats, col_stats, row_div, col_div, num_pos,
                      rows_total, cols_total, grad_out):
@@ -197,7 +245,7 @@ class CudaOps:
         Bq, Bk = scores.shape
         ds = torch.empty_like(scores)
         with _on(scores):
-            _lib.check(self.L.xmc_infonce_grad(_p(scores), Bq, Bk, _p(labels), diag, scale, _p(row_stats),
+            self._check(self.L.xmc_infonce_grad(_p(scores), Bq, Bk, _p(labels), diag, scale, _p(row_stats),
                                                _p(col_stats), _p(row_div), _p(col_div), float(num_pos),
                                                rows_total, cols_total, _p(grad_out), _p(ds), _stream()))
         self.launches += 1
@@ -210,7 +258,7 @@ class CudaOps:
         row_count = torch.empty(B, device=sim.device, dtype=torch.float32)
         tmp = torch.empty(B, device=sim.device, dtype=torch.float32)
         with _on(sim):
-            _lib.check(self.L.xmc_make_labels(_p(sim), B, float(p), float(smooth_global), _p(labels),
+            self._check(self.L.xmc_make_labels(_p(sim), B, float(p), float(smooth_global), _p(labels),
                                               _p(row_count), _p(tmp), _stream()))
         self.launches += 2
         return labels, row_count
@@ -230,7 +278,7 @@ class CudaOps:
         sumsq = torch.empty(B, device=g0.device, dtype=torch.float32)
         loss = torch.empty((), device=g0.device, dtype=torch.float32)
         with _on(g0), self._timed("gradpen_fwd"):
-            _lib.check(self.L.xmc_gradnorm_penalty_forward(_p(g0), n0, _p(g1), n1, B, _dt(g0), float(power),
+            self._check(self.L.xmc_gradnorm_penalty_forward(_p(g0), n0, _p(g1), n1, B, _dt(g0), float(power),
                                                            float(weight), S, _p(partial), _p(sumsq), _p(loss), _stream()))
         self.launches += 2
         return loss, sumsq
@@ -242,7 +290,7 @@ class CudaOps:
         d0 = torch.empty_like(g0) if need0 else None
         d1 = torch.empty_like(g1) if need1 else None
         with _on(g0), self._timed("gradpen_bwd"):
-            _lib.check(self.L.xmc_gradnorm_penalty_backward(_p(g0), n0, _p(g1), n1, B, _dt(g0), float(power),
+            self._check(self.L.xmc_gradnorm_penalty_backward(_p(g0), n0, _p(g1), n1, B, _dt(g0), float(power),
                                                             float(weight), S, _p(sumsq), _p(grad_out), _p(d0), _p(d1),
                                                             _stream()))
         self.launches += 1
@@ -259,7 +307,7 @@ class CudaOps:
         row_of = torch.empty(Bc * T, device=mask_u8.device, dtype=torch.int32)
         cap_ptr = torch.empty(Bc + 1, device=mask_u8.device, dtype=torch.int32)
         with _on(mask_u8):
-            _lib.check(self.L.xmc_word_rows_compact(_p(mask_u8), Bc, T, _p(row_of), _p(cap_ptr), _stream()))
+            self._check(self.L.xmc_word_rows_compact(_p(mask_u8), Bc, T, _p(row_of), _p(cap_ptr), _stream()))
         self.launches += 1
         return row_of, cap_ptr
 
@@ -272,18 +320,19 @@ class CudaOps:
             xn = torch.empty(B, Lpad, D, device=x.device, dtype=out_dtype)
         norm = torch.empty(B, Lpad, device=x.device, dtype=torch.float32)
         with _on(x):
-            _lib.check(self.L.xmc_normalize_transpose(_p(x), B, D, L, Lpad, _dt(x), _DT[out_dtype], _p(row_of),
+            self._check(self.L.xmc_normalize_transpose(_p(x), B, D, L, Lpad, _dt(x), _DT[out_dtype], _p(row_of),
                                                       _p(xn), _p(norm), _stream()))
         self.launches += 1
         return xn, norm
 
-    def normalize_transpose_backward(self, xn, norm, dxn, dnorm, L, out_dtype, row_of=None):
+    def normalize_transpose_backward(self, xn, norm, dxn, dnorm, L, out_dtype, row_of=None, error_word=None):
         _cuda(xn, dxn)
         B, Lpad, D = xn.shape
         dx = torch.empty(B, D, L, device=xn.device, dtype=out_dtype)
         with _on(xn):
-            _lib.check(self.L.xmc_normalize_transpose_backward(_p(xn), _p(norm), _p(dxn), _p(dnorm), B, D, L, Lpad,
-                                                               _dt(xn), _DT[out_dtype], _p(row_of), _p(dx), _stream()))
+            self._check(self.L.xmc_normalize_transpose_backward(_p(xn), _p(norm), _p(dxn), _p(dnorm), B, D, L, Lpad,
+                                                               _dt(xn), _DT[out_dtype], _p(row_of), _p(error_word), _p(dx),
+                                                               _stream()))
         self.launches += 1
         return dx
 
@@ -303,7 +352,8 @@ class CudaOps:
         return ws, n
 
     def wordregion_forward(self, path, qn, kn, rnorm, R, rho1, save_context=False, nq_dev=None):
-        """-> lsum, cnorm, rel [Bi, NQ] (+ chat [Bi, NQ, D] bf16 on the tcgen05 path when asked).
+        """-> lsum, cnorm, rel [Bi, NQ] (+ chat [Bi, NQ, D] bf16 on the tcgen05 path when asked).  The kernel's
+        workspace (word 0 = its error flag) is ``self.last_workspace`` on the calling thread afterwards.
 
         nq_dev: device int32 holding the number of valid (compact) rows of qn; rows beyond it are
         neither read nor written by any kernel of the path."""
@@ -319,7 +369,7 @@ class CudaOps:
             chat = torch.empty(Bi, NQ, D, device=dev, dtype=torch.bfloat16)
         ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
         with _on(qn), self._timed("wordregion_fwd"):
-            _lib.check(self.L.xmc_wordregion_forward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
+            self._check(self.L.xmc_wordregion_forward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
                                                      _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(nq_dev), _p(ws), n,
                                                      _stream()))
         self.launches += 1
@@ -339,16 +389,19 @@ class CudaOps:
     # A fork/join pair for independent pieces of one autograd function (capture-safe: the join happens
     # before the function returns, so a CUDA-graph capture never ends with a dangling forked stream).
     @contextlib.contextmanager
-    def side_scope(self, dev):
-        """Body runs on the side stream, ordered after what the current stream holds so far.  Yields a
+    def side_scope(self, dev, idx=0):
+        """Body runs on side stream ``idx``, ordered after what the current stream holds so far.  Yields a
         function ``mark()`` -> event recorded on the side stream at that point."""
         if getattr(self, "events", None) is not None or not self.use_side_stream:
             yield lambda: None                 # per-kernel timing (enable_timing): one stream, clean event pairs
             return
         cur = torch.cuda.current_stream(dev)
-        side = self._side_stream(dev)
+        side = self._side_stream(dev, idx)
+        if cur == side:                        # nested use from a body that already runs there
+            yield lambda: None
+            return
         side.wait_stream(cur)
-        self._tls.forked = True
+        self._forked().add(idx)
         with torch.cuda.stream(side):
             def mark():
                 ev = torch.cuda.Event()
@@ -359,20 +412,26 @@ class CudaOps:
     def wait_mark(self, dev, ev):
         torch.cuda.current_stream(dev).wait_event(ev)
 
-    def join_side(self, dev, *tensors):
-        """Current stream waits for everything on the side stream; ``tensors`` (allocated there) are marked
+    def join_side(self, dev, *tensors, idx=0):
+        """Current stream waits for everything on side stream ``idx``; ``tensors`` (allocated there) are marked
         as used by the current stream for the caching allocator."""
-        if not getattr(self._tls, "forked", False):
+        forked = self._forked()
+        if idx not in forked:
             return
-        self._tls.forked = False
+        forked.discard(idx)
         cur = torch.cuda.current_stream(dev)
-        cur.wait_stream(self._side_stream(dev))
+        cur.wait_stream(self._side_stream(dev, idx))
         for t in tensors:
             if t is not None:
                 t.record_stream(cur)
 
-    def _side_stream(self, dev):
-        key = (dev.type, dev.index)
+    def _forked(self):
+        if not hasattr(self._tls, "forked"):
+            self._tls.forked = set()
+        return self._tls.forked
+
+    def _side_stream(self, dev, idx=0):
+        key = (dev.type, dev.index, idx)
         if not hasattr(self, "_sides"):
             self._sides = {}
         if key not in self._sides:
@@ -394,7 +453,7 @@ class CudaOps:
             drnorm = torch.zeros(Bi, Rpad, device=dev, dtype=torch.float32) if rnorm is not None else None
             ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
         with _on(qn), self._timed("wordregion_bwd"):
-            _lib.check(self.L.xmc_wordregion_backward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
+            self._check(self.L.xmc_wordregion_backward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),
                                                       _p(lsum), _p(cnorm), _p(rel), _p(chat), _p(grel), _p(dqn), _p(dkn),
                                                       _p(drnorm), _p(nq_dev), _p(ws), n, _stream()))
         self.launches += 1
@@ -406,7 +465,7 @@ class CudaOps:
         Bi, NQs = rel.shape
         scores = torch.empty(Bi, Bc, device=rel.device, dtype=torch.float32)
         with _on(rel):
-            _lib.check(self.L.xmc_word_scores(_p(rel), _p(mask_u8), _p(cap_ptr), Bi, Bc, T, NQs, float(rho2),
+            self._check(self.L.xmc_word_scores(_p(rel), _p(mask_u8), _p(cap_ptr), Bi, Bc, T, NQs, float(rho2),
                                               _p(scores), _stream()))
         self.launches += 1
         return scores
@@ -417,7 +476,7 @@ class CudaOps:
         NQs = rel.shape[1]
         grel = torch.empty_like(rel)
         with _on(rel):
-            _lib.check(self.L.xmc_word_scores_backward(_p(rel), _p(mask_u8), _p(cap_ptr), _p(scores), _p(dscores),
+            self._check(self.L.xmc_word_scores_backward(_p(rel), _p(mask_u8), _p(cap_ptr), _p(scores), _p(dscores),
                                                        Bi, Bc, T, NQs, float(rho2), _p(grel), _stream()))
         self.launches += 1
         return grel
@@ -430,7 +489,7 @@ class CudaOps:
         NQs = rel.shape[1]
         grel = torch.empty_like(rel)
         with _on(rel):
-            _lib.check(self.L.xmc_word_scores_infonce_backward(
+            self._check(self.L.xmc_word_scores_infonce_backward(
                 _p(rel), _p(mask_u8), _p(cap_ptr), _p(scores), Bi, Bc, T, NQs, float(rho2), _p(labels), diag,
                 float(scale), _p(row_stats), _p(col_stats), _p(row_div), _p(col_div), float(num_pos), rows_total,
                 cols_total, _p(grad_out), _p(grel), _stream()))

@@ -21,7 +21,8 @@ from . import losses as _L
 from .config import cfg  # noqa: F401  (re-exported: callers set cfg.TRAIN.SMOOTH.GLOBAL here)
 from .ops import default_ops
 
-__all__ = ["cfg", "make_labels", "cosine_scores", "sent_loss", "img_loss", "word_loss", "magp_penalty"]
+__all__ = ["cfg", "make_labels", "cosine_scores", "sent_loss", "img_loss", "word_loss", "contrastive_losses",
+           "magp_penalty"]
 
 
 def make_labels(batch_size, sent_embs, b_global, p=0.6, *, group=None, device=None, _ops=None):
@@ -34,33 +35,38 @@ def make_labels(batch_size, sent_embs, b_global, p=0.6, *, group=None, device=No
     With ``group``, returns the rank's rows ``[B, B_global]`` of the global label matrix.
     """
     ops = _ops or default_ops()            # _ops: test hook (CPU checker backend under gloo), never set by users
-    comm = _L.Comm(group)
+    comm = _L.as_comm(group)
     if device is None:
         device = sent_embs.device if sent_embs is not None and (sent_embs.is_cuda or _ops) else torch.device("cuda")
     if not b_global:
         B_all = batch_size * comm.world
         labels = torch.zeros(batch_size, B_all, device=device, dtype=torch.float32)
         labels.diagonal(comm.rank * batch_size).fill_(1.0)
-        labels._xmc_identity = True
-        return labels
+        return _L.tag_identity(labels)
     s = sent_embs.detach()
     if s.dtype not in (torch.float32, torch.bfloat16):
         s = s.to(torch.float32)
     s_all = comm.all_gather_cat(s.contiguous())
     sim = ops.cosine_scores(s_all, s_all)
     labels, row_count = ops.make_labels(sim, p, cfg.TRAIN.SMOOTH.GLOBAL)
+    col_count = row_count                  # the divisor of column j is the positive count of ROW j (:99, 105)
     if comm.active:
         lo = comm.rank * batch_size
         labels = labels[lo:lo + batch_size].contiguous()
         row_count = row_count[lo:lo + batch_size].contiguous()
-    labels._xmc_identity = False
-    labels._xmc_row_count = row_count
+    # (labels > 0).sum(1) of the local rows / of every row of the global matrix, valid while the tensor is unedited
+    labels._xmc_row_count, labels._xmc_col_count = row_count, col_count
+    labels._xmc_counts_of = (labels._version, tuple(labels.shape))
     return labels
 
 
 def cosine_scores(emb0, emb1, *, _ops=None):
-    """``normalize(emb0) @ normalize(emb1).T`` — ``xmc_gan/train_gan.py:85-91`` (no autograd)."""
-    return (_ops or default_ops()).cosine_scores(emb0.detach(), emb1.detach())
+    """``normalize(emb0) @ normalize(emb1).T`` — ``xmc_gan/train_gan.py:85-91``; differentiable like the
+    reference's expression (the backward is one kernel: dS @ other side + normalize-backward)."""
+    ops = _ops or default_ops()
+    if torch.is_grad_enabled() and (emb0.requires_grad or emb1.requires_grad):
+        return _L.CosineScoresFn.apply(emb0, emb1, ops)
+    return ops.cosine_scores(emb0.detach(), emb1.detach())
 
 
 def sent_loss(imgs, txts, labels, b_global, *, tau=1.0, group=None, _ops=None):
@@ -85,6 +91,19 @@ def word_loss(imgs, words, mask, labels, b_global, *, rho1=5.0, rho2=5.0, rho3=1
     """
     return _L.WordLossFn.apply(imgs, words, mask, labels, bool(b_global), float(rho1), float(rho2), float(rho3),
                                bool(normalize_values), precision, group, _ops or default_ops())
+
+
+def contrastive_losses(imgs=None, txts=None, real_imgs=None, fake_imgs=None, regions=None, words=None, mask=None,
+                       labels=None, b_global=False, *, tau=1.0, rho1=5.0, rho2=5.0, rho3=10.0, normalize_values=False,
+                       precision=None, group=None, _ops=None):
+    """``(sent_loss(imgs, txts), img_loss(real_imgs, fake_imgs), word_loss(regions, words, mask))`` of one training
+    step (``xmc_gan/train_gan.py:218/265, :278, :220-222/267-269``), evaluated together: same numbers as the three
+    calls, but with a process ``group`` the collectives are grouped (one all-gather of all column operands, one
+    statistics exchange, one reduce-scatter of the gradients) and the similarity losses run on side streams beside
+    the word-region kernels.  A pair left ``None`` is skipped and its loss is a constant 0."""
+    return _L.FusedLossesFn.apply(imgs, txts, real_imgs, fake_imgs, regions, words, mask, labels, bool(b_global),
+                                  float(tau), float(rho1), float(rho2), float(rho3), bool(normalize_values), precision,
+                                  group, _ops or default_ops())
 
 
 def magp_penalty(grads, *, power=6.0, weight=2.0, _ops=None):
