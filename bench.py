@@ -31,6 +31,12 @@ B_LOCAL, D_SENT, D_IMG, D_WORD, T_WORDS, R_SIDE = 256, 256, 512, 256, 18, 17
 RHO = (5.0, 5.0, 10.0)
 
 
+def workload_name(world):
+    """config.workload, the same string in both arms (the driver compares them)."""
+    return ("COCO-256 (BASELINE config %d): sent_loss D=256 + img_loss D=512 + word_loss T=18 R=289 D=256, "
+            "fwd+bwd, batch 256/GPU" % (2 if world == 1 else 3))
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -91,29 +97,69 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
 
 
-def oracle_step(inp, words_slice=None):
-    """All three losses fwd+bwd with the CPU oracle (float32, as the reference would run)."""
+def oracle_step(inp, cols=None):
+    """All three losses fwd+bwd with the CPU oracle (float32, as the reference would run).
+
+    inp: the ROW side (one rank's batch).  cols (N > 1): the column operands of the global batch — sentence / fake-image
+    embeddings, words and masks of all ranks, rank 0's first — so the step is rank 0's share of the sharded problem
+    (B rows x B_global columns, identity labels with offset 0).  -> (loss, [d img, d sent, d fake, d words, d regions])."""
     import oracle
     B = inp["sent"].shape[0]
-    labels = oracle.make_labels(B, inp["sent"], False)
     leaf = lambda x: x.clone().requires_grad_()
-    i_, s_, f_, w_, v_ = leaf(inp["img"]), leaf(inp["sent"]), leaf(inp["fake"]), leaf(inp["words"]), leaf(inp["regions"])
+    c = inp if cols is None else cols
+    Bk = c["sent"].shape[0]
+    labels = torch.zeros(B, Bk)
+    labels.diagonal().fill_(1.0)                              # make_labels(b_global=False) (train_gan.py:74), rank 0's rows
+    i_, s_, f_, w_, v_ = leaf(inp["img"]), leaf(c["sent"]), leaf(c["fake"]), leaf(c["words"]), leaf(inp["regions"])
     loss = (oracle.sent_loss(i_, s_, labels, False) + oracle.img_loss(inp["real"], f_, labels, False)
-            + oracle.word_loss(v_, w_, inp["mask"], labels, False, 0.5, *RHO, img_block=8))
+            + oracle.word_loss(v_, w_, c["mask"], labels, False, 0.5, *RHO, img_block=8))
     loss.backward()
-    return float(loss.detach())
+    return float(loss.detach()), [t.grad for t in (i_, s_, f_, w_, v_)]
 
 
-def time_oracle(steps, warmup, B):
+def oracle_inputs(B, world, precision):
+    """The GPU arm's own inputs (same seeds), rounded to bf16 when the GPU arm computes on bf16 operands:
+    BASELINE.md section 4 — both arms see bit-identical tensors."""
+    rd = (lambda v: v.bfloat16().float()) if precision == "bf16" else (lambda v: v)
+    ranks = [{k: (rd(v) if v.dtype.is_floating_point else v) for k, v in make_inputs(B, 1000 + r).items()} for r in range(world)]
+    cols = None if world == 1 else {k: torch.cat([x[k] for x in ranks]) for k in ("sent", "fake", "words", "mask")}
+    return ranks[0], cols
+
+
+def time_oracle(steps, warmup, B, world=1, precision="fp32"):
+    """-> (samples/s of the global batch, s per step, outputs of the first step).  With world > 1 one step is rank 0's
+    share (B rows x B*world columns), the same per-rank problem the GPU arm times."""
     torch.set_num_threads(os.cpu_count())
-    inp = make_inputs(B, 0)
+    inp, cols = oracle_inputs(B, world, precision)
+    first = None
     for _ in range(warmup):
-        oracle_step(inp)
+        out = oracle_step(inp, cols)
+        first = first or out
     t0 = time.perf_counter()
     for _ in range(steps):
-        oracle_step(inp)
+        out = oracle_step(inp, cols)
+        first = first or out
     dt = (time.perf_counter() - t0) / steps
-    return B / dt, dt
+    return B * world / dt, dt, first
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the newest committed `ncu --set full` summary
+    (profiles/rNN_ncu_wr_tc_summary.txt, written by profiles/ncu_summary.py) -> (bytes, file name) or (None, None)."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_wr_tc_summary.txt")), reverse=True):
+        block, total = False, {}
+        for line in open(path):
+            if line.startswith("-- "):
+                block = kernel in line
+            elif block:
+                m = re.match(r"\s+(dram__bytes_(?:read|write)\.sum)\s+([0-9.]+)\s+(\w+)", line)
+                if m:
+                    total[m.group(1)] = float(m.group(2)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(3)]
+        if len(total) == 2:
+            return sum(total.values()), os.path.relpath(path, ROOT)
+    return None, None
 
 
 def run_reference(args):
@@ -121,21 +167,80 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    sps, dt = time_oracle(steps, warmup, B_LOCAL)
+    world = max(1, args.gpus)
+    steps, warmup = max(1, min(args.steps, 3 if world == 1 else 1)), max(1, min(args.warmup, 1))
+    precision = args.precision or os.environ.get("XMC_BENCH_PRECISION", "bf16")
+    sps, dt, _ = time_oracle(steps, warmup, args.batch, world, precision)
     cores = os.cpu_count()
-    sample = (f"full COCO-256 batch (B=256, T=18, R=289, D=256; sent D=256, img D=512), fp32, "
+    sample = (f"rank 0's share of the COCO-256 step (B={args.batch} rows x {args.batch * world} columns, T=18, R=289, D=256; "
+              f"sent D=256, img D=512), fp32 arithmetic on the GPU arm's inputs, "
               f"{steps} timed + {warmup} warm-up fwd+bwd steps; reference functions restated "
               f"(train_gan.py:72-139) + this repo's word-loss restatement (reference has none)")
     line = {
         "impl": "reference", "metric": "contrastive-loss fwd+bwd samples/sec", "value": sps, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "COCO-256: sent_loss+img_loss+word_loss fwd+bwd, B=256 T=18 R=289 D=256, CPU"},
+        "config": {"workload": workload_name(world), "arithmetic": "CPU oracle, fp32",
+                   "global_batch": args.batch * world, "pairs_per_s": args.batch * args.batch * world / dt,
+                   "per_rank_problem": f"{args.batch} rows x {args.batch * world} columns"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    print(json.dumps(line), flush=True)
+
+
+def run_step_workload(args):
+    """--workload step (BASELINE config 4): the reference's G/D update (train_gan.py:187-289 as
+    xmc_gan_b200.step.gd_step) around DF-GAN-shaped networks at IMG.SIZE 256, NCH 32, NEF 256, IMG_MATCH, MA-GP on,
+    synthetic images / captions — once with the stock PyTorch loss block, once with this package's ops swapped in,
+    each with and without the word loss the reference leaves unimplemented.  One GPU; prints one JSON line."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import stock_losses
+    from dfgan_harness import NetD, NetG
+    from xmc_gan_b200 import step as S
+    from xmc_gan_b200 import train_gan as T
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, size, nch, nef, T_ = args.batch if args.batch != B_LOCAL else 64, 256, 32, 256, T_WORDS
+    torch.manual_seed(0)
+    G = NetG(size, nch, 100, nef, nef).to(dev)
+    D = NetD(size, nch, nef, img_match=True, spec_norm=True, region_res=16).to(dev)
+    optG = torch.optim.Adam(G.parameters(), 1e-4, betas=(0.0, 0.9))
+    optD = torch.optim.Adam(D.parameters(), 4e-4, betas=(0.0, 0.9))
+    g = torch.Generator().manual_seed(1)
+    imgs = (torch.rand(B, 3, size, size, generator=g) * 2 - 1).to(dev)
+    words = torch.randn(B, nef, T_, generator=g).to(dev)
+    sent = torch.randn(B, nef, generator=g).to(dev)
+    lens = torch.randint(5, T_ + 1, (B,), generator=g)
+    mask = (torch.arange(T_)[None] >= lens[:, None]).to(dev)
+    W, K = max(args.warmup, 3), args.steps
+    res = {}
+    for word in (False, True):
+        for name, ns, wkw in (("stock", stock_losses, None), ("xmc_gan_b200", T, {"precision": "bf16"})):
+            cfg = S.default_step_cfg()
+            cfg.TRAIN.ENCODER_LOSS.WORD = word
+            def one():
+                noise = torch.randn(B, 100, device=dev)
+                return S.gd_step(G, D, optG, optD, imgs, words, sent, mask, noise, cfg=cfg, losses=ns, word_kwargs=wkw)
+            for _ in range(W):
+                out = one()
+            torch.cuda.synchronize()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for _ in range(K):
+                out = one()
+            eb.record()
+            torch.cuda.synchronize()
+            res[("word" if word else "no_word", name)] = {"ms_per_step": ea.elapsed_time(eb) / K,
+                                                          "scalars": {k: float(v) for k, v in out.items()}}
+    line = {"workload": "G/D step (BASELINE config 4): DF-GAN-shaped netG/netD 256x256, NCH 32, NEF 256, IMG_MATCH, spectral norm, "
+                        "MA-GP, sent_loss + img_loss%s, batch %d, fp32 networks" % (" (+ word_loss T=18, R=16x16, bf16 tcgen05 path)", B),
+            "n_gpus": 1, "steps": K, "warmup": W, "unit": "ms/step", "higher_is_better": False, "data": "synthetic",
+            "sent+img": {n: res[("no_word", n)] for n in ("stock", "xmc_gan_b200")},
+            "sent+img+word": {n: res[("word", n)] for n in ("stock", "xmc_gan_b200")}}
+    for k in ("sent+img", "sent+img+word"):
+        line[k]["speedup"] = line[k]["stock"]["ms_per_step"] / line[k]["xmc_gan_b200"]["ms_per_step"]
     print(json.dumps(line), flush=True)
 
 
@@ -150,9 +255,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--one-stream", action="store_true", help="run the three losses back to back on one stream")
+    ap.add_argument("--fused", default=None, choices=["on", "off"],
+                    help="evaluate the three losses through train_gan.contrastive_losses (grouped collectives); default: on for N > 1")
+    ap.add_argument("--graph-multi", default="on", choices=["on", "off"], help="capture the N > 1 step as a CUDA graph as well")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run comparison with the CPU oracle / single-GPU run")
+    ap.add_argument("--sustain-s", type=float, default=1.5, help="seconds of back-to-back steps for the `sustained` block")
+    ap.add_argument("--workload", default="losses", choices=["losses", "step"],
+                    help="losses: the contract's metric (default); step: the G/D training step with the ops swapped in (config 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "step":
+        return run_step_workload(args)
 
     import torch.distributed as dist
     from xmc_gan_b200 import train_gan as T
@@ -164,7 +278,7 @@ def main():
     torch.cuda.set_device(local_rank)
     group = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # quiet by default (rank 0 prints ONE JSON line); a caller's setting wins
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         group = dist.group.WORLD
     dev = torch.device("cuda", local_rank)
@@ -183,27 +297,38 @@ def main():
     # The three losses are independent until they are summed: the two similarity losses run on side streams
     # (autograd replays each backward on its forward's stream), so their ~30 us kernels fill the tails of the
     # two big word-region kernels instead of queueing behind them.  One GPU only (NCCL order across ranks).
-    side = [torch.cuda.Stream(device=dev) for _ in range(2)] if (world == 1 and not args.one_stream) else None
+    fused = (args.fused == "on") if args.fused else world > 1
+    side = [torch.cuda.Stream(device=dev) for _ in range(2)] if (world == 1 and not args.one_stream and not fused) else None
+    ops.use_side_stream = not args.one_stream
 
-    def step(x, use_side=True):
+    def step(x, use_side=True, grp=group, nb=B):
         leaf = lambda t: t.detach().requires_grad_()
         i_, s_, f_, w_, v_ = leaf(x["img"]), leaf(x["sent"]), leaf(x["fake"]), leaf(x["words"]), leaf(x["regions"])
-        labels = T.make_labels(B, x["sent"], False, group=group)
+        labels = T.make_labels(nb, x["sent"], False, group=grp)
+        if fused:
+            # one autograd function for the three losses: grouped all-gather / packet exchange / reduce-scatter,
+            # similarity losses on side streams inside it
+            l_sent, l_img, l_word = T.contrastive_losses(i_, s_, x["real"], f_, v_, w_, x["mask"], labels, False,
+                                                         rho1=RHO[0], rho2=RHO[1], rho3=RHO[2], precision=precision, group=grp)
+            loss = l_sent + l_img + l_word
+            loss.backward()
+            return loss, (i_.grad, s_.grad, f_.grad, w_.grad, v_.grad)
         forked = side is not None and use_side
         if not forked:
-            l_sent = T.sent_loss(i_, s_, labels, False, group=group)
-            l_img = T.img_loss(x["real"], f_, labels, False, group=group)
+            l_sent = T.sent_loss(i_, s_, labels, False, group=grp)
+            l_img = T.img_loss(x["real"], f_, labels, False, group=grp)
         else:
             cur = torch.cuda.current_stream(dev)
             side[0].wait_stream(cur); side[1].wait_stream(cur)
             with torch.cuda.stream(side[0]):
-                l_sent = T.sent_loss(i_, s_, labels, False, group=group)
+                l_sent = T.sent_loss(i_, s_, labels, False, group=grp)
             with torch.cuda.stream(side[1]):
-                l_img = T.img_loss(x["real"], f_, labels, False, group=group)
+                l_img = T.img_loss(x["real"], f_, labels, False, group=grp)
         l_word = T.word_loss(v_, w_, x["mask"], labels, False, rho1=RHO[0], rho2=RHO[1], rho3=RHO[2],
-                             precision=precision, group=group)
+                             precision=precision, group=grp)
         if forked:
             cur.wait_stream(side[0]); cur.wait_stream(side[1])
+            l_sent.record_stream(cur); l_img.record_stream(cur)      # allocated on the side streams, consumed here
         loss = l_sent + l_img + l_word
         loss.backward()
         return loss, (i_.grad, s_.grad, f_.grad, w_.grad, v_.grad)
@@ -239,6 +364,41 @@ def main():
     # ---- per-kernel CUDA-event times (eager launches; feeds the roofline) --------------------
     for _ in range(W):
         step(devin)
+
+    # ---- parity of THIS run's numbers (both arms on identical tensors) -------------------
+    # N = 1: the step's loss and five gradients are kept and compared below with the CPU oracle run on the same inputs.
+    # N > 1: every rank's inputs are gathered, rank 0 evaluates the whole global batch on its own GPU (no group) and
+    # compares the sharded step's global loss and its own gradient rows with it (SURVEY section 4's definition).
+    nerr = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300))
+    parity, gpu_out = None, None
+    if not args.no_parity:
+        loss_g, grads_g = step(devin)
+        torch.cuda.synchronize()
+        gpu_out = (float(loss_g.detach()), [g.detach().float().cpu() for g in grads_g])
+        if world > 1:
+            from xmc_gan_b200 import losses as L_
+            full = {}
+            for k, v in devin.items():
+                u = v.to(torch.uint8) if v.dtype == torch.bool else v
+                out = torch.empty((world * u.shape[0],) + tuple(u.shape[1:]), device=dev, dtype=u.dtype)
+                dist.all_gather_into_tensor(out, u.contiguous(), group=group)
+                full[k] = out.bool() if v.dtype == torch.bool else out
+            if rank == 0:
+                keep = L_.MAX_CONTEXT_BYTES
+                L_.MAX_CONTEXT_BYTES = 1 << 40                      # a one-off check on a 180 GB device
+                try:
+                    loss_1, grads_1 = step(full, grp=None, nb=B * world)
+                    torch.cuda.synchronize()
+                    parity = {"against": "rank 0 alone on the gathered global batch (single-GPU path, same kernels, no group)",
+                              "loss_rel": abs(gpu_out[0] - float(loss_1.detach())) / abs(float(loss_1.detach())),
+                              "grad_nerr": [nerr(a, b[:B].float().cpu()) for a, b in zip(gpu_out[1], grads_1)],
+                              "order": ["d img", "d sent", "d fake", "d words", "d regions"], "rows": "rank 0's"}
+                finally:
+                    L_.MAX_CONTEXT_BYTES = keep
+                del loss_1, grads_1
+            del full
+            torch.cuda.empty_cache()
+            dist.barrier(group)
     l0 = ops.launches
     ops.enable_timing(True)
     timed(lambda: step(devin, use_side=False), K)            # one stream: clean per-kernel event pairs
@@ -268,15 +428,16 @@ def main():
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # N > 1: NCCL's watchdog thread polls events while this thread captures; only this thread's calls belong to the capture
+        with torch.cuda.graph(g, **({"capture_error_mode": "thread_local"} if world > 1 else {})):
             loss, grads = step(x_static)
         return g, loss, grads
 
     graphs = None
     mode = "eager"
-    # Single GPU only: with N > 1 the per-rank work doubles with N while the host time stays, so eager launches
-    # are GPU-bound there (and a 2-rank capture with the NCCL collectives inside hung in a replay on this pool).
-    if not args.no_graph and world == 1:
+    # N > 1: the NCCL collectives are captured with the kernels (every rank captures and replays the same sequence);
+    # whether the capture succeeded is agreed on by all ranks before anyone replays.
+    if not args.no_graph and (world == 1 or args.graph_multi == "on"):
         try:
             sets = [devin, {k: v.clone() for k, v in devin.items()}]
             graphs = [capture(x) for x in sets]
@@ -295,6 +456,11 @@ def main():
             print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
             graphs = None
             torch.cuda.synchronize()
+        if world > 1:
+            okf = torch.tensor([1.0 if graphs is not None else 0.0], device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN, group=group)
+            if float(okf) == 0.0:
+                graphs, mode = None, "eager"
 
     # ---- device-resident throughput ---------------------------------------------------------
     # Clocks are sampled by rank 0 only, for its own GPU: one nvidia-smi per rank every 100 ms takes the
@@ -309,6 +475,43 @@ def main():
     else:
         ms = timed(lambda: step(devin), K)
     clocks = sampler.summary() if sampler is not None else None
+
+    # ---- sustained: back-to-back steps for >= --sustain-s seconds (no L2 flush, no per-step events) ----------------
+    # The contract's K timed steps are a ~20 ms burst on a cold-ish GPU; this is the number after the clocks and the
+    # power limiter have settled, with the median SM clock sampled over the same window.
+    sustained = None
+    if args.sustain_s > 0:
+        run1 = graphs[0][0].replay if graphs is not None else (lambda: step(devin))
+        n_sus = max(K, int(args.sustain_s * 1e3 / max(ms, 1e-3)) + 1)
+        if world > 1:                                           # every rank must run the same number of steps
+            tn = torch.tensor([n_sus], device=dev)
+            dist.all_reduce(tn, op=dist.ReduceOp.MAX, group=group)
+            n_sus = int(tn)
+        sampler2 = ClockSampler(local_rank) if rank == 0 else None
+        barrier()
+        if sampler2 is not None:
+            sampler2.start()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        last = None
+        for i in range(n_sus):
+            run1()
+            if graphs is None and i % 2 == 1:                   # eager loop: keep the host at most ~2 steps ahead
+                if last is not None:
+                    last.synchronize()
+                last = torch.cuda.Event()
+                last.record()
+        eb.record()
+        barrier()
+        ms_sus = ea.elapsed_time(eb) / n_sus
+        if world > 1:
+            t = torch.tensor([ms_sus], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            ms_sus = float(t)
+        c2 = sampler2.summary() if sampler2 is not None else None
+        sustained = {"ms_per_step": ms_sus, "value": B * world / (ms_sus * 1e-3), "steps": n_sus,
+                     "seconds": ms_sus * n_sus * 1e-3, "sm_mhz_median": c2["sm_mhz"] if c2 else None,
+                     "reasons": c2["reasons"] if c2 else None, "l2": "not flushed between steps"}
 
     # ---- end to end: pinned host -> device, loss -> host -------------------------------------
     # Every step copies ITS inputs from pinned host memory (copy stream, issued one step ahead into the other
@@ -411,12 +614,14 @@ def main():
     n_bwd, ms_bwd = kern.get("wordregion_bwd", (0, float("nan")))
     n_fwd, ms_fwd = kern.get("wordregion_fwd", (0, float("nan")))
     ach = flops_bwd / (ms_bwd * 1e-3) / 1e12
+    traffic, traffic_src = ncu_traffic("wr_bwd_tc_kernel")
     roofline = {
         "kernel": "wr_bwd_tc_kernel (word-region backward, %s path)" % ("tcgen05 bf16" if precision == "bf16" else "fp32 SIMT"),
         "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the `ncu --set full` capture of this very
-        # workload (profiles/r01_ncu_wr_tc_summary.txt: 534.1 MB + 74.6 MB); only valid for the default 1-GPU bf16 run
-        "traffic": 6.087e8 if (precision == "bf16" and world == 1 and B == B_LOCAL) else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, read from the newest committed `ncu --set full`
+        # summary of this very workload (not measured in this run); only valid for the default 1-GPU bf16 run
+        "traffic": traffic if (precision == "bf16" and world == 1 and B == B_LOCAL) else None,
+        "traffic_source": traffic_src if (precision == "bf16" and world == 1 and B == B_LOCAL) else None,
         "peak_source": pk["src"] + ", bf16 sustained",
         "algorithmic_flops_per_launch": flops_bwd, "ms_per_launch": ms_bwd, "launches_timed": n_bwd,
         "word_rows": {"valid": words_valid, "padded_T": float(Bg * T_WORDS),
@@ -437,13 +642,14 @@ def main():
         "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
         "config": {
-            "workload": ("COCO-256 (BASELINE config %d): sent_loss D=256 + img_loss D=512 + word_loss T=18 R=289 D=256, "
-                         "fwd+bwd, batch 256/GPU, %s" % (2 if world == 1 else 3,
-                                                       "bf16-in/fp32-accumulate" if precision == "bf16" else "fp32")),
+            "workload": workload_name(world),
+            "arithmetic": "bf16-in/fp32-accumulate" if precision == "bf16" else "fp32",
             "global_batch": Bg, "pairs_per_s": B * Bg * world / (ms * 1e-3), "rho": RHO,
             "parallelism": "single GPU" if world == 1 else f"rows local, columns all-gathered over NCCL x{world}",
             "l2": "256 MiB buffer written between timed steps (untimed) to flush the 126 MB L2",
-            "launch": mode, "streams": 1 if side is None else 3, "eager_ms_per_step": ms_eager, "host_enqueue_ms_per_step": host_ms,
+            "launch": mode, "streams": 1 if (side is None and not fused) or args.one_stream else 3 + int(fused),
+            "api": ("train_gan.contrastive_losses (the three losses through one autograd function, grouped collectives)" if fused
+                    else "train_gan.sent_loss / img_loss / word_loss (the reference's call sites)"), "eager_ms_per_step": ms_eager, "host_enqueue_ms_per_step": host_ms,
             "scaling_note": "global negatives: per-rank work grows with the global batch (rows local, columns "
                             "gathered), so samples/s stays flat with N while pairs/s grows ~N",
         },
@@ -455,13 +661,24 @@ def main():
                        "every step and read by the host one step late" % mode},
         "gpu_launches": launches,
         "roofline": roofline,
+        "sustained": sustained,
     }
     if world == 1 and not args.no_cpu_baseline:
-        sps, dt = time_oracle(2, 1, B)
+        sps, dt, first = time_oracle(2, 1, B, 1, precision)
         line["cpu_baseline"] = {
             "value": sps, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "full COCO-256 batch, 2 timed + 1 warm-up fwd+bwd steps of the CPU oracle (fp32, all host threads)",
+            "sample": "the GPU arm's own COCO-256 batch (same seed%s), 2 timed + 1 warm-up fwd+bwd steps of the CPU oracle "
+                      "(fp32 arithmetic, all host threads)" % (", rounded to bf16 as the kernels see it" if precision == "bf16" else ""),
             "ms_per_step": dt * 1e3}
+        if gpu_out is not None:
+            parity = {"against": "CPU oracle (oracle/ref_losses.py + oracle/word_region.py) on identical inputs",
+                      "loss_rel": abs(gpu_out[0] - first[0]) / abs(first[0]),
+                      "grad_nerr": [nerr(a, b) for a, b in zip(gpu_out[1], first[1])],
+                      "order": ["d img", "d sent", "d fake", "d words", "d regions"]}
+    if parity is not None:
+        parity["tol"] = 2e-2 if precision == "bf16" else 1e-4
+        parity["ok"] = bool(parity["loss_rel"] <= parity["tol"] and max(parity["grad_nerr"]) <= parity["tol"])
+        line["parity"] = parity
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
