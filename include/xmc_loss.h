@@ -202,10 +202,11 @@ size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad,
  * (= sum_r exp(rho1*(s_qr - 1)) v_r), saved for the backward pass when gradients are needed (the
  * fp32 path recomputes them and ignores it).
  * Rpad must be a multiple of 16 and >= R.
- * nq_dev (tcgen05 path, nullable): DEVICE pointer to the number of valid word rows (<= NQ, e.g.
+ * nq_dev (nullable): DEVICE pointer to the number of valid word rows (<= NQ, e.g.
  * &cap_ptr[Bc] of xmc_word_rows_compact); NQ stays the row stride of every [Bi, NQ] buffer and
  * rows at or beyond *nq_dev are neither read nor written.  The kernels size their own schedule
- * from it (one persistent CTA per SM), so no host synchronisation is needed. */
+ * from it (tcgen05 path: one persistent CTA per SM; fp32 path: tiles past the count exit), so no host
+ * synchronisation is needed. */
 int xmc_wordregion_forward(int path, const void* qn, const void* kn, const float* rnorm,
                            int NQ, int Bi, int R, int Rpad, int D, float rho1,
                            float* lsum, float* cnorm, float* rel, void* chat, const int* nq_dev,

@@ -72,15 +72,16 @@ def _worker(rank, port, b_global, smooth, precision, Dw, out, fused=False):
                 + T.word_loss(regions, words, d["mask"][sl], labels, b_global, rho1=4.0, rho2=5.0, rho3=6.0,
                               precision=precision, group=group, _ops=ops))
         loss.backward()
-        assert ops.compactions == (1 if precision == "bf16" else 0)
+        assert ops.compactions == 1          # padding words are compacted away on both paths
         out[rank] = dict(loss=loss.detach(), labels=labels.detach().clone(),
                          grads=[t.grad.clone() for t in (img, sent, words, regions)])
     finally:
         dist.destroy_process_group()
 
 
-# precision "bf16" selects the tcgen05-path host flow (padding words compacted away, device-side row
-# count, gradients scattered back through row_of); the checker backend still computes in fp64.
+# precision "bf16" selects the tcgen05-path host flow (saved contexts, pre-filled accumulators); both paths
+# compact the padding words away (device-side row count, gradients scattered back through row_of).  The
+# checker backend computes in fp64 either way.
 @pytest.mark.parametrize("b_global,smooth,precision,Dw", [(False, 0.5, None, 8), (True, 0.5, None, 8), (True, 0.0, None, 8),
                                                           (True, 0.5, "bf16", 128), (False, 0.5, "bf16", 128)])
 def test_two_rank_global_negatives_match_single_process_oracle(b_global, smooth, precision, Dw):

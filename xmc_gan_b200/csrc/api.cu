@@ -66,7 +66,6 @@ extern "C" int xmc_wordregion_forward(int path, const void* qn, const void* kn, 
   p.qn = static_cast<const float*>(qn); p.kn = static_cast<const float*>(kn); p.rnorm = rnorm;
   p.NQ = NQ; p.Bi = Bi; p.R = R; p.Rpad = Rpad; p.rho1 = rho1;
   p.lsum = lsum; p.cnorm = cnorm; p.rel = rel; p.chat = chat; p.nq_dev = nq_dev;
-  XMC_REQUIRE(!nq_dev || path == XMC_PATH_BF16_TCGEN05, XMC_ERR_UNSUPPORTED, "nq_dev (compacted word rows) is a tcgen05-path option");
   XMC_REQUIRE(!chat || aligned16(chat), XMC_ERR_ALIGNMENT, "chat must be 16-byte aligned");
   if (path == XMC_PATH_FP32_SIMT) return wordregion_f32_forward(p, D, as_stream(stream));
   return wordregion_tc_forward(p, D, workspace, workspace_bytes, as_stream(stream));
@@ -86,7 +85,6 @@ extern "C" int xmc_wordregion_backward(int path, const void* qn, const void* kn,
   p.NQ = NQ; p.Bi = Bi; p.R = R; p.Rpad = Rpad; p.rho1 = rho1;
   p.lsum = const_cast<float*>(lsum); p.cnorm = const_cast<float*>(cnorm); p.rel = const_cast<float*>(rel);
   p.grel = grel; p.dqn = dqn; p.dkn = dkn; p.drnorm = drnorm; p.chat = const_cast<void*>(chat); p.nq_dev = nq_dev;
-  XMC_REQUIRE(!nq_dev || path == XMC_PATH_BF16_TCGEN05, XMC_ERR_UNSUPPORTED, "nq_dev (compacted word rows) is a tcgen05-path option");
   if (path == XMC_PATH_FP32_SIMT) return wordregion_f32_backward(p, D, as_stream(stream));
   return wordregion_tc_backward(p, D, workspace, workspace_bytes, as_stream(stream));
 }

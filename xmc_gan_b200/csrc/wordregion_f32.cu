@@ -127,9 +127,16 @@ __device__ __forceinline__ void context_pass(const WrParams& p, const float* __r
   }
 }
 
+// Compacted word rows: the number of valid rows lives on the device (nq_dev); NQ stays the row stride of the
+// [Bi, NQ] statistics.  Tiles that start past the count have nothing to do.
+__device__ __forceinline__ int valid_rows(const WrParams& p) { return p.nq_dev ? min(p.NQ, __ldg(p.nq_dev)) : p.NQ; }
+
 template <int D>
 __global__ void __launch_bounds__(256) wr_fwd_f32_kernel(WrParams p) {
   extern __shared__ __align__(16) float smem[];
+  const int NQs = p.NQ;                 // row stride of lsum / cnorm / rel
+  p.NQ = valid_rows(p);                 // rows at or past the count are neither read nor written
+  if ((int)blockIdx.x * BM >= p.NQ) return;
   float* As = smem;
   float* Bs1 = As + KB * LDA;
   float* Ps = Bs1 + KB * LDA;
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(256) wr_fwd_f32_kernel(WrParams p) {
     const int row = m0 + ty * 4 + i;
     if (tx == 0 && row < p.NQ) {
       const float cn = sqrtf(c2) / l;
-      const size_t o = (size_t)img * p.NQ + row;
+      const size_t o = (size_t)img * NQs + row;
       p.lsum[o] = l;
       p.cnorm[o] = cn;
       p.rel[o] = (a / l) / fmaxf(cn, kEps);
@@ -172,6 +179,9 @@ template <int D>
 __global__ void __launch_bounds__(256, 1) wr_bwd_f32_kernel(WrParams p) {
   constexpr int LDC = D + 4;
   extern __shared__ __align__(16) float smem[];
+  const int NQs = p.NQ;
+  p.NQ = valid_rows(p);
+  if ((int)blockIdx.x * BM >= p.NQ) return;
   float* As = smem;
   float* Bs1 = As + KB * LDA;
   float* Xs = Bs1 + KB * LDA;      // [r][t]  (k = r for dQ = X Khat)        also P in pass 1
@@ -202,7 +212,7 @@ __global__ void __launch_bounds__(256, 1) wr_bwd_f32_kernel(WrParams p) {
       const int row = m0 + ty * 4 + i;
       float l = 1.f, b = 1.f, rl = 0.f, g = 0.f;
       if (row < p.NQ) {
-        const size_t o = (size_t)img * p.NQ + row;
+        const size_t o = (size_t)img * NQs + row;
         l = p.lsum[o]; b = fmaxf(p.cnorm[o], kEps); rl = p.rel[o]; g = p.grel[o];
       }
       inv_l[i] = 1.f / l; gam[i] = g / b; relv[i] = rl;
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(256, 1) wr_bwd_f32_kernel(WrParams p) {
         const int row = m0 + ty * 4 + i;
         float cs = 0.f;
         if (row < p.NQ) {
-          const size_t o = (size_t)img * p.NQ + row;
+          const size_t o = (size_t)img * NQs + row;
           cs = inv_l[i] / fmaxf(p.cnorm[o], kEps);
         }
 #pragma unroll

@@ -327,10 +327,11 @@ def _word_local(ops, comm, prep, regions, w_all, m_all, labels, b_global, rho1, 
     Bc, _, T = w_all.shape
     path = _lib.PATH_FP32_SIMT if precision == "fp32" else _lib.PATH_BF16_TCGEN05
     use_tc_bwd = path == _lib.PATH_BF16_TCGEN05 and D in TC_BACKWARD_DIMS
-    # Padding words never contribute (excluded from the log-sum-exp, zero gradient): on the tcgen05
-    # path the kernels visit only the valid word rows, compacted in caption-major order.  Their
-    # number stays on the device (cap_ptr[Bc]); nothing here synchronises with the host.
-    compact = (m_all is not None and path == _lib.PATH_BF16_TCGEN05 and (use_tc_bwd or not need_grad)
+    # Padding words never contribute (excluded from the log-sum-exp, zero gradient): the kernels visit
+    # only the valid word rows, compacted in caption-major order.  Their number stays on the device
+    # (cap_ptr[Bc]); nothing here synchronises with the host.  (Not with the tcgen05 forward followed by
+    # the fp32 backward — D outside the tensor-core backward's set —: that pair shares dense rows.)
+    compact = (m_all is not None and (path == _lib.PATH_FP32_SIMT or use_tc_bwd or not need_grad)
                and getattr(ops, "supports_compaction", False))
     save_ctx = need_grad and use_tc_bwd
     if save_ctx and Bi * Bc * T * D * 2 > MAX_CONTEXT_BYTES:
