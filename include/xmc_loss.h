@@ -82,7 +82,10 @@ int xmc_cosine_scores_backward(const void* a, const void* b, int Bq, int Bk, int
 /* Fused forward of sent_loss / img_loss up to the statistics — train_gan.py:93-111 / 117-135:
  * L2-normalise, cosine matrix, scale (=1/tau; the reference has no temperature: 1.0),
  * log-sum-exp over rows and over columns and the label-weighted sums, ONE kernel.
- * Writes scores[Bq,Bk] (kept for backward), inv norms and both statistics blocks. */
+ * Writes scores[Bq,Bk] (kept for backward), inv norms and both statistics blocks.
+ * Large rectangular problems (Bq*Bk >= 256*512, D a multiple of 128, Bk of 8: the sharded global-negative case,
+ * 256 x 2048) take tcgen05 score tiles — fp32 operands split into two bf16 numbers, three MMAs per product,
+ * fp32 accumulation: same 1e-4 tolerance — followed by one statistics pass; small ones the one-kernel form. */
 int xmc_simloss_forward(const void* a, const void* b, int Bq, int Bk, int D, int dtype,
                         const float* labels, int diag_offset, float scale,
                         float* scores, float* inv_norm_a, float* inv_norm_b,
@@ -134,14 +137,18 @@ int xmc_infonce_grad(const float* scores, int Bq, int Bk, const float* labels, i
 
 /* Fused backward of sent_loss / img_loss: d scores on the fly, dA = dS * Bhat, dB = dS^T * Ahat
  * and the backward of F.normalize, ONE kernel.  da / db may be NULL (img_loss only needs db,
- * train_gan.py:271-278; the D step only needs da, :194,218).  Outputs have dtype `dtype`. */
+ * train_gan.py:271-278; the D step only needs da, :194,218).  Outputs have dtype `dtype`.
+ * workspace (nullable): xmc_simloss_workspace_bytes(Bq, Bk, D) bytes of scratch.  When given and non-empty the
+ * large-problem tensor-core form runs (dS blocks staged once, two tcgen05 products per block, fp32 reduction in
+ * the workspace, one normalise-backward pass); without it the one-kernel CUDA-core form runs at any size. */
+size_t xmc_simloss_workspace_bytes(int Bq, int Bk, int D);
 int xmc_simloss_backward(const void* a, const void* b, int Bq, int Bk, int D, int dtype,
                          const float* scores, const float* inv_norm_a, const float* inv_norm_b,
                          const float* labels, int diag_offset, float scale,
                          const float* row_stats, const float* col_stats,
                          const float* row_div, const float* col_div, float num_pos,
                          int rows_total, int cols_total, const float* grad_out,
-                         void* da, void* db, void* stream);
+                         void* da, void* db, void* workspace, size_t workspace_bytes, void* stream);
 
 /* make_labels soft-positive path — train_gan.py:72-83.  sim[B,B] is cosine_scores(sent, sent).
  * smooth_global != 0: weight = smooth_global; == 0: weight_j = 1/(max(count_j,1)+1) (:79-81),

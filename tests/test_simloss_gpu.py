@@ -175,3 +175,52 @@ def test_full_size_properties(T):
     ar = a.clone().requires_grad_()
     T.sent_loss(ar, b, lab, False).backward()
     assert float((ar.grad * ar.detach()).sum(1).abs().max()) < 1e-5   # grad orthogonal to the row (normalise)
+
+
+# ---- large rectangular problems: the tcgen05 form (simloss_tc.cu) -------------------------------------------------
+@pytest.mark.parametrize("Bq,Bk,D", [(256, 2048, 256), (256, 2048, 512), (200, 712, 256), (128, 1024, 768), (130, 1032, 128)])
+@pytest.mark.parametrize("dt,tol", [(torch.float32, TOL_FP32), (torch.bfloat16, TOL_BF16)])
+@pytest.mark.parametrize("dense", [False, True])
+def test_large_rectangular_tensor_core_path_vs_oracle(T, Bq, Bk, D, dt, tol, dense):
+    """Rank-shaped problem (local rows x gathered columns, identity labels with a diagonal offset or dense soft
+    labels): split-bf16 tcgen05 tiles must stay inside the fp32 tolerance; ragged tiles, D up to 768."""
+    from xmc_gan_b200 import _lib
+    from xmc_gan_b200.ops import default_ops
+    ops = default_ops()
+    assert _lib.lib().xmc_simloss_workspace_bytes(Bq, Bk, D) > 0, "shape must take the tensor-core form"
+    g = torch.Generator().manual_seed(Bq + Bk + D)
+    a = torch.randn(Bq, D, generator=g).to(dt)
+    b = (torch.randn(Bk, D, generator=g) + 0.4 * a.float()[torch.randint(0, Bq, (Bk,), generator=g)]).to(dt)
+    diag = 64 if Bk >= Bq + 64 else 0
+    lab_o = torch.zeros(Bq, Bk)
+    lab_o[torch.arange(Bq), torch.arange(Bq) + diag] = 1.0
+    if dense:
+        extra = torch.rand(Bq, Bk, generator=g) < 0.002
+        lab_o = (lab_o + 0.3 * extra.float()).clamp(max=1.0)
+    labels = lab_o.cuda() if dense else None
+    scale = 2.0
+    go = torch.tensor(1.7, device="cuda")
+    ac, bc = a.cuda(), b.cuda()
+    scores, inv_a, inv_b, row_stats, col_stats = ops.simloss_forward(ac, bc, labels, diag, scale)
+    loss3 = ops.infonce_loss(row_stats, col_stats, None, None, 1.0, Bq, Bk, 0, Bk)
+    da, db = ops.simloss_backward(ac, bc, scores, inv_a, inv_b, labels, diag, scale, row_stats, col_stats, None, None, 1.0,
+                                  Bq, Bk, go, True, True)
+    ar, br = a.double().requires_grad_(), b.double().requires_grad_()
+    so = oracle.cosine_scores(ar, br)
+    lo = oracle.infonce_tail(scale * so, lab_o.double(), 1)
+    (1.7 * lo).backward()
+    assert nerr(scores, so) <= 2e-6 if dt == torch.float32 else 1e-5          # fp32 inputs: split-bf16 product
+    assert lerr(loss3[0], lo.detach()) <= tol
+    assert nerr(da, ar.grad) <= tol and nerr(db, br.grad) <= tol
+    assert da.dtype == dt and db.dtype == dt
+    # one-sided gradients (img_loss: only db; D step: only da) and the CUDA-core form on the same problem
+    _, db1 = ops.simloss_backward(ac, bc, scores, inv_a, inv_b, labels, diag, scale, row_stats, col_stats, None, None, 1.0,
+                                  Bq, Bk, go, False, True)
+    assert nerr(db1, br.grad) <= tol
+    ops.use_sim_tc = False
+    try:
+        da0, db0 = ops.simloss_backward(ac, bc, scores, inv_a, inv_b, labels, diag, scale, row_stats, col_stats, None, None,
+                                        1.0, Bq, Bk, go, True, True)
+    finally:
+        ops.use_sim_tc = True
+    assert nerr(da, da0) <= tol and nerr(db, db0) <= tol

@@ -47,7 +47,8 @@ SIGNATURES = {
     "xmc_infonce_loss": (_i, [_vp, _vp, _i, _i, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "xmc_infonce_grad": (_i, [_vp, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),
     "xmc_simloss_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp,
-                                  _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp]),
+                                  _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xmc_simloss_workspace_bytes": (_sz, [_i, _i, _i]),
     "xmc_make_labels": (_i, [_vp, _i, _f, _f, _vp, _vp, _vp, _vp]),
     "xmc_word_rows_compact": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "xmc_normalize_transpose": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -12,29 +12,9 @@
 // the same ownership: d scores in closed form on the fly, rank-1 updates into register
 // accumulators, normalise-backward in the epilogue.
 #include "common.cuh"
+#include "simloss.cuh"
 
 namespace xmc {
-
-// Label of (row i, col j): explicit matrix or identity with column offset.
-__device__ __forceinline__ float label_at(const float* labels, int Bk, int i, int j, int diag) {
-  return labels ? __ldg(labels + (size_t)i * Bk + j) : (j == i + diag ? 1.f : 0.f);
-}
-
-struct SimParams {
-  const void* a; const void* b;
-  int Bq, Bk, D;
-  const float* labels; int diag; float scale;
-  float* scores; float* inv_a; float* inv_b;
-  float* row_stats; float* col_stats;
-  int n_row_blocks;
-  // backward only
-  const float* row_div; const float* col_div; float num_pos;
-  float inv_rows_total, inv_cols_total;
-  const float* grad_out;
-  void* da; void* db;
-  int n_a_blocks;
-  const float* ds_given;   // cosine_scores backward: d loss / d scores comes from the caller instead of the closed form
-};
 
 constexpr int kSimThreads = 256;
 constexpr int kSimWarps = kSimThreads / 32;
@@ -142,13 +122,6 @@ __global__ void __launch_bounds__(kSimThreads) sim_fwd_kernel(SimParams p) {
     out[NX + k] = t.sl;
     out[2 * NX + k] = t.slz;
   }
-}
-
-// d loss / d score(i,j) without the grad_out*scale factor.
-__device__ __forceinline__ float dscore(float z, float lab, float row_lse, float row_sl, float inv_nr,
-                                        float col_lse, float col_sl, float inv_nc) {
-  float pr = __expf(z - row_lse), pc = __expf(z - col_lse);
-  return (pc * col_sl - lab) * inv_nc + (pr * row_sl - lab) * inv_nr;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -615,6 +588,7 @@ extern "C" int xmc_cosine_scores(const void* a, const void* b, int Bq, int Bk, i
   SimParams p{};
   p.a = a; p.b = b; p.Bq = Bq; p.Bk = Bk; p.D = D;
   p.scores = scores; p.inv_a = inv_norm_a; p.inv_b = inv_norm_b;
+  if (sim_tc_eligible(Bq, Bk, D)) return sim_tc_forward(p, dtype, as_stream(stream));
   return sim_dispatch(2, p, dtype, as_stream(stream));
 }
 
@@ -641,6 +615,12 @@ extern "C" int xmc_simloss_forward(const void* a, const void* b, int Bq, int Bk,
   p.labels = labels; p.diag = diag_offset; p.scale = scale;
   p.scores = scores; p.inv_a = inv_norm_a; p.inv_b = inv_norm_b;
   p.row_stats = row_stats; p.col_stats = col_stats;
+  if (sim_tc_eligible(Bq, Bk, D)) {
+    // large rectangular problem (global negatives): score tiles on the tensor cores, then one pass over the scores
+    // for both directions' statistics (the kernel the word-region scores use)
+    if (int rc = sim_tc_forward(p, dtype, as_stream(stream))) return rc;
+    return xmc_infonce_stats(scores, Bq, Bk, labels, diag_offset, scale, row_stats, col_stats, stream);
+  }
   return sim_dispatch(0, p, dtype, as_stream(stream));
 }
 
@@ -650,7 +630,7 @@ extern "C" int xmc_simloss_backward(const void* a, const void* b, int Bq, int Bk
                                     const float* row_stats, const float* col_stats,
                                     const float* row_div, const float* col_div, float num_pos,
                                     int rows_total, int cols_total, const float* grad_out,
-                                    void* da, void* db, void* stream) {
+                                    void* da, void* db, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_sim_args(a, b, Bq, Bk, D, dtype)) return rc;
   XMC_REQUIRE(scores && inv_norm_a && inv_norm_b && row_stats && col_stats && grad_out,
               XMC_ERR_INVALID_ARG, "null saved-state pointer");
@@ -665,8 +645,11 @@ extern "C" int xmc_simloss_backward(const void* a, const void* b, int Bq, int Bk
   p.row_div = row_div; p.col_div = col_div; p.num_pos = num_pos;
   p.inv_rows_total = 1.f / rows_total; p.inv_cols_total = 1.f / cols_total;
   p.grad_out = grad_out; p.da = da; p.db = db;
+  if (workspace && sim_tc_eligible(Bq, Bk, D)) return sim_tc_backward(p, dtype, workspace, workspace_bytes, as_stream(stream));
   return sim_dispatch(1, p, dtype, as_stream(stream));
 }
+
+extern "C" size_t xmc_simloss_workspace_bytes(int Bq, int Bk, int D) { return sim_tc_workspace_bytes(Bq, Bk, D); }
 
 static int check_tail(const float* scores, int Bq, int Bk) {
   XMC_REQUIRE(scores, XMC_ERR_INVALID_ARG, "null scores");

@@ -182,12 +182,14 @@ class CudaOps:
         db = torch.empty_like(b) if need_b else None
         if not (need_a or need_b):
             return None, None
+        nws = self.L.xmc_simloss_workspace_bytes(Bq, Bk, D) if self.use_sim_tc else 0    # > 0: large problem, tensor-core form
+        ws = torch.empty(nws, device=a.device, dtype=torch.uint8) if nws else None
         with _on(a), self._timed("simloss_bwd"):
             self._check(self.L.xmc_simloss_backward(
                 _p(a), _p(b), Bq, Bk, D, _dt(a), _p(scores), _p(inv_a), _p(inv_b), _p(labels), diag, scale,
                 _p(row_stats), _p(col_stats), _p(row_div), _p(col_div), float(num_pos), rows_total, cols_total,
-                _p(grad_out), _p(da), _p(db), _stream()))
-        self.launches += 1
+                _p(grad_out), _p(da), _p(db), _p(ws), nws, _stream()))
+        self.launches += 1 + (3 if nws else 0)
         return da, db
 
     # -- InfoNCE tail over a given score matrix -----------------------------------------------
@@ -297,6 +299,7 @@ class CudaOps:
         return d0, d1
 
     # -- word-region --------------------------------------------------------------------------
+    use_sim_tc = True              # similarity-loss backward: hand the library a workspace (tensor-core form for large problems)
     supports_compaction = True     # the tcgen05 kernels visit only the non-padding word rows
     use_side_stream = True         # word-side prologue / zero fills / word epilogue beside the main stream
 
