@@ -197,6 +197,16 @@ int xmc_normalize_transpose_backward(const void* xn, const float* norm, const fl
                                      int xn_dtype, int out_dtype, const int* row_of,
                                      const int* error_word, void* dx, void* stream);
 
+/* The same pair for rows that already are rows (the producer emits the kernels' layout):
+ * x[B, L, D] with D contiguous — a channels-last feature map, i.e. what a 1x1 region head run as a GEMM on the
+ * discriminator's [B, C, 16, 16] stage (df_gan.py:106-132) writes — -> xn[B, Lpad, D] unit rows + norm[B, Lpad].
+ * No transpose, one pass at HBM speed; dx[B, L, D] comes back in the same layout.  D must be a multiple of 4 and <= 1024. */
+int xmc_normalize_rows(const void* x, int B, int D, int L, int Lpad, int in_dtype, int out_dtype,
+                       void* xn, float* norm, void* stream);
+int xmc_normalize_rows_backward(const void* xn, const float* norm, const float* dxn, const float* dnorm,
+                                int B, int D, int L, int Lpad, int xn_dtype, int out_dtype,
+                                const int* error_word, void* dx, void* stream);
+
 size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad, int D);
 
 /* qn[NQ,D]: unit word rows (NQ = Bc*T); kn[Bi,Rpad,D]: unit region rows; rnorm[Bi,Rpad]: region

@@ -171,6 +171,12 @@ class CpuOps:
             dx = dx + dnorm[:, :L, None] * xh
         return dx.transpose(1, 2).contiguous()
 
+    def normalize_rows(self, x, Lpad, out_dtype):
+        return self.normalize_transpose(x.transpose(1, 2), Lpad, out_dtype)
+
+    def normalize_rows_backward(self, xn, norm, dxn, dnorm, L, out_dtype, error_word=None):
+        return self.normalize_transpose_backward(xn, norm, dxn, dnorm, L, out_dtype).transpose(1, 2).contiguous()
+
     @staticmethod
     def _wr(qn, kn, rnorm, R, rho1):
         s = torch.einsum('qd,ird->iqr', qn, kn[:, :R])

@@ -168,3 +168,35 @@ def test_identity_tag_does_not_survive_an_edit():
     assert not L._is_identity(lab, (4, 8))
     lab[0, 1] = 0.5
     assert not L._is_identity(lab, (4, 4))
+
+
+def test_channels_last_regions_take_the_row_layout_path():
+    """SURVEY §8f N2 host logic: a channels-last region map is consumed as [B, R, D] rows (no transposing layout
+    kernels) and its gradient comes back channels-last; same numbers as the contiguous map."""
+    import oracle
+    sys.path.insert(0, HERE)
+    from cpu_ops import CpuOps
+    from xmc_gan_b200 import train_gan as T
+
+    class Counting(CpuOps):
+        rows = 0
+
+        def normalize_rows(self, *a, **k):
+            self.rows += 1
+            return super().normalize_rows(*a, **k)
+
+    g = torch.Generator().manual_seed(4)
+    B, D, H, W, T_ = 5, 8, 3, 4, 6
+    reg = torch.randn(B, D, H, W, generator=g, dtype=torch.float64)
+    words = torch.randn(B, D, T_, generator=g, dtype=torch.float64)
+    mask = torch.arange(T_)[None] >= torch.randint(1, T_ + 1, (B, 1), generator=g)
+    ops = Counting()
+    r_cl = reg.clone().contiguous(memory_format=torch.channels_last).requires_grad_()
+    loss = T.word_loss(r_cl, words, mask, T.make_labels(B, None, False, device=torch.device("cpu"), _ops=ops), False, _ops=ops)
+    loss.backward()
+    assert ops.rows == 1 and r_cl.grad.is_contiguous(memory_format=torch.channels_last)
+    r_ref = reg.clone().requires_grad_()
+    lo = oracle.word_loss(r_ref, words, mask, torch.eye(B), False)
+    lo.backward()
+    assert abs(float(loss) - float(lo)) < 1e-6 * abs(float(lo))
+    assert float((r_cl.grad - r_ref.grad).norm() / r_ref.grad.norm()) < 1e-6

@@ -184,3 +184,50 @@ def test_combine_col_stats_matches_torch(world, Bk):
     fin = ~torch.isinf(ref0)
     assert torch.allclose(out[0][fin].double(), ref0[fin], rtol=1e-6, atol=1e-6)
     assert torch.allclose(out[1:].double(), gathered[:, 1:].double().sum(0), rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,D,H,W", [(3, 256, 16, 16), (2, 256, 17, 17), (4, 128, 8, 8), (2, 64, 5, 3), (2, 512, 4, 6)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_row_layout_kernels_equal_the_transposing_ones(B, D, H, W, dt):
+    """xmc_normalize_rows (+ backward) on a channels-last map == xmc_normalize_transpose (+ backward) on the
+    contiguous map: same arithmetic, no transpose."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * D + H)
+    x = torch.randn(B, D, H, W, generator=g).to(dt).cuda()
+    x[0, :, 0, 1] = 0
+    L, Lpad = H * W, (H * W + 15) // 16 * 16
+    rows = x.permute(0, 2, 3, 1).contiguous().view(B, L, D)
+    xn_r, n_r = ops.normalize_rows(rows, Lpad, dt)
+    xn_t, n_t = ops.normalize_transpose(x.flatten(2).contiguous(), Lpad, dt)
+    assert torch.equal(n_r, n_t)
+    assert torch.allclose(xn_r.float(), xn_t.float(), atol=0, rtol=0) or float((xn_r.float() - xn_t.float()).abs().max()) <= 1e-2 * 2 ** -7
+    dxn = torch.randn(B, Lpad, D, generator=g).cuda()
+    dnorm = torch.randn(B, Lpad, generator=g).cuda()
+    d_r = ops.normalize_rows_backward(xn_t, n_t, dxn, dnorm, L, torch.float32)                     # [B, L, D]
+    d_t = ops.normalize_transpose_backward(xn_t, n_t, dxn, dnorm, L, torch.float32)               # [B, D, L]
+    err = float((d_r.transpose(1, 2) - d_t).norm() / d_t.norm())
+    assert err <= 1e-6, err
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("fp32", 1e-4)])
+def test_word_loss_on_channels_last_regions(precision, tol):
+    """The word loss fed a channels-last region map (what a 1x1 region head writes): same loss and gradients as
+    the contiguous map against the oracle, gradient returned channels-last."""
+    import oracle
+    from util import lerr, nerr, word_inputs
+    from xmc_gan_b200 import train_gan as T
+    B, D, T_, H = 12, 256, 9, 16
+    words, regions, mask = word_inputs(B, D, T_, H * H, seed=3)
+    dt = torch.bfloat16 if precision == "bf16" else torch.float32
+    rd = (lambda v: v.to(dt).double())
+    r4 = regions.view(B, D, H, H).to(dt).cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    w = words.to(dt).cuda().requires_grad_()
+    labels = T.make_labels(B, None, False)
+    loss = T.word_loss(r4, w, mask.cuda(), labels, False, precision=precision)
+    loss.backward()
+    assert r4.grad.is_contiguous(memory_format=torch.channels_last)
+    ro, wo = rd(regions).requires_grad_(), rd(words).requires_grad_()
+    lo = oracle.word_loss(ro, wo, mask, torch.eye(B), False)
+    lo.backward()
+    assert lerr(loss.detach(), lo.detach()) <= tol
+    assert nerr(r4.grad.flatten(2), ro.grad) <= tol and nerr(w.grad, wo.grad) <= tol

@@ -341,6 +341,80 @@ __global__ void __launch_bounds__(256, 3) norm_tr_bwd_bf16_kernel(const __nv_bfl
   }
 }
 
+// ---- rows that already are rows: x[B, L, D] with D contiguous (a channels-last feature map, the natural output of a
+// 1x1 region head run as a GEMM) -> unit rows xn[B, Lpad, D] + norms.  No transpose: one warp per row, 16-byte accesses,
+// the row stays in registers between the reduction and the store.  SURVEY section 8(f) N2: the producer emits the
+// tensor-core kernels' layout directly, so the smem-transpose kernels above drop out of the word loss.
+template <typename TI, typename TO, int kMaxV>
+__global__ void __launch_bounds__(256) norm_rows_kernel(const TI* __restrict__ x, long long nrows, int D, int L, int Lpad,
+                                                         TO* __restrict__ xn, float* __restrict__ norm) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);       // over B * Lpad
+  if (row >= nrows) return;
+  const int b = (int)(row / Lpad), l = (int)(row % Lpad);
+  TO* dst = xn + (size_t)row * D;
+  if (l >= L) {                                                              // padding rows: zeros, norm 0
+    for (int d = lane * 4; d < D; d += 128) st4(dst + d, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (lane == 0) norm[row] = 0.f;
+    return;
+  }
+  const TI* src = x + ((size_t)b * L + l) * D;
+  float4 v[kMaxV];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxV; ++k) {
+    const int d = k * 128 + lane * 4;
+    v[k] = d < D ? ld4_nc(src + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss += dot4(v[k], v[k]);
+  }
+  ss = warp_sum(ss);
+  const float n = fmaxf(sqrtf(ss), kEps), inv = 1.f / n;
+#pragma unroll
+  for (int k = 0; k < kMaxV; ++k) {
+    const int d = k * 128 + lane * 4;
+    if (d < D) st4(dst + d, make_float4(v[k].x * inv, v[k].y * inv, v[k].z * inv, v[k].w * inv));
+  }
+  if (lane == 0) norm[row] = n;
+}
+
+// dx[b,l,:] = (dxn - xh <xh, dxn>) / norm + dnorm * xh    (rows l < L; same arithmetic as norm_tr_bwd_kernel)
+template <typename TX, typename TO, int kMaxV>
+__global__ void __launch_bounds__(256) norm_rows_bwd_kernel(const TX* __restrict__ xn, const float* __restrict__ norm,
+                                                             const float* __restrict__ dxn, const float* __restrict__ dnorm,
+                                                             long long nrows, int D, int L, int Lpad,
+                                                             const int* __restrict__ error_word, TO* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const long long orow = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);      // over B * L
+  if (orow >= nrows) return;
+  const int b = (int)(orow / L), l = (int)(orow % L);
+  const float poison = (error_word && __ldg(error_word) != 0) ? __int_as_float(0x7fc00000) : 0.f;
+  const size_t irow = (size_t)b * Lpad + l;
+  const float n = norm[irow];
+  const bool clamped = n <= kEps;
+  const float inv = 1.f / n;
+  const float dn = (dnorm && !clamped) ? dnorm[irow] : 0.f;
+  float4 xh[kMaxV], g[kMaxV];
+  float proj = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxV; ++k) {
+    const int d = k * 128 + lane * 4;
+    if (d < D) {
+      xh[k] = ld4_nc(xn + irow * D + d);
+      g[k] = __ldg(reinterpret_cast<const float4*>(dxn + irow * D + d));
+      proj += dot4(xh[k], g[k]);
+    }
+  }
+  proj = clamped ? 0.f : warp_sum(proj);
+  TO* dst = dx + (size_t)orow * D;
+#pragma unroll
+  for (int k = 0; k < kMaxV; ++k) {
+    const int d = k * 128 + lane * 4;
+    if (d < D)
+      st4(dst + d, make_float4((g[k].x - xh[k].x * proj) * inv + dn * xh[k].x + poison, (g[k].y - xh[k].y * proj) * inv + dn * xh[k].y + poison,
+                               (g[k].z - xh[k].z * proj) * inv + dn * xh[k].z + poison, (g[k].w - xh[k].w * proj) * inv + dn * xh[k].w + poison));
+  }
+}
+
 // scores[i,c] = (1/rho2) log sum_{t unmasked} exp(rho2 rel[i, row(c,t)]);   one thread per (i,c).
 // Dense rows: row(c,t) = c*T+t with the padding mask; compact rows: caption c owns rows [cap_ptr[c], cap_ptr[c+1]).
 __global__ void __launch_bounds__(256) word_scores_kernel(const float* __restrict__ rel, const uint8_t* __restrict__ mask,
@@ -492,6 +566,57 @@ extern "C" int xmc_normalize_transpose_backward(const void* xn, const float* nor
   return xn_dtype == XMC_F32
              ? launch_norm_tr_bwd<float>(xn, norm, dxn, dnorm, B, D, L, Lpad, out_dtype, row_of, error_word, dx, as_stream(stream))
              : launch_norm_tr_bwd<__nv_bfloat16>(xn, norm, dxn, dnorm, B, D, L, Lpad, out_dtype, row_of, error_word, dx, as_stream(stream));
+}
+
+template <typename TI, typename TO>
+static int launch_norm_rows(const void* x, int B, int D, int L, int Lpad, void* xn, float* norm, cudaStream_t st) {
+  const long long rows = (long long)B * Lpad;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  auto* xi = static_cast<const TI*>(x);
+  auto* xo = static_cast<TO*>(xn);
+  if (D <= 256) norm_rows_kernel<TI, TO, 2><<<grid, 256, 0, st>>>(xi, rows, D, L, Lpad, xo, norm);
+  else norm_rows_kernel<TI, TO, 8><<<grid, 256, 0, st>>>(xi, rows, D, L, Lpad, xo, norm);
+  return cuda_fail(cudaGetLastError(), "norm_rows_kernel launch");
+}
+
+template <typename TX, typename TO>
+static int launch_norm_rows_bwd(const void* xn, const float* norm, const float* dxn, const float* dnorm, int B, int D, int L,
+                                int Lpad, const int* err, void* dx, cudaStream_t st) {
+  const long long rows = (long long)B * L;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  auto* xi = static_cast<const TX*>(xn);
+  auto* o = static_cast<TO*>(dx);
+  if (D <= 256) norm_rows_bwd_kernel<TX, TO, 2><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, rows, D, L, Lpad, err, o);
+  else norm_rows_bwd_kernel<TX, TO, 8><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, rows, D, L, Lpad, err, o);
+  return cuda_fail(cudaGetLastError(), "norm_rows_bwd_kernel launch");
+}
+
+extern "C" int xmc_normalize_rows(const void* x, int B, int D, int L, int Lpad, int in_dtype, int out_dtype, void* xn,
+                                  float* norm, void* stream) {
+  if (int rc = check_nt(x, xn, B, D, L, Lpad, in_dtype, out_dtype)) return rc;
+  XMC_REQUIRE(norm, XMC_ERR_INVALID_ARG, "null norm");
+  XMC_REQUIRE(D % 4 == 0 && aligned16(x) && aligned16(xn), XMC_ERR_ALIGNMENT, "rows need D %% 4 == 0 and 16-byte aligned pointers");
+  cudaStream_t st = as_stream(stream);
+  if (in_dtype == XMC_F32)
+    return out_dtype == XMC_F32 ? launch_norm_rows<float, float>(x, B, D, L, Lpad, xn, norm, st)
+                                : launch_norm_rows<float, __nv_bfloat16>(x, B, D, L, Lpad, xn, norm, st);
+  return out_dtype == XMC_F32 ? launch_norm_rows<__nv_bfloat16, float>(x, B, D, L, Lpad, xn, norm, st)
+                              : launch_norm_rows<__nv_bfloat16, __nv_bfloat16>(x, B, D, L, Lpad, xn, norm, st);
+}
+
+extern "C" int xmc_normalize_rows_backward(const void* xn, const float* norm, const float* dxn, const float* dnorm, int B, int D,
+                                           int L, int Lpad, int xn_dtype, int out_dtype, const int* error_word, void* dx,
+                                           void* stream) {
+  if (int rc = check_nt(xn, dx, B, D, L, Lpad, xn_dtype, out_dtype)) return rc;
+  XMC_REQUIRE(norm && dxn, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(D % 4 == 0 && aligned16(xn) && aligned16(dx) && aligned16(dxn), XMC_ERR_ALIGNMENT,
+              "rows need D %% 4 == 0 and 16-byte aligned pointers");
+  cudaStream_t st = as_stream(stream);
+  if (xn_dtype == XMC_F32)
+    return out_dtype == XMC_F32 ? launch_norm_rows_bwd<float, float>(xn, norm, dxn, dnorm, B, D, L, Lpad, error_word, dx, st)
+                                : launch_norm_rows_bwd<float, __nv_bfloat16>(xn, norm, dxn, dnorm, B, D, L, Lpad, error_word, dx, st);
+  return out_dtype == XMC_F32 ? launch_norm_rows_bwd<__nv_bfloat16, float>(xn, norm, dxn, dnorm, B, D, L, Lpad, error_word, dx, st)
+                              : launch_norm_rows_bwd<__nv_bfloat16, __nv_bfloat16>(xn, norm, dxn, dnorm, B, D, L, Lpad, error_word, dx, st);
 }
 
 extern "C" int xmc_word_scores(const float* rel, const uint8_t* mask, const int* cap_ptr, int Bi, int Bc, int T,

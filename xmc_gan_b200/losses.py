@@ -302,28 +302,47 @@ def _ceil_to(x, m):
 class _Word:
     __slots__ = ("path", "R", "T", "rho1", "rho2", "rho3", "qn", "qnorm", "kn", "rnorm", "has_rn", "lsum", "cnorm", "rel",
                  "scores", "m_all", "chat", "row_of", "cap_ptr", "compact", "bufs", "tail", "reg_shape", "reg_dtype", "w_dtype",
-                 "Bc", "fwd_ws")
+                 "Bc", "fwd_ws", "rows_layout")
+
+
+def _rows_view(regions):
+    """[B, D, H, W] in channels-last memory (what a 1x1 region head run as a GEMM writes, or any
+    ``memory_format=torch.channels_last`` producer) -> its [B, H*W, D] row view, else None.  SURVEY §8f N2: such a
+    producer already emits the kernels' layout, so the word loss skips both transposing layout kernels."""
+    if (regions.dim() == 4 and regions.shape[2] * regions.shape[3] > 1 and not regions.is_contiguous()
+            and regions.is_contiguous(memory_format=torch.channels_last) and regions.shape[1] % 4 == 0):
+        B, D, H, W = regions.shape
+        return regions.permute(0, 2, 3, 1).reshape(B, H * W, D)              # a view: D is the contiguous axis
+    return None
 
 
 def _word_prepare_regions(ops, regions, precision):
-    """Region prologue (independent of the gathered words: runs while the all-gather is in flight)."""
-    reg = regions.detach().flatten(2).contiguous()             # [Bi, D, R]
+    """Region prologue (independent of the gathered words: runs while the all-gather is in flight).
+    -> (shape [Bi, D, R], input dtype, precision, operand dtype, Rpad, unit rows kn, norms, rows_layout)."""
+    regions = regions.detach()
+    rows = _rows_view(regions) if hasattr(ops, "normalize_rows") else None
     if precision is None:
-        precision = "bf16" if reg.dtype == torch.bfloat16 else "fp32"
+        precision = "bf16" if regions.dtype == torch.bfloat16 else "fp32"
     if precision not in ("fp32", "bf16"):
         raise ValueError("precision must be 'fp32', 'bf16' or None")
     op_dtype = torch.float32 if precision == "fp32" else torch.bfloat16
-    Rpad = _ceil_to(reg.shape[2], 16)                          # zero rows up to the MMA's N granularity
-    kn, rnorm = ops.normalize_transpose(reg, Rpad, op_dtype)   # [Bi, Rpad, D]
-    return reg, precision, op_dtype, Rpad, kn, rnorm
+    if rows is not None:
+        Bi, R, D = rows.shape
+        Rpad = _ceil_to(R, 16)
+        kn, rnorm = ops.normalize_rows(rows, Rpad, op_dtype)                  # [Bi, Rpad, D], no transpose
+    else:
+        reg = regions.flatten(2).contiguous()                                # [Bi, D, R]
+        Bi, D, R = reg.shape
+        Rpad = _ceil_to(R, 16)                                               # zero rows up to the MMA's N granularity
+        kn, rnorm = ops.normalize_transpose(reg, Rpad, op_dtype)             # [Bi, Rpad, D]
+    return (Bi, D, R), regions.dtype, precision, op_dtype, Rpad, kn, rnorm, rows is not None
 
 
 def _word_local(ops, comm, prep, regions, w_all, m_all, labels, b_global, rho1, rho2, rho3, normalize_values, need_grad,
                 packet):
-    reg, precision, op_dtype, Rpad, kn, rnorm = prep
-    if reg.dtype != w_all.dtype:
-        raise TypeError(f"operand dtypes differ: {reg.dtype} vs {w_all.dtype}")
-    Bi, D, R = reg.shape
+    (Bi, D, R), reg_dtype, precision, op_dtype, Rpad, kn, rnorm, rows_layout = prep
+    if reg_dtype != w_all.dtype:
+        raise TypeError(f"operand dtypes differ: {reg_dtype} vs {w_all.dtype}")
     Bc, _, T = w_all.shape
     path = _lib.PATH_FP32_SIMT if precision == "fp32" else _lib.PATH_BF16_TCGEN05
     use_tc_bwd = path == _lib.PATH_BF16_TCGEN05 and D in TC_BACKWARD_DIMS
@@ -341,7 +360,7 @@ def _word_local(ops, comm, prep, regions, w_all, m_all, labels, b_global, rho1, 
     st = _Word()
     st.row_of = st.cap_ptr = nq_dev = None
     rn_used = not normalize_values
-    dev = reg.device
+    dev = kn.device
     # The word-side prologue and the zero fill of the backward's accumulators are independent of the
     # forward kernel's other operand: they go to a side stream and are joined below.
     with _side_scope(ops, dev) as mark:
@@ -376,7 +395,7 @@ def _word_local(ops, comm, prep, regions, w_all, m_all, labels, b_global, rho1, 
     st.path, st.R, st.T, st.rho1, st.rho2, st.rho3 = path, R, T, float(rho1), float(rho2), float(rho3)
     st.qn, st.qnorm, st.kn, st.rnorm, st.has_rn = qn, qnorm, kn, rnorm, rn is not None
     st.m_all, st.compact, st.tail, st.Bc = m_all, compact, tl, Bc
-    st.reg_shape, st.reg_dtype, st.w_dtype = tuple(regions.shape), regions.dtype, w_all.dtype
+    st.reg_shape, st.reg_dtype, st.w_dtype, st.rows_layout = tuple(regions.shape), regions.dtype, w_all.dtype, rows_layout
     return st
 
 
@@ -415,7 +434,11 @@ def _word_backward(ops, st: _Word, go, need_reg, need_w):
         with _side_scope(ops, dev):
             dw_all = ops.normalize_transpose_backward(qn, st.qnorm, dqn.view(qn.shape), None, T, torch.float32, error_word=ws,
                                                       **({"row_of": st.row_of} if st.compact else {}))
-    if need_reg:
+    if need_reg and st.rows_layout:            # gradient in the producer's own (channels-last) layout, no transpose
+        B_, D_, H_, W_ = st.reg_shape
+        dreg = ops.normalize_rows_backward(kn, st.rnorm, dkn, drnorm, st.R, st.reg_dtype, error_word=ws)
+        dreg = dreg.view(B_, H_, W_, D_).permute(0, 3, 1, 2)
+    elif need_reg:
         dreg = ops.normalize_transpose_backward(kn, st.rnorm, dkn, drnorm, st.R, st.reg_dtype, error_word=ws).view(st.reg_shape)
     return dreg, dw_all
 
@@ -435,7 +458,7 @@ class WordLossFn(torch.autograd.Function):
         prep = _word_prepare_regions(ops, regions, precision)
         work.wait()
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        packet = (torch.empty(_packet_floats(w_all.shape[0]), device=prep[0].device, dtype=torch.float32)
+        packet = (torch.empty(_packet_floats(w_all.shape[0]), device=regions.device, dtype=torch.float32)
                   if comm.active else None)
         st = _word_local(ops, comm, prep, regions, w_all.contiguous(), m_all, labels, b_global, rho1, rho2, rho3,
                          normalize_values, need_grad, packet)

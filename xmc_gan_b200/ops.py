@@ -339,6 +339,27 @@ class CudaOps:
         self.launches += 1
         return dx
 
+    def normalize_rows(self, x, Lpad, out_dtype):
+        """x [B, L, D] (D contiguous: a channels-last map) -> unit rows [B, Lpad, D] + norms [B, Lpad]; no transpose."""
+        _cuda(x)
+        B, L, D = x.shape
+        xn = torch.empty(B, Lpad, D, device=x.device, dtype=out_dtype)
+        norm = torch.empty(B, Lpad, device=x.device, dtype=torch.float32)
+        with _on(x):
+            self._check(self.L.xmc_normalize_rows(_p(x), B, D, L, Lpad, _dt(x), _DT[out_dtype], _p(xn), _p(norm), _stream()))
+        self.launches += 1
+        return xn, norm
+
+    def normalize_rows_backward(self, xn, norm, dxn, dnorm, L, out_dtype, error_word=None):
+        _cuda(xn, dxn)
+        B, Lpad, D = xn.shape
+        dx = torch.empty(B, L, D, device=xn.device, dtype=out_dtype)
+        with _on(xn):
+            self._check(self.L.xmc_normalize_rows_backward(_p(xn), _p(norm), _p(dxn), _p(dnorm), B, D, L, Lpad, _dt(xn),
+                                                           _DT[out_dtype], _p(error_word), _p(dx), _stream()))
+        self.launches += 1
+        return dx
+
     def _check_error_word(self, ws, what):
         """XMC_CHECK_ERRORS=1 (tests): synchronise and raise if a bounded mbarrier wait of the tcgen05 kernel
         timed out (word 0 of its workspace).  Off by default: the product path never synchronises."""
