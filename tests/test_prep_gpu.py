@@ -199,8 +199,8 @@ def test_row_layout_kernels_equal_the_transposing_ones(B, D, H, W, dt):
     rows = x.permute(0, 2, 3, 1).contiguous().view(B, L, D)
     xn_r, n_r = ops.normalize_rows(rows, Lpad, dt)
     xn_t, n_t = ops.normalize_transpose(x.flatten(2).contiguous(), Lpad, dt)
-    assert torch.equal(n_r, n_t)
-    assert torch.allclose(xn_r.float(), xn_t.float(), atol=0, rtol=0) or float((xn_r.float() - xn_t.float()).abs().max()) <= 1e-2 * 2 ** -7
+    assert torch.allclose(n_r, n_t, rtol=1e-6, atol=0)                      # same sum, different order
+    assert float((xn_r.float() - xn_t.float()).abs().max()) <= (2 ** -8 if dt == torch.bfloat16 else 1e-6)   # <= 1 bf16 ulp of a unit row
     dxn = torch.randn(B, Lpad, D, generator=g).cuda()
     dnorm = torch.randn(B, Lpad, generator=g).cuda()
     d_r = ops.normalize_rows_backward(xn_t, n_t, dxn, dnorm, L, torch.float32)                     # [B, L, D]

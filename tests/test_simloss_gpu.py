@@ -209,7 +209,7 @@ def test_large_rectangular_tensor_core_path_vs_oracle(T, Bq, Bk, D, dt, tol, den
     so = oracle.cosine_scores(ar, br)
     lo = oracle.infonce_tail(scale * so, lab_o.double(), 1)
     (1.7 * lo).backward()
-    assert nerr(scores, so) <= (2e-6 if dt == torch.float32 else 1e-5)        # fp32 inputs: split-bf16 product
+    assert nerr(scores, so) <= 1e-5                                         # split-bf16 product: ~2^-17 per operand
     assert lerr(loss3[0], lo.detach()) <= tol
     assert nerr(da, ar.grad) <= tol and nerr(db, br.grad) <= tol
     assert da.dtype == dt and db.dtype == dt
