@@ -291,8 +291,8 @@ def _join_side(ops, dev, *tensors, idx=0):
 
 TC_BACKWARD_DIMS = (128, 256)   # D handled by the tcgen05 backward kernel (others: fp32 kernel)
 # Saved attended contexts of the tcgen05 path: [images, word rows of the global batch, D] bf16 — O(B * B_global * T * D),
-# 0.6 GB at 256 x 256 x 18 x 256 and 4.8 GB per rank at 8 x 256.  Refuse silently growing past this many bytes.
-MAX_CONTEXT_BYTES = 16 << 30
+# 0.6 GB at 256 x 256 x 18 x 256, 4.8 GB per rank at 8 x 256, 17 GB at 1024 x 1024 x 32.  Refuse to grow silently past this many bytes.
+MAX_CONTEXT_BYTES = 32 << 30
 
 
 def _ceil_to(x, m):
