@@ -587,9 +587,11 @@ def main():
             return float(loss_host[(steps - 1) & 1])
 
     e2e_loop(5)
-    K_e2e = max(5, K)
+    # K steps are a 20 ms window, short enough for one slow PCIe / host moment to move the number by 10 % from run to run
+    # (230-257 k samples/s seen for the same build): take 5 K steps per pass, best of three passes
+    K_e2e = max(50, 5 * K)
     ms_e2e = float("inf")
-    for _ in range(2):                      # best of two passes of K_e2e steps (host-side jitter: PCIe, first-touch)
+    for _ in range(3):                      # best of three passes of K_e2e steps (host-side jitter: PCIe, first-touch)
         barrier()
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record()
@@ -666,7 +668,7 @@ def main():
         },
         "clocks": clocks,
         "e2e": {"value": Bg / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": K_e2e, "passes": "best of 2",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": K_e2e, "passes": "best of 3",
                 "how": "public API (train_gan.make_labels / sent_loss / img_loss / word_loss + backward, %s); pinned-host "
                        "inputs copied H2D every step on a copy stream one step ahead, loss copied D2H to pinned memory "
                        "every step and read by the host one step late" % mode},

@@ -83,7 +83,7 @@ int xmc_cosine_scores_backward(const void* a, const void* b, int Bq, int Bk, int
  * L2-normalise, cosine matrix, scale (=1/tau; the reference has no temperature: 1.0),
  * log-sum-exp over rows and over columns and the label-weighted sums, ONE kernel.
  * Writes scores[Bq,Bk] (kept for backward), inv norms and both statistics blocks.
- * Large rectangular problems (Bq*Bk >= 256*512, D a multiple of 128, Bk of 8: the sharded global-negative case,
+ * Large rectangular problems (Bq*Bk >= 256*1024, D a multiple of 128, Bk of 8: the sharded global-negative case,
  * 256 x 2048) take tcgen05 score tiles — fp32 operands split into two bf16 numbers, three MMAs per product,
  * fp32 accumulation: same 1e-4 tolerance — followed by one statistics pass; small ones the one-kernel form. */
 int xmc_simloss_forward(const void* a, const void* b, int Bq, int Bk, int D, int dtype,

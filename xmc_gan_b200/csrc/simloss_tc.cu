@@ -333,10 +333,13 @@ __global__ void __launch_bounds__(kTcThreads) sim_tc_bwd_kernel(SimParams p, flo
         uint32_t v[32];
         tmem_ld32(lane_base + c0, v);
         tmem_wait_ld();
-        if (g < n) {
+        if (g < n) {                                     // 16-byte vector reductions: a quarter of the instructions
           float* dst = G + (size_t)g * p.D + d0 + c0;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) atomicAdd(dst + q, __uint_as_float(v[q]));
+          for (int q = 0; q < 8; ++q)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(v[4 * q])),
+                         "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])), "f"(__uint_as_float(v[4 * q + 3]))
+                         : "memory");
         }
       }
     }
@@ -382,7 +385,9 @@ constexpr int kBwdSmem = 8 * kBlk + 384 * 4 + 64 + 1024;
 }  // namespace
 
 bool sim_tc_eligible(int Bq, int Bk, int D) {
-  return (long long)Bq * Bk >= 256LL * 512 && D % 128 == 0 && D <= 768 && Bk % 8 == 0;
+  // measured (profiles/r02_sim_tc.jsonl): at 256 x 512 the one-kernel CUDA-core form still wins (27 vs 46 us backward),
+  // from 256 x 1024 on the tensor-core form does (48 vs 88 us at D = 512; 50 vs 98-148 us at 256 x 2048)
+  return (long long)Bq * Bk >= 256LL * 1024 && D % 128 == 0 && D <= 768 && Bk % 8 == 0;
 }
 
 size_t sim_tc_workspace_bytes(int Bq, int Bk, int D) {
