@@ -345,44 +345,36 @@ __global__ void __launch_bounds__(256, 3) norm_tr_bwd_bf16_kernel(const __nv_bfl
 // 1x1 region head run as a GEMM) -> unit rows xn[B, Lpad, D] + norms.  No transpose: one warp per row, 16-byte accesses,
 // the row stays in registers between the reduction and the store.  SURVEY section 8(f) N2: the producer emits the
 // tensor-core kernels' layout directly, so the smem-transpose kernels above drop out of the word loss.
-constexpr int kRowsPerWarp = 4;      // rows a warp has in flight at once (memory-level parallelism: one row is only 512 B)
-
 template <typename TI, typename TO, int kMaxV>
 __global__ void __launch_bounds__(256) norm_rows_kernel(const TI* __restrict__ x, long long nrows, int D, int L, int Lpad,
                                                          TO* __restrict__ xn, float* __restrict__ norm) {
   const int lane = threadIdx.x & 31;
-  const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kRowsPerWarp;      // over B * Lpad
-  float4 v[kRowsPerWarp][kMaxV];
-  bool live[kRowsPerWarp];
-#pragma unroll
-  for (int q = 0; q < kRowsPerWarp; ++q) {                 // every load of the warp's rows is issued before the first use
-    const long long row = row0 + q;
-    const int b = (int)(row / Lpad), l = (int)(row % Lpad);
-    live[q] = row < nrows && l < L;
-    const TI* src = x + ((size_t)b * L + l) * D;
-#pragma unroll
-    for (int k = 0; k < kMaxV; ++k) {
-      const int d = k * 128 + lane * 4;
-      v[q][k] = (live[q] && d < D) ? ld4_nc(src + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);       // over B * Lpad
+  if (row >= nrows) return;
+  const int b = (int)(row / Lpad), l = (int)(row % Lpad);
+  TO* dst = xn + (size_t)row * D;
+  if (l >= L) {                                                              // padding rows: zeros, norm 0
+    for (int d = lane * 4; d < D; d += 128) st4(dst + d, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (lane == 0) norm[row] = 0.f;
+    return;
   }
+  const TI* src = x + ((size_t)b * L + l) * D;
+  float4 v[kMaxV];
+  float ss = 0.f;
 #pragma unroll
-  for (int q = 0; q < kRowsPerWarp; ++q) {
-    const long long row = row0 + q;
-    if (row >= nrows) break;
-    TO* dst = xn + (size_t)row * D;
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < kMaxV; ++k) ss += dot4(v[q][k], v[q][k]);
-    ss = warp_sum(ss);
-    const float n = fmaxf(sqrtf(ss), kEps), inv = live[q] ? 1.f / n : 0.f;      // padding rows: zeros, norm 0
-#pragma unroll
-    for (int k = 0; k < kMaxV; ++k) {
-      const int d = k * 128 + lane * 4;
-      if (d < D) st4(dst + d, make_float4(v[q][k].x * inv, v[q][k].y * inv, v[q][k].z * inv, v[q][k].w * inv));
-    }
-    if (lane == 0) norm[row] = live[q] ? n : 0.f;
+  for (int k = 0; k < kMaxV; ++k) {
+    const int d = k * 128 + lane * 4;
+    v[k] = d < D ? ld4_nc(src + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss += dot4(v[k], v[k]);
   }
+  ss = warp_sum(ss);
+  const float n = fmaxf(sqrtf(ss), kEps), inv = 1.f / n;
+#pragma unroll
+  for (int k = 0; k < kMaxV; ++k) {
+    const int d = k * 128 + lane * 4;
+    if (d < D) st4(dst + d, make_float4(v[k].x * inv, v[k].y * inv, v[k].z * inv, v[k].w * inv));
+  }
+  if (lane == 0) norm[row] = n;
 }
 
 // dx[b,l,:] = (dxn - xh <xh, dxn>) / norm + dnorm * xh    (rows l < L; same arithmetic as norm_tr_bwd_kernel)
@@ -391,48 +383,35 @@ __global__ void __launch_bounds__(256) norm_rows_bwd_kernel(const TX* __restrict
                                                              const float* __restrict__ dxn, const float* __restrict__ dnorm,
                                                              long long nrows, int D, int L, int Lpad,
                                                              const int* __restrict__ error_word, TO* __restrict__ dx) {
-  constexpr int kR = kMaxV <= 2 ? kRowsPerWarp : 1;         // rows in flight per warp (registers: 2 operands per row)
   const int lane = threadIdx.x & 31;
-  const long long orow0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kR;      // over B * L
+  const long long orow = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);      // over B * L
+  if (orow >= nrows) return;
+  const int b = (int)(orow / L), l = (int)(orow % L);
   const float poison = (error_word && __ldg(error_word) != 0) ? __int_as_float(0x7fc00000) : 0.f;
-  float4 xh[kR][kMaxV], g[kR][kMaxV];
-  float n[kR], dn[kR];
+  const size_t irow = (size_t)b * Lpad + l;
+  const float n = norm[irow];
+  const bool clamped = n <= kEps;
+  const float inv = 1.f / n;
+  const float dn = (dnorm && !clamped) ? dnorm[irow] : 0.f;
+  float4 xh[kMaxV], g[kMaxV];
+  float proj = 0.f;
 #pragma unroll
-  for (int q = 0; q < kR; ++q) {
-    const long long orow = orow0 + q;
-    const bool ok = orow < nrows;
-    const int b = ok ? (int)(orow / L) : 0, l = ok ? (int)(orow % L) : 0;
-    const size_t irow = (size_t)b * Lpad + l;
-    n[q] = ok ? norm[irow] : 1.f;
-    dn[q] = (ok && dnorm) ? dnorm[irow] : 0.f;
-#pragma unroll
-    for (int k = 0; k < kMaxV; ++k) {
-      const int d = k * 128 + lane * 4;
-      const bool in = ok && d < D;
-      xh[q][k] = in ? ld4_nc(xn + irow * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-      g[q][k] = in ? __ldg(reinterpret_cast<const float4*>(dxn + irow * D + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < kMaxV; ++k) {
+    const int d = k * 128 + lane * 4;
+    if (d < D) {
+      xh[k] = ld4_nc(xn + irow * D + d);
+      g[k] = __ldg(reinterpret_cast<const float4*>(dxn + irow * D + d));
+      proj += dot4(xh[k], g[k]);
     }
   }
+  proj = clamped ? 0.f : warp_sum(proj);
+  TO* dst = dx + (size_t)orow * D;
 #pragma unroll
-  for (int q = 0; q < kR; ++q) {
-    const long long orow = orow0 + q;
-    if (orow >= nrows) break;
-    const bool clamped = n[q] <= kEps;                      // x/eps is linear: no projection, no norm path
-    const float inv = 1.f / n[q];
-    const float dnq = clamped ? 0.f : dn[q];
-    float proj = 0.f;
-#pragma unroll
-    for (int k = 0; k < kMaxV; ++k) proj += dot4(xh[q][k], g[q][k]);
-    proj = clamped ? 0.f : warp_sum(proj);
-    TO* dst = dx + (size_t)orow * D;
-#pragma unroll
-    for (int k = 0; k < kMaxV; ++k) {
-      const int d = k * 128 + lane * 4;
-      const float4 X = xh[q][k], G = g[q][k];
-      if (d < D)
-        st4(dst + d, make_float4((G.x - X.x * proj) * inv + dnq * X.x + poison, (G.y - X.y * proj) * inv + dnq * X.y + poison,
-                                 (G.z - X.z * proj) * inv + dnq * X.z + poison, (G.w - X.w * proj) * inv + dnq * X.w + poison));
-    }
+  for (int k = 0; k < kMaxV; ++k) {
+    const int d = k * 128 + lane * 4;
+    if (d < D)
+      st4(dst + d, make_float4((g[k].x - xh[k].x * proj) * inv + dn * xh[k].x + poison, (g[k].y - xh[k].y * proj) * inv + dn * xh[k].y + poison,
+                               (g[k].z - xh[k].z * proj) * inv + dn * xh[k].z + poison, (g[k].w - xh[k].w * proj) * inv + dn * xh[k].w + poison));
   }
 }
 
@@ -592,7 +571,7 @@ extern "C" int xmc_normalize_transpose_backward(const void* xn, const float* nor
 template <typename TI, typename TO>
 static int launch_norm_rows(const void* x, int B, int D, int L, int Lpad, void* xn, float* norm, cudaStream_t st) {
   const long long rows = (long long)B * Lpad;
-  const unsigned grid = (unsigned)((rows + 8 * kRowsPerWarp - 1) / (8 * kRowsPerWarp));
+  const unsigned grid = (unsigned)((rows + 7) / 8);
   auto* xi = static_cast<const TI*>(x);
   auto* xo = static_cast<TO*>(xn);
   if (D <= 256) norm_rows_kernel<TI, TO, 2><<<grid, 256, 0, st>>>(xi, rows, D, L, Lpad, xo, norm);
@@ -604,15 +583,11 @@ template <typename TX, typename TO>
 static int launch_norm_rows_bwd(const void* xn, const float* norm, const float* dxn, const float* dnorm, int B, int D, int L,
                                 int Lpad, const int* err, void* dx, cudaStream_t st) {
   const long long rows = (long long)B * L;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
   auto* xi = static_cast<const TX*>(xn);
   auto* o = static_cast<TO*>(dx);
-  if (D <= 256) {
-    const unsigned grid = (unsigned)((rows + 8 * kRowsPerWarp - 1) / (8 * kRowsPerWarp));
-    norm_rows_bwd_kernel<TX, TO, 2><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, rows, D, L, Lpad, err, o);
-  } else {
-    const unsigned grid = (unsigned)((rows + 7) / 8);
-    norm_rows_bwd_kernel<TX, TO, 8><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, rows, D, L, Lpad, err, o);
-  }
+  if (D <= 256) norm_rows_bwd_kernel<TX, TO, 2><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, rows, D, L, Lpad, err, o);
+  else norm_rows_bwd_kernel<TX, TO, 8><<<grid, 256, 0, st>>>(xi, norm, dxn, dnorm, rows, D, L, Lpad, err, o);
   return cuda_fail(cudaGetLastError(), "norm_rows_bwd_kernel launch");
 }
 
