@@ -46,9 +46,13 @@ typedef enum {
 
 typedef enum { XMC_F32 = 0, XMC_BF16 = 1 } xmc_dtype;
 
-/* Word-region compute path: CUDA-core fp32 (operands fp32, tolerance 1e-4) or
- * tcgen05/TMEM tensor-core path (operands bf16, fp32 accumulate, tolerance 2e-2). */
-typedef enum { XMC_PATH_FP32_SIMT = 0, XMC_PATH_BF16_TCGEN05 = 1 } xmc_path;
+/* Word-region compute path:
+ *   XMC_PATH_FP32_SIMT     CUDA-core fp32 (operands fp32, tolerance 1e-4), D = 64 / 128 / 256;
+ *   XMC_PATH_BF16_TCGEN05  tcgen05/TMEM path, operands bf16, fp32 accumulate, tolerance 2e-2 (the throughput path);
+ *   XMC_PATH_FP32_TCGEN05  tcgen05/TMEM path at fp32 tolerance: operands fp32, carried as hi + lo bf16 pairs, three
+ *                          MMAs per product, fp32 accumulate (tolerance 1e-4), D = 256.  `chat` is then TWO bf16 planes
+ *                          [2][Bi, NQ, D] (hi, lo) and the workspace holds the operands' planes. */
+typedef enum { XMC_PATH_FP32_SIMT = 0, XMC_PATH_BF16_TCGEN05 = 1, XMC_PATH_FP32_TCGEN05 = 2 } xmc_path;
 
 int xmc_version(void);
 const char* xmc_last_error(void);

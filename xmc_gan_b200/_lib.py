@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 HOOKED_SOURCES = ("wordregion_tc.cu", "prep.cu")
 
 XMC_F32, XMC_BF16 = 0, 1
-PATH_FP32_SIMT, PATH_BF16_TCGEN05 = 0, 1
+PATH_FP32_SIMT, PATH_BF16_TCGEN05, PATH_FP32_TCGEN05 = 0, 1, 2
 
 _vp, _i, _f, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 

@@ -24,7 +24,9 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 static int check_wr(int path, const void* qn, const void* kn, int NQ, int Bi, int R, int Rpad, int D) {
-  XMC_REQUIRE(path == XMC_PATH_FP32_SIMT || path == XMC_PATH_BF16_TCGEN05, XMC_ERR_UNSUPPORTED, "unknown path %d", path);
+  XMC_REQUIRE(path == XMC_PATH_FP32_SIMT || path == XMC_PATH_BF16_TCGEN05 || path == XMC_PATH_FP32_TCGEN05, XMC_ERR_UNSUPPORTED,
+              "unknown path %d", path);
+  XMC_REQUIRE(path != XMC_PATH_FP32_TCGEN05 || D == 256, XMC_ERR_UNSUPPORTED, "the split-bf16 path supports D = 256 (got %d)", D);
   XMC_REQUIRE(qn && kn, XMC_ERR_INVALID_ARG, "null operand pointer");
   XMC_REQUIRE(NQ > 0 && Bi > 0 && R > 0, XMC_ERR_INVALID_ARG, "bad shape NQ=%d Bi=%d R=%d", NQ, Bi, R);
   XMC_REQUIRE(Rpad >= R && Rpad % 16 == 0, XMC_ERR_INVALID_ARG, "Rpad=%d must be a multiple of 16 and >= R=%d", Rpad, R);
@@ -52,6 +54,7 @@ extern "C" int xmc_check_device(void) {
 
 extern "C" size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad, int D) {
   if (path == XMC_PATH_BF16_TCGEN05) return wordregion_tc_workspace_bytes(NQ, Bi, R, Rpad, D);
+  if (path == XMC_PATH_FP32_TCGEN05) return wordregion_split_workspace_bytes(NQ, Bi, R, Rpad, D);
   return 0;
 }
 
@@ -68,6 +71,7 @@ extern "C" int xmc_wordregion_forward(int path, const void* qn, const void* kn, 
   p.lsum = lsum; p.cnorm = cnorm; p.rel = rel; p.chat = chat; p.nq_dev = nq_dev;
   XMC_REQUIRE(!chat || aligned16(chat), XMC_ERR_ALIGNMENT, "chat must be 16-byte aligned");
   if (path == XMC_PATH_FP32_SIMT) return wordregion_f32_forward(p, D, as_stream(stream));
+  if (path == XMC_PATH_FP32_TCGEN05) return wordregion_split_forward(p, D, workspace, workspace_bytes, as_stream(stream));
   return wordregion_tc_forward(p, D, workspace, workspace_bytes, as_stream(stream));
 }
 
@@ -86,5 +90,6 @@ extern "C" int xmc_wordregion_backward(int path, const void* qn, const void* kn,
   p.lsum = const_cast<float*>(lsum); p.cnorm = const_cast<float*>(cnorm); p.rel = const_cast<float*>(rel);
   p.grel = grel; p.dqn = dqn; p.dkn = dkn; p.drnorm = drnorm; p.chat = const_cast<void*>(chat); p.nq_dev = nq_dev;
   if (path == XMC_PATH_FP32_SIMT) return wordregion_f32_backward(p, D, as_stream(stream));
+  if (path == XMC_PATH_FP32_TCGEN05) return wordregion_split_backward(p, D, workspace, workspace_bytes, as_stream(stream));
   return wordregion_tc_backward(p, D, workspace, workspace_bytes, as_stream(stream));
 }

@@ -1,0 +1,594 @@
+// wordregion_split.cu — the fp32-TOLERANCE word-region path on the 5th-gen tensor cores (XMC_PATH_FP32_TCGEN05).
+//
+// BASELINE config 2 names two modes, fp32 (rel 1e-4) and bf16-in/fp32-accumulate (rel 2e-2).  wordregion_tc.cu is the
+// second; the first used to run on CUDA cores (wordregion_f32.cu, 35-58 ms per COCO-256 step).  A single bf16 or tf32
+// product cannot meet 1e-4, but every fp32 operand can be carried as TWO bf16 numbers, x = hi + lo
+// (|x - hi - lo| <= 2^-17 |x|), and every product as three MMAs, hi*hi + hi*lo + lo*hi, accumulated in fp32 in TMEM.
+// Emulated on the CPU against the fp64 oracle this keeps loss and gradients of the word loss within 4e-6
+// (plain bf16 operands: 2e-3); measured on the GPU: tests/test_wordregion_split_gpu.py.
+//
+// Same mathematics and the same per-(image, word) state as the other two paths (spec: oracle/word_region.py; the
+// loss is the `word_loss` the reference names at xmc_gan/train_gan.py:220-222, 267-269 and never implements):
+//   forward   S = Q Khat^T -> P = exp(rho1 (S - 1)), P' = P ||v_r|| -> C += P' Khat -> lsum, cnorm, rel, and C itself
+//             (kept for the backward as a hi/lo bf16 pair: as many bytes as fp32)
+//   backward  S, W = C Khat^T -> X, Y (closed form) -> dQ += X Khat,  dK^T = C^T Y + Q^T X  -> fp32 reductions
+// Operands are split ONCE per call into hi / lo bf16 planes in the caller's workspace (split_planes_kernel); the CTAs
+// copy tiles of those planes into 128B-swizzled shared memory with cp.async (no arithmetic on the way) and ONE thread
+// issues the tcgen05 MMAs.  The schedule is synchronous — stage, multiply, wait — on purpose: this is the precise mode,
+// 12x faster than the CUDA-core kernels it replaces and simple enough to audit; the throughput path is wordregion_tc.cu.
+// Shared memory bounds the shape of the backward: Q and C tiles (128 x 256, hi + lo = 128 KB each) cannot both stay
+// resident, so they pass through ONE 64 KB buffer in feature halves (S and W accumulate over the halves; each half is
+// one M-tile of dK^T).
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "wordregion.h"
+
+namespace xmc {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TMs = 128;               // word rows per tile (UMMA M)
+constexpr int CHs = 64;                // regions per chunk (UMMA N of the score products)
+constexpr int kABlk = TMs * 128;       // [128 rows x 64 bf16] swizzled block: 16 KB
+constexpr int kKBlk = CHs * 128;       // [64 rows x 64 bf16] swizzled block: 8 KB
+constexpr int kThreads = 256;
+constexpr float kLog2eS = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 16-byte asynchronous copy global -> shared; src_bytes = 0 zero-fills (rows past the end of the operand)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// rows [row0, row0 + rows) x columns [col0, col0 + 64 nblk) of a row-major bf16 plane (leading dimension ld) ->
+// nblk swizzled blocks of [rows x 64], blk_bytes apart.  Rows at or past n_valid are zero-filled.
+__device__ __forceinline__ void stage_tile(uint8_t* dst, int blk_bytes, const __nv_bfloat16* src, size_t ld, long long row0,
+                                           long long n_valid, int rows, int col0, int nblk) {
+  const int per_row = nblk * 8;                       // 16-byte chunks per tile row
+  for (int idx = threadIdx.x; idx < rows * per_row; idx += kThreads) {
+    const int r = idx / per_row, rem = idx - r * per_row, b = rem >> 3, c = rem & 7;
+    const bool ok = row0 + r < n_valid;
+    const __nv_bfloat16* s = src + (size_t)(ok ? row0 + r : 0) * ld + col0 + b * 64 + c * 8;
+    cp_async16(dst + b * blk_bytes + r * 128 + ((c ^ (r & 7)) << 4), s, ok ? 16 : 0);
+  }
+}
+
+__device__ __forceinline__ void st_chunk16(uint8_t* blk, int r, int c, uint4 v) {
+  *reinterpret_cast<uint4*>(blk + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+}
+
+// x[0..8) -> bf16 hi and bf16 lo = rn(x - hi), each as one 16-byte chunk
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 hv = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+    const float2 hf = __bfloat1622float2(hv);
+    h[e] = *reinterpret_cast<const uint32_t*>(&hv);
+    l[e] = pack_bf16(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// fp32 operand -> hi / lo bf16 planes (8 elements per thread)
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, size_t n8, __nv_bfloat16* __restrict__ hi,
+                                                            __nv_bfloat16* __restrict__ lo) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(x) + 2 * i), v = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+    const float f[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+    uint4 h, l;
+    split8(f, h, l);
+    reinterpret_cast<uint4*>(hi)[i] = h;
+    reinterpret_cast<uint4*>(lo)[i] = l;
+  }
+}
+
+struct SplitParams {
+  const __nv_bfloat16* qh; const __nv_bfloat16* ql;     // [NQ, D] planes
+  const __nv_bfloat16* kh; const __nv_bfloat16* kl;     // [Bi, Rpad, D] planes
+  __nv_bfloat16* ch; __nv_bfloat16* cl;                 // [Bi, NQ, D] planes of the context sums (forward writes, backward reads)
+  const float* rnorm;
+  int NQ, Bi, R, Rpad;
+  const int* nq_dev;
+  float rho1;
+  float* lsum; float* cnorm; float* rel;
+  const float* grel;
+  float* dqn; float* dkn; float* drnorm;
+  int* err;
+};
+
+struct Ctl {
+  uint64_t bar;
+  uint32_t tmem_slot;
+  int abort_flag;
+};
+
+__device__ __forceinline__ uint8_t* align1k(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+// three MMAs of one k-step: hi*hi (+)= , hi*lo +=, lo*hi +=          (SS form)
+__device__ __forceinline__ void mma3_ss(uint32_t d, Desc ah, Desc al, Desc bh, Desc bl, uint32_t idesc, bool acc) {
+  mma_ss(d, ah, bh, idesc, acc);
+  mma_ss(d, ah, bl, idesc, true);
+  mma_ss(d, al, bh, idesc, true);
+}
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+template <int D>
+struct FwdS {
+  static constexpr int kOffQh = 0, kOffQl = (D / 64) * kABlk, kOffKh = 2 * (D / 64) * kABlk, kOffKl = kOffKh + (D / 64) * kKBlk,
+                       kOffRn = kOffKl + (D / 64) * kKBlk, kOffPart = kOffRn + CHs * 4, kOffCtl = kOffPart + 3 * 2 * TMs * 4,
+                       kBytes = kOffCtl + 64 + 1024;
+  static constexpr int kColC = 0, kColS = D;
+  static_assert(kBytes <= 232448, "shared memory budget");
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(SplitParams p) {
+  using L = FwdS<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1k(smem_raw);
+  uint8_t* Qh = smem + L::kOffQh; uint8_t* Ql = smem + L::kOffQl;
+  uint8_t* Kh = smem + L::kOffKh; uint8_t* Kl = smem + L::kOffKl;
+  float* rn_s = reinterpret_cast<float*>(smem + L::kOffRn);
+  float* part = reinterpret_cast<float*>(smem + L::kOffPart);          // [3: l, a, |C|^2][2 halves][128]
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + L::kOffCtl);
+  const WaitCtx wc{&ctl->abort_flag, p.err};
+
+  const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;             // thread = TMEM lane (word row) x column half
+  const int NQv = p.nq_dev ? min(p.NQ, __ldg(p.nq_dev)) : p.NQ;
+  const int m0 = blockIdx.x * TMs;
+  if (m0 >= NQv) return;
+  const int grow = m0 + row;
+  const int nch = (p.Rpad + CHs - 1) / CHs;
+  const bool has_rn = p.rnorm != nullptr;
+  const float c1 = p.rho1 * kLog2eS;
+
+  if (tid == 0) { ctl->abort_flag = 0; mbar_init(&ctl->bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&ctl->tmem_slot, 512);
+  stage_tile(Qh, kABlk, p.qh, D, m0, NQv, TMs, 0, D / 64);
+  stage_tile(Ql, kABlk, p.ql, D, m0, NQv, TMs, 0, D / 64);
+  cp_async_wait_all();
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctl->tmem_slot;
+  const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  uint32_t phase = 0;
+
+  for (int img = blockIdx.y; img < p.Bi; img += gridDim.y) {
+    float l = 0.f, a = 0.f;
+    for (int c = 0; c < nch; ++c) {
+      const int n = min(CHs, p.Rpad - c * CHs);
+      const long long krow0 = (long long)img * p.Rpad + c * CHs;
+      stage_tile(Kh, kKBlk, p.kh, D, krow0, krow0 + n, CHs, 0, D / 64);
+      stage_tile(Kl, kKBlk, p.kl, D, krow0, krow0 + n, CHs, 0, D / 64);
+      if (tid < CHs) rn_s[tid] = (has_rn && tid < n) ? __ldg(p.rnorm + (size_t)img * p.Rpad + c * CHs + tid) : 1.f;
+      cp_async_wait_all();
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (warp == 0) {
+        if (elect_one()) {                                      // S = Q Khat^T, three MMAs per 16 features
+          tc_fence_after();
+          constexpr uint32_t idesc = idesc_bf16(TMs, CHs, false, false);
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t ao = (k >> 2) * kABlk + (k & 3) * 32, bo = (k >> 2) * kKBlk + (k & 3) * 32;
+            mma3_ss(tmem + L::kColS, make_desc(smem_u32(Qh) + ao, 16, 1024), make_desc(smem_u32(Ql) + ao, 16, 1024),
+                    make_desc(smem_u32(Kh) + bo, 16, 1024), make_desc(smem_u32(Kl) + bo, 16, 1024), idesc, k > 0);
+          }
+          mma_commit(&ctl->bar);
+        }
+        __syncwarp();
+      }
+      mbar_wait(&ctl->bar, phase, wc, 31); phase ^= 1;
+      tc_fence_after();
+      {   // softmax numerators of this thread's 32 columns; P' = hi + lo written back over S (A operand of the next product)
+        uint32_t sv[32];
+        tmem_ld32(lane_base + L::kColS + half * 32, sv);
+        tmem_wait_ld();
+        uint32_t ph[16], pl[16];
+        const int r0 = c * CHs + half * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float pw[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float s = __uint_as_float(sv[j + e]);
+            const float pv = (r0 + j + e) < p.R ? ex2f(fmaf(s, c1, -c1)) : 0.f;
+            l += pv;
+            pw[e] = pv * rn_s[half * 32 + j + e];
+            a = fmaf(pw[e], s, a);
+          }
+          const __nv_bfloat162 hv = __floats2bfloat162_rn(pw[0], pw[1]);
+          const float2 hf = __bfloat1622float2(hv);
+          ph[j >> 1] = *reinterpret_cast<const uint32_t*>(&hv);
+          pl[j >> 1] = pack_bf16(pw[0] - hf.x, pw[1] - hf.y);
+        }
+        tmem_st16(lane_base + L::kColS + half * 32, ph);             // hi: 16 packed columns
+        tmem_st16(lane_base + L::kColS + half * 32 + 16, pl);        // lo: the next 16
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        if (elect_one()) {                                      // C += P' Khat (A from tensor memory, B = the same smem bytes, MN-major)
+          tc_fence_after();
+          constexpr uint32_t idesc2 = idesc_bf16(TMs, D, false, true);
+#pragma unroll
+          for (int ks = 0; ks < CHs / 16; ++ks) {
+            if (ks * 16 < n) {
+              const uint32_t ah = tmem + L::kColS + (ks >> 1) * 32 + (ks & 1) * 8, al = ah + 16;
+              const Desc bh = make_desc(smem_u32(Kh) + ks * 2048, kKBlk, 1024), bl = make_desc(smem_u32(Kl) + ks * 2048, kKBlk, 1024);
+              mma_ts(tmem + L::kColC, ah, bh, idesc2, c > 0 || ks > 0);
+              mma_ts(tmem + L::kColC, ah, bl, idesc2, true);
+              mma_ts(tmem + L::kColC, al, bh, idesc2, true);
+            }
+          }
+          mma_commit(&ctl->bar);
+        }
+        __syncwarp();
+      }
+      mbar_wait(&ctl->bar, phase, wc, 32); phase ^= 1;           // region tiles and S are free again
+      tc_fence_after();
+    }
+    // ---- per image: context sums -> hi/lo planes, |C|^2; statistics of the row ----
+    {
+      float c2 = 0.f;
+      const size_t o = ((size_t)img * p.NQ + grow) * D + half * (D / 2);
+#pragma unroll 1
+      for (int b = 0; b < D / 64; ++b) {                        // this thread's D/2 columns, 32 at a time
+        uint32_t cv[32];
+        tmem_ld32(lane_base + L::kColC + half * (D / 2) + b * 32, cv);
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { x[e] = __uint_as_float(cv[8 * u + e]); c2 = fmaf(x[e], x[e], c2); }
+          if (grow < NQv && p.ch) {
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            *reinterpret_cast<uint4*>(p.ch + o + b * 32 + u * 8) = hi;
+            *reinterpret_cast<uint4*>(p.cl + o + b * 32 + u * 8) = lo;
+          }
+        }
+      }
+      part[(0 * 2 + half) * TMs + row] = l;
+      part[(1 * 2 + half) * TMs + row] = a;
+      part[(2 * 2 + half) * TMs + row] = c2;
+      tc_fence_before();
+      __syncthreads();                                          // C may be overwritten by the next image; partials visible
+      tc_fence_after();
+      if (half == 0 && grow < NQv) {
+        const float lt = part[row] + part[TMs + row], at = part[2 * TMs + row] + part[3 * TMs + row];
+        const float ct = part[4 * TMs + row] + part[5 * TMs + row];
+        const float cn = sqrtf(ct) / lt;
+        const size_t o2 = (size_t)img * p.NQ + grow;
+        p.lsum[o2] = lt;
+        p.cnorm[o2] = cn;
+        p.rel[o2] = (at / lt) / fmaxf(cn, kEps);
+      }
+      __syncthreads();                                          // partials are rewritten by the next image
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =====================================================================================================
+// backward
+// =====================================================================================================
+template <int D>
+struct BwdS {
+  static_assert(D == 256, "feature halves of 128 columns: each is one M = 128 tile of dK^T");
+  static constexpr int kHalf = D / 2;                    // features per half
+  static constexpr int kHB = kHalf / 64;                 // 64-feature blocks per half
+  static constexpr int kOffAh = 0, kOffAl = kHB * kABlk, kOffKh = 2 * kHB * kABlk, kOffKl = kOffKh + (D / 64) * kKBlk,
+                       kOffXh = kOffKl + (D / 64) * kKBlk, kOffXl = kOffXh + kABlk, kOffYh = kOffXl + kABlk, kOffYl = kOffYh + kABlk,
+                       kOffRn = kOffYl + kABlk, kOffCol = kOffRn + CHs * 4, kOffCtl = kOffCol + CHs * 4, kBytes = kOffCtl + 64 + 1024;
+  static constexpr int kColDQ = 0, kColS = D, kColW = D + CHs, kColDK = D + 2 * CHs;
+  static_assert(kColDK + CHs <= 512, "TMEM budget");
+  static_assert(kBytes <= 232448, "shared memory budget");
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p) {
+  using L = BwdS<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1k(smem_raw);
+  uint8_t* Ah = smem + L::kOffAh; uint8_t* Al = smem + L::kOffAl;      // one feature half of Q or of C, hi / lo
+  uint8_t* Kh = smem + L::kOffKh; uint8_t* Kl = smem + L::kOffKl;
+  uint8_t* Xh = smem + L::kOffXh; uint8_t* Xl = smem + L::kOffXl;
+  uint8_t* Yh = smem + L::kOffYh; uint8_t* Yl = smem + L::kOffYl;
+  float* rn_s = reinterpret_cast<float*>(smem + L::kOffRn);
+  float* colacc = reinterpret_cast<float*>(smem + L::kOffCol);
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + L::kOffCtl);
+  const WaitCtx wc{&ctl->abort_flag, p.err};
+
+  const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+  const int NQv = p.nq_dev ? min(p.NQ, __ldg(p.nq_dev)) : p.NQ;
+  const int m0 = blockIdx.x * TMs;
+  if (m0 >= NQv) return;
+  const int grow = m0 + row;
+  const int nch = (p.Rpad + CHs - 1) / CHs;
+  const bool has_rn = p.rnorm != nullptr;
+  const float c1 = p.rho1 * kLog2eS;
+
+  if (tid == 0) { ctl->abort_flag = 0; mbar_init(&ctl->bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&ctl->tmem_slot, 512);
+  if (tid < CHs) colacc[tid] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctl->tmem_slot;
+  const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  uint32_t phase = 0;
+  bool dq_started = false;
+
+  // one feature half of a [128 x D] operand (planes hi / lo, row-major, leading dimension D) -> the A buffer
+  auto stage_half = [&](const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long row0, long long n_valid, int h) {
+    stage_tile(Ah, kABlk, hi, D, row0, n_valid, TMs, h * L::kHalf, L::kHB);
+    stage_tile(Al, kABlk, lo, D, row0, n_valid, TMs, h * L::kHalf, L::kHB);
+    cp_async_wait_all();
+    fence_proxy_async_smem();
+    __syncthreads();
+  };
+  auto issue = [&](auto&& body) {                       // one elected thread issues, everybody waits for completion
+    if (warp == 0) {
+      if (elect_one()) { tc_fence_after(); body(); mma_commit(&ctl->bar); }
+      __syncwarp();
+    }
+    mbar_wait(&ctl->bar, phase, wc, 41); phase ^= 1;
+    tc_fence_after();
+  };
+  // [128 x 64] += A_half[128 x kHalf] . Khat_half^T : score product over one feature half
+  auto scores_half = [&](uint32_t d_col, int h, bool first) {
+    constexpr uint32_t idesc = idesc_bf16(TMs, CHs, false, false);
+#pragma unroll
+    for (int k = 0; k < L::kHalf / 16; ++k) {
+      const uint32_t ao = (k >> 2) * kABlk + (k & 3) * 32, bo = (h * L::kHB + (k >> 2)) * kKBlk + (k & 3) * 32;
+      mma3_ss(tmem + d_col, make_desc(smem_u32(Ah) + ao, 16, 1024), make_desc(smem_u32(Al) + ao, 16, 1024),
+              make_desc(smem_u32(Kh) + bo, 16, 1024), make_desc(smem_u32(Kl) + bo, 16, 1024), idesc, !(first && k == 0));
+    }
+  };
+  // dK^T[half] [kHalf x 64] (+)= A_half^T . Z   (A and Z as MN-major operands; contraction over the 128 word rows)
+  auto dk_half = [&](uint8_t* Zh, uint8_t* Zl, bool first) {
+    constexpr uint32_t idesc = idesc_bf16(L::kHalf, CHs, true, true);
+#pragma unroll
+    for (int kt = 0; kt < TMs / 16; ++kt) {
+      const uint32_t o = kt * 2048;
+      mma3_ss(tmem + L::kColDK, make_desc(smem_u32(Ah) + o, kABlk, 1024), make_desc(smem_u32(Al) + o, kABlk, 1024),
+              make_desc(smem_u32(Zh) + o, kABlk, 1024), make_desc(smem_u32(Zl) + o, kABlk, 1024), idesc, !(first && kt == 0));
+    }
+  };
+
+  for (int img = blockIdx.y; img < p.Bi; img += gridDim.y) {
+    float inv_l = 1.f, gam = 0.f, ngrl = 0.f;
+    if (grow < NQv) {
+      const size_t o = (size_t)img * p.NQ + grow;
+      const float inv_cn = 1.f / fmaxf(p.cnorm[o], kEps);
+      inv_l = 1.f / p.lsum[o];
+      gam = p.grel[o] * inv_cn;
+      ngrl = -gam * p.rel[o] * inv_cn * inv_l;          // the saved context is the unscaled sum C = l c
+    }
+    const long long crow0 = (long long)img * p.NQ + m0, cvalid = (long long)img * p.NQ + NQv;
+    for (int c = 0; c < nch; ++c) {
+      const int n = min(CHs, p.Rpad - c * CHs);
+      const long long krow0 = (long long)img * p.Rpad + c * CHs;
+      stage_tile(Kh, kKBlk, p.kh, D, krow0, krow0 + n, CHs, 0, D / 64);
+      stage_tile(Kl, kKBlk, p.kl, D, krow0, krow0 + n, CHs, 0, D / 64);
+      if (tid < CHs) rn_s[tid] = (has_rn && tid < n) ? __ldg(p.rnorm + (size_t)img * p.Rpad + c * CHs + tid) : (has_rn ? 0.f : 1.f);
+      // ---- S = Q Khat^T and W = C Khat^T, each over the two feature halves ----
+      for (int h = 0; h < 2; ++h) {
+        stage_half(p.qh, p.ql, m0, NQv, h);
+        issue([&] { scores_half(L::kColS, h, h == 0); });
+      }
+      for (int h = 0; h < 2; ++h) {
+        stage_half(p.ch, p.cl, crow0, cvalid, h);
+        issue([&] { scores_half(L::kColW, h, h == 0); });
+      }
+      // ---- X = dS + gamma alpha', Y = -gamma rel alpha' / (l |c|): this thread's 32 columns, split into hi / lo tiles ----
+      {
+        uint32_t sv[32], wv[32];
+        tmem_ld32(lane_base + L::kColS + half * 32, sv);
+        tmem_ld32(lane_base + L::kColW + half * 32, wv);
+        tmem_wait_ld();
+        const int r0 = c * CHs + half * 32;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float xv[8], yv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = u * 8 + e;
+            const float s = __uint_as_float(sv[j]), w = __uint_as_float(wv[j]);
+            const float al = (r0 + j) < p.R ? ex2f(fmaf(s, c1, -c1)) * inv_l : 0.f;          // alpha
+            const float alp = al * rn_s[half * 32 + j];                                     // alpha' = alpha |v_r|
+            const float dap = fmaf(ngrl, w, gam * s);                                       // d loss / d alpha'
+            xv[e] = alp * fmaf(p.rho1, dap, gam);
+            yv[e] = ngrl * alp;
+            if (has_rn) atomicAdd(colacc + half * 32 + j, al * dap);                        // -> d |v_r|
+          }
+          uint4 hi, lo;
+          split8(xv, hi, lo);
+          st_chunk16(Xh, row, half * 4 + u, hi); st_chunk16(Xl, row, half * 4 + u, lo);
+          split8(yv, hi, lo);
+          st_chunk16(Yh, row, half * 4 + u, hi); st_chunk16(Yl, row, half * 4 + u, lo);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (has_rn && tid < CHs) {
+        const int r = c * CHs + tid;
+        if (r < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r, colacc[tid]);
+        colacc[tid] = 0.f;
+      }
+      // ---- dQ += X Khat_chunk;  dK^T[half 1] = C_1^T Y (the A buffer still holds the second half of C) ----
+      issue([&] {
+        constexpr uint32_t idesc_dq = idesc_bf16(TMs, D, false, true);
+#pragma unroll
+        for (int ks = 0; ks < CHs / 16; ++ks) {
+          if (ks * 16 < n) {
+            const Desc xh = make_desc(smem_u32(Xh) + ks * 32, 16, 1024), xl = make_desc(smem_u32(Xl) + ks * 32, 16, 1024);
+            const Desc bh = make_desc(smem_u32(Kh) + ks * 2048, kKBlk, 1024), bl = make_desc(smem_u32(Kl) + ks * 2048, kKBlk, 1024);
+            mma3_ss(tmem + L::kColDQ, xh, xl, bh, bl, idesc_dq, dq_started || ks > 0);
+          }
+        }
+        dk_half(Yh, Yl, true);
+      });
+      dq_started = true;
+      // ---- the rest of dK^T, one feature half (= one M-tile) at a time: + Q_1^T X | drain | Q_0^T X + C_0^T Y | drain ----
+      for (int step = 0; step < 2; ++step) {
+        const int h = 1 - step;
+        stage_half(p.qh, p.ql, m0, NQv, h);
+        issue([&] { dk_half(Xh, Xl, h == 0); });
+        if (h == 0) {
+          stage_half(p.ch, p.cl, crow0, cvalid, 0);
+          issue([&] { dk_half(Yh, Yl, false); });
+        }
+        {   // thread = feature (TMEM lane) x 32 regions: a warp adds 32 consecutive features of one region row (128 bytes)
+          const int dl = (warp & 3) * 32 + lane;
+          if (dl < L::kHalf) {
+            uint32_t dv[32];
+            tmem_ld32(lane_base + L::kColDK + half * 32, dv);
+            tmem_wait_ld();
+            float* dst = p.dkn + ((size_t)img * p.Rpad + c * CHs + half * 32) * D + h * L::kHalf + dl;
+            const int nr = p.R - (c * CHs + half * 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nr) atomicAdd(dst + (size_t)j * D, __uint_as_float(dv[j]));
+          }
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+      }
+    }
+  }
+  // ---- dQ of this word tile (summed over the CTA's images) -> fp32 adds ----
+  if (dq_started) {
+#pragma unroll 1
+    for (int b = 0; b < D / 64; ++b) {
+      uint32_t dv[32];
+      tmem_ld32(lane_base + L::kColDQ + half * (D / 2) + b * 32, dv);
+      tmem_wait_ld();
+      if (grow < NQv) {
+        float* dst = p.dqn + (size_t)grow * D + half * (D / 2) + b * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(dv[4 * q])),
+                       "f"(__uint_as_float(dv[4 * q + 1])), "f"(__uint_as_float(dv[4 * q + 2])), "f"(__uint_as_float(dv[4 * q + 3]))
+                       : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// workspace: [64 B error word | qh | ql | kh | kl]   (bf16 planes, 16-byte aligned)
+struct Planes { __nv_bfloat16 *qh, *ql, *kh, *kl; };
+size_t plane_bytes(size_t n) { return (n * 2 + 255) & ~size_t(255); }
+Planes carve(void* ws, int NQ, int Bi, int Rpad, int D) {
+  uint8_t* b = static_cast<uint8_t*>(ws) + 64;
+  const size_t nq = plane_bytes((size_t)NQ * D), nk = plane_bytes((size_t)Bi * Rpad * D);
+  Planes pl;
+  pl.qh = reinterpret_cast<__nv_bfloat16*>(b); pl.ql = reinterpret_cast<__nv_bfloat16*>(b + nq);
+  pl.kh = reinterpret_cast<__nv_bfloat16*>(b + 2 * nq); pl.kl = reinterpret_cast<__nv_bfloat16*>(b + 2 * nq + nk);
+  return pl;
+}
+
+int split_operands(const WrParams& w, int D, const Planes& pl, cudaStream_t st) {
+  const size_t nq8 = (size_t)w.NQ * D / 8, nk8 = (size_t)w.Bi * w.Rpad * D / 8;
+  split_planes_kernel<<<(unsigned)std::min<size_t>((nq8 + 255) / 256, 148 * 8), 256, 0, st>>>(static_cast<const float*>(w.qn), nq8, pl.qh, pl.ql);
+  split_planes_kernel<<<(unsigned)std::min<size_t>((nk8 + 255) / 256, 148 * 8), 256, 0, st>>>(static_cast<const float*>(w.kn), nk8, pl.kh, pl.kl);
+  return cuda_fail(cudaGetLastError(), "split_planes_kernel launch");
+}
+
+// A CTA keeps one word tile and walks every `groups`-th image.  The number of live tiles is only known on the device
+// (compacted rows), so the grid cannot be sized to whole waves; four images per CTA keeps the tail below a few percent
+// (~1 500 CTAs at COCO-256) while a tile's operands (128 KB) are staged once per four images (320 KB of region chunks each).
+int grid_groups(int Bi) { return std::max(1, (Bi + 3) / 4); }
+
+SplitParams fill(const WrParams& w, const Planes& pl, void* ws, int D) {
+  SplitParams p{};
+  p.qh = pl.qh; p.ql = pl.ql; p.kh = pl.kh; p.kl = pl.kl;
+  p.ch = static_cast<__nv_bfloat16*>(w.chat);                        // two planes: hi [Bi, NQ, D], then lo
+  p.cl = w.chat ? p.ch + (size_t)w.Bi * w.NQ * D : nullptr;
+  p.rnorm = w.rnorm; p.NQ = w.NQ; p.Bi = w.Bi; p.R = w.R; p.Rpad = w.Rpad; p.nq_dev = w.nq_dev; p.rho1 = w.rho1;
+  p.lsum = w.lsum; p.cnorm = w.cnorm; p.rel = w.rel; p.grel = w.grel;
+  p.dqn = w.dqn; p.dkn = w.dkn; p.drnorm = w.drnorm;
+  p.err = static_cast<int*>(ws);
+  return p;
+}
+
+template <int D>
+int launch_fwd(const WrParams& w, void* ws, cudaStream_t st) {
+  const Planes pl = carve(ws, w.NQ, w.Bi, w.Rpad, D);
+  if (int rc = split_operands(w, D, pl, st)) return rc;
+  SplitParams p = fill(w, pl, ws, D);
+  const int tiles = (w.NQ + TMs - 1) / TMs;
+  dim3 grid(tiles, grid_groups(w.Bi));
+  XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_fwd_split_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdS<D>::kBytes));
+  wr_fwd_split_kernel<D><<<grid, kThreads, FwdS<D>::kBytes, st>>>(p);
+  return cuda_fail(cudaGetLastError(), "wr_fwd_split_kernel launch");
+}
+
+template <int D>
+int launch_bwd(const WrParams& w, void* ws, cudaStream_t st) {
+  const Planes pl = carve(ws, w.NQ, w.Bi, w.Rpad, D);
+  if (int rc = split_operands(w, D, pl, st)) return rc;
+  SplitParams p = fill(w, pl, ws, D);
+  const int tiles = (w.NQ + TMs - 1) / TMs;
+  dim3 grid(tiles, grid_groups(w.Bi));
+  XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_bwd_split_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdS<D>::kBytes));
+  wr_bwd_split_kernel<D><<<grid, kThreads, BwdS<D>::kBytes, st>>>(p);
+  return cuda_fail(cudaGetLastError(), "wr_bwd_split_kernel launch");
+}
+
+}  // namespace
+
+size_t wordregion_split_workspace_bytes(int NQ, int Bi, int, int Rpad, int D) {
+  return 64 + 2 * plane_bytes((size_t)NQ * D) + 2 * plane_bytes((size_t)Bi * Rpad * D);
+}
+
+int wordregion_split_forward(const WrParams& w, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+  XMC_REQUIRE(ws && ws_bytes >= wordregion_split_workspace_bytes(w.NQ, w.Bi, w.R, w.Rpad, D), XMC_ERR_WORKSPACE,
+              "workspace too small (%zu bytes)", ws_bytes);
+  if (D == 256) return launch_fwd<256>(w, ws, st);
+  set_error("split-bf16 word-region path supports D = 256 (got %d)", D);
+  return XMC_ERR_UNSUPPORTED;
+}
+
+int wordregion_split_backward(const WrParams& w, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+  XMC_REQUIRE(ws && ws_bytes >= wordregion_split_workspace_bytes(w.NQ, w.Bi, w.R, w.Rpad, D), XMC_ERR_WORKSPACE,
+              "workspace too small (%zu bytes)", ws_bytes);
+  XMC_REQUIRE(w.chat != nullptr, XMC_ERR_INVALID_ARG, "the split-bf16 backward needs the contexts saved by the forward (chat)");
+  if (D == 256) return launch_bwd<256>(w, ws, st);
+  set_error("split-bf16 word-region path supports D = 256 (got %d)", D);
+  return XMC_ERR_UNSUPPORTED;
+}
+
+}  // namespace xmc

@@ -289,7 +289,8 @@ def _join_side(ops, dev, *tensors, idx=0):
         ops.join_side(dev, *tensors, idx=idx)
 
 
-TC_BACKWARD_DIMS = (128, 256)   # D handled by the tcgen05 backward kernel (others: fp32 kernel)
+TC_BACKWARD_DIMS = (128, 256)   # D handled by the bf16 tcgen05 backward kernel (others: fp32 CUDA-core kernel)
+SPLIT_DIMS = (256,)             # D handled by the fp32-tolerance tcgen05 path (split-bf16 operands); others: CUDA cores
 # Saved attended contexts of the tcgen05 path: [images, word rows of the global batch, D] bf16 — O(B * B_global * T * D),
 # 0.6 GB at 256 x 256 x 18 x 256, 4.8 GB per rank at 8 x 256, 17 GB at 1024 x 1024 x 32.  Refuse to grow silently past this many bytes.
 MAX_CONTEXT_BYTES = 32 << 30
@@ -323,9 +324,9 @@ def _word_prepare_regions(ops, regions, precision):
     rows = _rows_view(regions) if hasattr(ops, "normalize_rows") else None
     if precision is None:
         precision = "bf16" if regions.dtype == torch.bfloat16 else "fp32"
-    if precision not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32', 'bf16' or None")
-    op_dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+    if precision not in ("fp32", "bf16", "fp32-simt"):
+        raise ValueError("precision must be 'fp32', 'bf16', 'fp32-simt' or None")
+    op_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
     if rows is not None:
         Bi, R, D = rows.shape
         Rpad = _ceil_to(R, 16)
@@ -344,8 +345,13 @@ def _word_local(ops, comm, prep, regions, w_all, m_all, labels, b_global, rho1, 
     if reg_dtype != w_all.dtype:
         raise TypeError(f"operand dtypes differ: {reg_dtype} vs {w_all.dtype}")
     Bc, _, T = w_all.shape
-    path = _lib.PATH_FP32_SIMT if precision == "fp32" else _lib.PATH_BF16_TCGEN05
-    use_tc_bwd = path == _lib.PATH_BF16_TCGEN05 and D in TC_BACKWARD_DIMS
+    if precision == "bf16":
+        path = _lib.PATH_BF16_TCGEN05
+    elif precision == "fp32" and D in SPLIT_DIMS and getattr(ops, "supports_split", False):
+        path = _lib.PATH_FP32_TCGEN05          # fp32 tolerance on the tensor cores: hi + lo bf16 operands, three MMAs per product
+    else:
+        path = _lib.PATH_FP32_SIMT             # "fp32-simt", or a width the split path does not take
+    use_tc_bwd = (path == _lib.PATH_BF16_TCGEN05 and D in TC_BACKWARD_DIMS) or path == _lib.PATH_FP32_TCGEN05
     # Padding words never contribute (excluded from the log-sum-exp, zero gradient): the kernels visit
     # only the valid word rows, compacted in caption-major order.  Their number stays on the device
     # (cap_ptr[Bc]); nothing here synchronises with the host.  (Not with the tcgen05 forward followed by
@@ -353,9 +359,10 @@ def _word_local(ops, comm, prep, regions, w_all, m_all, labels, b_global, rho1, 
     compact = (m_all is not None and (path == _lib.PATH_FP32_SIMT or use_tc_bwd or not need_grad)
                and getattr(ops, "supports_compaction", False))
     save_ctx = need_grad and use_tc_bwd
-    if save_ctx and Bi * Bc * T * D * 2 > MAX_CONTEXT_BYTES:
-        raise RuntimeError(f"word_loss would save {Bi * Bc * T * D * 2 / 2**30:.1f} GiB of attended contexts "
-                           f"([{Bi}, {Bc * T}, {D}] bf16) for its backward; raise xmc_gan_b200.losses.MAX_CONTEXT_BYTES "
+    ctx_bytes = Bi * Bc * T * D * (4 if path == _lib.PATH_FP32_TCGEN05 else 2)
+    if save_ctx and ctx_bytes > MAX_CONTEXT_BYTES:
+        raise RuntimeError(f"word_loss would save {ctx_bytes / 2**30:.1f} GiB of attended contexts "
+                           f"([{Bi}, {Bc * T}, {D}]) for its backward; raise xmc_gan_b200.losses.MAX_CONTEXT_BYTES "
                            "or split the batch")
     st = _Word()
     st.row_of = st.cap_ptr = nq_dev = None
@@ -419,7 +426,7 @@ def _word_backward(ops, st: _Word, go, need_reg, need_w):
     if st.compact:
         dqn, dkn, drnorm = ops.wordregion_backward(st.path, qn.view(-1, D), kn, rn, st.R, st.rho1, st.lsum, st.cnorm, st.rel,
                                                    grel, st.chat, nq_dev=st.cap_ptr[Bc:], bufs=bufs)
-    elif st.path == _lib.PATH_BF16_TCGEN05 and st.chat is None:
+    elif st.path == _lib.PATH_BF16_TCGEN05 and st.chat is None:       # (the split path always has its contexts: D = 256 only)
         # D outside the tcgen05 backward kernel's set: run the fp32 CUDA-core backward kernel on the
         # (bf16-rounded) operands the forward used.  Still libxmcloss, never PyTorch.
         dqn, dkn, drnorm = ops.wordregion_backward(_lib.PATH_FP32_SIMT, qn.view(-1, D).float(), kn.float(), rn, st.R,

@@ -301,6 +301,7 @@ class CudaOps:
     # -- word-region --------------------------------------------------------------------------
     use_sim_tc = True              # similarity-loss backward: hand the library a workspace (tensor-core form for large problems)
     supports_compaction = True     # the tcgen05 kernels visit only the non-padding word rows
+    supports_split = True          # fp32 tolerance on the tensor cores (XMC_PATH_FP32_TCGEN05, D = 256)
     use_side_stream = True         # word-side prologue / zero fills / word epilogue beside the main stream
 
     def word_rows_compact(self, mask_u8):
@@ -369,9 +370,16 @@ class CudaOps:
                 raise RuntimeError(f"{what}: pipeline wait timed out inside the kernel (code {code})")
 
     def _workspace(self, path, NQ, Bi, R, Rpad, D, dev):
-        """Caller-owned scratch of the tcgen05 path; word 0 is its error flag (0 = ok), so zero-filled."""
+        """Caller-owned scratch of the tcgen05 paths; word 0 is the kernel's error flag (0 = ok): the first 64 bytes are
+        zeroed (the split path's workspace also holds its operand planes, tens of MB that need no fill)."""
         n = self.L.xmc_wordregion_workspace_bytes(path, NQ, Bi, R, Rpad, D)
-        ws = torch.zeros(n, device=dev, dtype=torch.uint8) if n else None
+        if not n:
+            ws = None
+        elif n <= (1 << 20):
+            ws = torch.zeros(n, device=dev, dtype=torch.uint8)
+        else:
+            ws = torch.empty(n, device=dev, dtype=torch.uint8)
+            ws[:64].zero_()
         self.last_workspace = ws
         return ws, n
 
@@ -391,6 +399,8 @@ class CudaOps:
         chat = None
         if save_context and path == _lib.PATH_BF16_TCGEN05:
             chat = torch.empty(Bi, NQ, D, device=dev, dtype=torch.bfloat16)
+        elif save_context and path == _lib.PATH_FP32_TCGEN05:      # hi plane, lo plane
+            chat = torch.empty(2, Bi, NQ, D, device=dev, dtype=torch.bfloat16)
         ws, n = self._workspace(path, NQ, Bi, R, Rpad, D, dev)
         with _on(qn), self._timed("wordregion_fwd"):
             self._check(self.L.xmc_wordregion_forward(path, _p(qn), _p(kn), _p(rnorm), NQ, Bi, R, Rpad, D, float(rho1),

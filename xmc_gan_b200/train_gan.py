@@ -86,8 +86,9 @@ def word_loss(imgs, words, mask, labels, b_global, *, rho1=5.0, rho2=5.0, rho3=1
     imgs: region features ``[B, D, H, W]`` (or ``[B, D, R]``); words ``[B, D, T]`` and
     mask ``[B, T]`` (True = padding) as produced by the reference's encoders
     (``xmc_gan/model/encoder.py:61,68,140,149``).  Rows = images, cols = captions.
-    ``precision``: ``"fp32"`` (CUDA-core fp32, rel 1e-4) or ``"bf16"`` (tcgen05, bf16 operands,
-    fp32 accumulate, rel 2e-2); default follows the input dtype.
+    ``precision``: ``"fp32"`` (rel 1e-4: tcgen05 with every operand carried as a hi + lo bf16 pair for D = 256,
+    CUDA-core fp32 kernels otherwise or with ``"fp32-simt"``) or ``"bf16"`` (tcgen05, bf16 operands, fp32
+    accumulate, rel 2e-2); default follows the input dtype.
     """
     return _L.WordLossFn.apply(imgs, words, mask, labels, bool(b_global), float(rho1), float(rho2), float(rho3),
                                bool(normalize_values), precision, group, _ops or default_ops())
