@@ -70,14 +70,14 @@ def test_word_loss_fp32_on_tensor_cores_vs_oracle(B, T_, R, b_global, smooth):
         ro, wo = regions.double().requires_grad_(), words.double().requires_grad_()
         lo = oracle.word_loss(ro, wo, mask, lab_o, b_global, smooth)
         (1.3 * lo).backward()
+        # the CUDA-core form stays reachable
+        r2, w2 = regions.cuda().requires_grad_(), words.cuda().requires_grad_()
+        l2 = T.word_loss(r2, w2, mask.cuda(), labels, b_global, precision="fp32-simt")
+        (1.3 * l2).backward()
     finally:
         T.cfg.TRAIN.SMOOTH.GLOBAL = 0.5
     assert lerr(loss.detach(), lo.detach()) <= TOL_FP32
     assert nerr(r.grad, ro.grad) <= TOL_FP32 and nerr(w.grad, wo.grad) <= TOL_FP32, (nerr(r.grad, ro.grad), nerr(w.grad, wo.grad))
-    # the CUDA-core form stays reachable and agrees
-    r2, w2 = regions.cuda().requires_grad_(), words.cuda().requires_grad_()
-    l2 = T.word_loss(r2, w2, mask.cuda(), labels, b_global, precision="fp32-simt")
-    (1.3 * l2).backward()
     assert lerr(l2.detach(), lo.detach()) <= TOL_FP32 and nerr(r2.grad, ro.grad) <= TOL_FP32 and nerr(w2.grad, wo.grad) <= TOL_FP32
 
 
