@@ -321,7 +321,6 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
   uint8_t* Xh = smem + L::kOffXh; uint8_t* Xl = smem + L::kOffXl;
   uint8_t* Yh = smem + L::kOffYh; uint8_t* Yl = smem + L::kOffYl;
   float* rn_s = reinterpret_cast<float*>(smem + L::kOffRn);
-  float* colacc = reinterpret_cast<float*>(smem + L::kOffCol);
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + L::kOffCtl);
   const WaitCtx wc{&ctl->abort_flag, p.err};
 
@@ -337,7 +336,6 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
 
   if (tid == 0) { ctl->abort_flag = 0; mbar_init(&ctl->bar, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(&ctl->tmem_slot, 512);
-  if (tid < CHs) colacc[tid] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -415,6 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
         tmem_ld32(lane_base + L::kColW + half * 32, wv);
         tmem_wait_ld();
         const int r0 = c * CHs + half * 32;
+        float z[32];                                                                        // alpha * d alpha' -> d |v_r|
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float xv[8], yv[8];
@@ -427,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
             const float dap = fmaf(ngrl, w, gam * s);                                       // d loss / d alpha'
             xv[e] = alp * fmaf(p.rho1, dap, gam);
             yv[e] = ngrl * alp;
-            if (has_rn) atomicAdd(colacc + half * 32 + j, al * dap);                        // -> d |v_r|
+            z[j] = al * dap;
           }
           uint4 hi, lo;
           split8(xv, hi, lo);
@@ -435,15 +434,14 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
           split8(yv, hi, lo);
           st_chunk16(Yh, row, half * 4 + u, hi); st_chunk16(Yl, row, half * 4 + u, lo);
         }
+        if (has_rn) {                 // column sums over this warp's 32 word rows (31 shuffles), one add per column and warp
+          const float colsum = warp_transpose_sum32(z, lane);
+          if (r0 + lane < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r0 + lane, colsum);
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (has_rn && tid < CHs) {
-        const int r = c * CHs + tid;
-        if (r < p.R) atomicAdd(p.drnorm + (size_t)img * p.Rpad + r, colacc[tid]);
-        colacc[tid] = 0.f;
-      }
       // ---- dQ += X Khat_chunk;  dK^T[half 1] = C_1^T Y (the A buffer still holds the second half of C) ----
       issue([&] {
         constexpr uint32_t idesc_dq = idesc_bf16(TMs, D, false, true);

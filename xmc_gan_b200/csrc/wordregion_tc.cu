@@ -729,20 +729,6 @@ struct TcBwdParams {
                                // flag 8 = per-CTA {start ns, end ns, segments, images} after it
 };
 
-// lane L returns sum over the warp of v[L] (31 shuffles instead of 160)
-__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int k = 0; k < off; ++k) {
-      const float keep = hi ? v[k + off] : v[k];
-      const float send = hi ? v[k] : v[k + off];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
