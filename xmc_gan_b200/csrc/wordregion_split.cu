@@ -394,6 +394,8 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
     for (int c = 0; c < nch; ++c) {
       const int n = min(CHs, p.Rpad - c * CHs);
       const long long krow0 = (long long)img * p.Rpad + c * CHs;
+      if (tid < CHs) bulk_wait_read<0>();               // the previous chunk's reduce-adds have read their staging (the region tiles' bytes)
+      __syncthreads();
       stage_tile(Kh, kKBlk, p.kh, D, krow0, krow0 + n, CHs, 0, D / 64);
       stage_tile(Kl, kKBlk, p.kl, D, krow0, krow0 + n, CHs, 0, D / 64);
       if (tid < CHs) rn_s[tid] = (has_rn && tid < n) ? __ldg(p.rnorm + (size_t)img * p.Rpad + c * CHs + tid) : (has_rn ? 0.f : 1.f);
@@ -465,17 +467,24 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
           stage_half(p.ch, p.cl, crow0, cvalid, 0);
           issue([&] { dk_half(Yh, Yl, false); });
         }
-        {   // thread = feature (TMEM lane) x 32 regions: a warp adds 32 consecutive features of one region row (128 bytes)
-          const int dl = (warp & 3) * 32 + lane;
-          if (dl < L::kHalf) {
-            uint32_t dv[32];
-            tmem_ld32(lane_base + L::kColDK + half * 32, dv);
-            tmem_wait_ld();
-            float* dst = p.dkn + ((size_t)img * p.Rpad + c * CHs + half * 32) * D + h * L::kHalf + dl;
-            const int nr = p.R - (c * CHs + half * 32);
+        {   // dK^T[half h] [128 features x 64 regions] -> fp32 adds into dkn.  The region tiles are dead by now (dQ has
+            // executed), so their bytes stage the tile TRANSPOSED ([64 regions][128 features], one 32 KB buffer per half)
+            // and one bulk reduce-add per region row (512 contiguous bytes of dkn) carries it out asynchronously: scalar
+            // red instructions (64 per thread and chunk) were 40 % of this kernel's time.
+          float* stg = reinterpret_cast<float*>(Kh) + (size_t)h * CHs * L::kHalf;          // h = 1 -> second 32 KB
+          uint32_t dv[32];
+          tmem_ld32(lane_base + L::kColDK + half * 32, dv);
+          tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nr) atomicAdd(dst + (size_t)j * D, __uint_as_float(dv[j]));
+          for (int j = 0; j < 32; ++j) stg[(half * 32 + j) * L::kHalf + row] = __uint_as_float(dv[j]);   // bank = feature mod 32
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncthreads();
+          tc_fence_after();
+          if (tid < CHs) {
+            const int r = c * CHs + tid;
+            if (r < p.R) bulk_reduce_add_f32(p.dkn + ((size_t)img * p.Rpad + r) * D + h * L::kHalf, stg + tid * L::kHalf, L::kHalf * 4);
+            bulk_commit();
           }
         }
         tc_fence_before();
@@ -484,6 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
       }
     }
   }
+  if (tid < CHs) bulk_wait<0>();                       // every reduce-add into dkn has been performed
   // ---- dQ of this word tile (summed over the CTA's images) -> fp32 adds ----
   if (dq_started) {
 #pragma unroll 1
