@@ -39,3 +39,15 @@ out["valid_words"] = valid
 out["algorithmic_TFLOPs_bwd_split"] = round(8.0 * B * valid * R * D / (out["split_tcgen05_bwd_ms"] * 1e-3) / 1e12, 1)
 out["algorithmic_TFLOPs_fwd_split"] = round(4.0 * B * valid * R * D / (out["split_tcgen05_fwd_ms"] * 1e-3) / 1e12, 1)
 print(json.dumps(out))
+# phase breakdown of the backward (hooks build): cycles of CTA (0, 0) per phase, summed over its chunks
+from xmc_gan_b200.ops import CudaOps
+hops = CudaOps(lib=_lib.hooks_lib())
+l, c, r, chat = hops.wordregion_forward(_lib.PATH_FP32_TCGEN05, qn, kn, rnorm, R, 5.0, save_context=True, nq_dev=nq)
+hops.wordregion_backward(_lib.PATH_FP32_TCGEN05, qn, kn, rnorm, R, 5.0, l, c, r, torch.randn_like(l) * 0.01, chat, nq_dev=nq)
+torch.cuda.synchronize()
+ph = hops.last_workspace[16:16 + 8 * 10].view(torch.int64).tolist()
+names = ["stage regions", "stage Q halves (S)", "S MMAs", "stage C halves (W)", "W MMAs", "elementwise X, Y", "dQ + dK[1] C-part MMAs",
+         "stage halves (dK)", "dK MMAs", "dK drains"]
+tot = sum(ph)
+print(json.dumps({"backward_phase_cycles_cta0": {n: v for n, v in zip(names, ph)}, "total": tot,
+                  "chunks": 5 * len(range(0, B, max(1, (B + 3) // 4)))}))

@@ -110,6 +110,23 @@ struct SplitParams {
   int* err;
 };
 
+// Phase timing of CTA (0, 0), hooks build only (profiles/exp_split.py): cycles accumulated per phase into the
+// workspace header, [16 B error word | 8 B x 14 phases].
+#ifdef XMC_TEST_HOOKS
+#define XMC_PHASE(k)                                                                   \
+  do {                                                                                 \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {                      \
+      const long long t_ = clock64();                                                  \
+      reinterpret_cast<long long*>(p.err + 4)[k] += t_ - t_phase;                      \
+      t_phase = t_;                                                                    \
+    }                                                                                  \
+  } while (0)
+#define XMC_PHASE_INIT() long long t_phase = clock64()
+#else
+#define XMC_PHASE(k) do {} while (0)
+#define XMC_PHASE_INIT() do {} while (0)
+#endif
+
 struct Ctl {
   uint64_t bar;
   uint32_t tmem_slot;
@@ -343,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
   const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   uint32_t phase = 0;
   bool dq_started = false;
+  XMC_PHASE_INIT();
 
   // one feature half of a [128 x D] operand (planes hi / lo, row-major, leading dimension D) -> the A buffer
   auto stage_half = [&](const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long row0, long long n_valid, int h) {
@@ -399,14 +417,19 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
       stage_tile(Kh, kKBlk, p.kh, D, krow0, krow0 + n, CHs, 0, D / 64);
       stage_tile(Kl, kKBlk, p.kl, D, krow0, krow0 + n, CHs, 0, D / 64);
       if (tid < CHs) rn_s[tid] = (has_rn && tid < n) ? __ldg(p.rnorm + (size_t)img * p.Rpad + c * CHs + tid) : (has_rn ? 0.f : 1.f);
+      XMC_PHASE(0);
       // ---- S = Q Khat^T and W = C Khat^T, each over the two feature halves ----
       for (int h = 0; h < 2; ++h) {
         stage_half(p.qh, p.ql, m0, NQv, h);
+        XMC_PHASE(1);
         issue([&] { scores_half(L::kColS, h, h == 0); });
+        XMC_PHASE(2);
       }
       for (int h = 0; h < 2; ++h) {
         stage_half(p.ch, p.cl, crow0, cvalid, h);
+        XMC_PHASE(3);
         issue([&] { scores_half(L::kColW, h, h == 0); });
+        XMC_PHASE(4);
       }
       // ---- X = dS + gamma alpha', Y = -gamma rel alpha' / (l |c|): this thread's 32 columns, split into hi / lo tiles ----
       {
@@ -444,6 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
+      XMC_PHASE(5);
       // ---- dQ += X Khat_chunk;  dK^T[half 1] = C_1^T Y (the A buffer still holds the second half of C) ----
       issue([&] {
         constexpr uint32_t idesc_dq = idesc_bf16(TMs, D, false, true);
@@ -458,14 +482,19 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
         dk_half(Yh, Yl, true);
       });
       dq_started = true;
+      XMC_PHASE(6);
       // ---- the rest of dK^T, one feature half (= one M-tile) at a time: + Q_1^T X | drain | Q_0^T X + C_0^T Y | drain ----
       for (int step = 0; step < 2; ++step) {
         const int h = 1 - step;
         stage_half(p.qh, p.ql, m0, NQv, h);
+        XMC_PHASE(7);
         issue([&] { dk_half(Xh, Xl, h == 0); });
+        XMC_PHASE(8);
         if (h == 0) {
           stage_half(p.ch, p.cl, crow0, cvalid, 0);
+          XMC_PHASE(7);
           issue([&] { dk_half(Yh, Yl, false); });
+          XMC_PHASE(8);
         }
         {   // dK^T[half h] [128 features x 64 regions] -> fp32 adds into dkn.  The region tiles are dead by now (dQ has
             // executed), so their bytes stage the tile TRANSPOSED ([64 regions][128 features], one 32 KB buffer per half)
@@ -516,11 +545,11 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// workspace: [64 B error word | qh | ql | kh | kl]   (bf16 planes, 16-byte aligned)
+// workspace: [256 B header: error word, phase counters of the hooks build | qh | ql | kh | kl]   (bf16 planes, 256-byte aligned)
 struct Planes { __nv_bfloat16 *qh, *ql, *kh, *kl; };
 size_t plane_bytes(size_t n) { return (n * 2 + 255) & ~size_t(255); }
 Planes carve(void* ws, int NQ, int Bi, int Rpad, int D) {
-  uint8_t* b = static_cast<uint8_t*>(ws) + 64;
+  uint8_t* b = static_cast<uint8_t*>(ws) + 256;
   const size_t nq = plane_bytes((size_t)NQ * D), nk = plane_bytes((size_t)Bi * Rpad * D);
   Planes pl;
   pl.qh = reinterpret_cast<__nv_bfloat16*>(b); pl.ql = reinterpret_cast<__nv_bfloat16*>(b + nq);
@@ -579,7 +608,7 @@ int launch_bwd(const WrParams& w, void* ws, cudaStream_t st) {
 }  // namespace
 
 size_t wordregion_split_workspace_bytes(int NQ, int Bi, int, int Rpad, int D) {
-  return 64 + 2 * plane_bytes((size_t)NQ * D) + 2 * plane_bytes((size_t)Bi * Rpad * D);
+  return 256 + 2 * plane_bytes((size_t)NQ * D) + 2 * plane_bytes((size_t)Bi * Rpad * D);
 }
 
 int wordregion_split_forward(const WrParams& w, int D, void* ws, size_t ws_bytes, cudaStream_t st) {

@@ -379,7 +379,7 @@ class CudaOps:
             ws = torch.zeros(n, device=dev, dtype=torch.uint8)
         else:
             ws = torch.empty(n, device=dev, dtype=torch.uint8)
-            ws[:64].zero_()
+            ws[:256].zero_()
         self.last_workspace = ws
         return ws, n
 
