@@ -44,25 +44,15 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-// 16-byte asynchronous copy global -> shared; src_bytes = 0 zero-fills (rows past the end of the operand)
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
+// The operand planes are read by TMA: 3-D maps (feature, row, outer), boxes of 64 features x {128 word rows | 64 region rows},
+// 128B swizzle (the layout the UMMA descriptors expect); rows past the end of a plane's middle dimension arrive as zeros.
+struct Maps { CUtensorMap qh, ql, ch, cl, kh, kl; };
 
-// rows [row0, row0 + rows) x columns [col0, col0 + 64 nblk) of a row-major bf16 plane (leading dimension ld) ->
-// nblk swizzled blocks of [rows x 64], blk_bytes apart.  Rows at or past n_valid are zero-filled.
-__device__ __forceinline__ void stage_tile(uint8_t* dst, int blk_bytes, const __nv_bfloat16* src, size_t ld, long long row0,
-                                           long long n_valid, int rows, int col0, int nblk) {
-  const int per_row = nblk * 8;                       // 16-byte chunks per tile row
-  for (int idx = threadIdx.x; idx < rows * per_row; idx += kThreads) {
-    const int r = idx / per_row, rem = idx - r * per_row, b = rem >> 3, c = rem & 7;
-    const bool ok = row0 + r < n_valid;
-    const __nv_bfloat16* s = src + (size_t)(ok ? row0 + r : 0) * ld + col0 + b * 64 + c * 8;
-    cp_async16(dst + b * blk_bytes + r * 128 + ((c ^ (r & 7)) << 4), s, ok ? 16 : 0);
-  }
+// nblk boxes of [rows x 64 features] starting at feature block blk0, rows from row0 of slice `outer`, into consecutive
+// swizzled blocks blk_bytes apart; completion (bytes) on `bar`
+__device__ __forceinline__ void tma_tile(uint8_t* dst, int blk_bytes, const CUtensorMap* m, int blk0, int nblk, int row0, int outer,
+                                         uint64_t* bar) {
+  for (int b = 0; b < nblk; ++b) tma_load_3d(dst + b * blk_bytes, m, (blk0 + b) * 64, row0, outer, bar);
 }
 
 __device__ __forceinline__ void st_chunk16(uint8_t* blk, int r, int c, uint4 v) {
@@ -128,7 +118,8 @@ struct SplitParams {
 #endif
 
 struct Ctl {
-  uint64_t bar;
+  uint64_t bar;            // MMA completion
+  uint64_t ld;             // TMA completion
   uint32_t tmem_slot;
   int abort_flag;
 };
@@ -157,7 +148,7 @@ struct FwdS {
 };
 
 template <int D>
-__global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(SplitParams p) {
+__global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(const __grid_constant__ Maps maps, SplitParams p) {
   using L = FwdS<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1k(smem_raw);
@@ -178,29 +169,32 @@ __global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(SplitParams p
   const bool has_rn = p.rnorm != nullptr;
   const float c1 = p.rho1 * kLog2eS;
 
-  if (tid == 0) { ctl->abort_flag = 0; mbar_init(&ctl->bar, 1); fence_barrier_init(); }
+  if (tid == 0) { ctl->abort_flag = 0; mbar_init(&ctl->bar, 1); mbar_init(&ctl->ld, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(&ctl->tmem_slot, 512);
-  stage_tile(Qh, kABlk, p.qh, D, m0, NQv, TMs, 0, D / 64);
-  stage_tile(Ql, kABlk, p.ql, D, m0, NQv, TMs, 0, D / 64);
-  cp_async_wait_all();
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ctl->tmem_slot;
   const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  uint32_t phase = 0;
+  uint32_t phase = 0, ld_phase = 0;
+  if (tid == 0) {                                           // the word tile, hi and lo planes: resident for the CTA's lifetime
+    mbar_expect_tx(&ctl->ld, 2 * (D / 64) * kABlk);
+    tma_tile(Qh, kABlk, &maps.qh, 0, D / 64, m0, 0, &ctl->ld);
+    tma_tile(Ql, kABlk, &maps.ql, 0, D / 64, m0, 0, &ctl->ld);
+  }
+  mbar_wait(&ctl->ld, ld_phase, wc, 30); ld_phase ^= 1;
 
   for (int img = blockIdx.y; img < p.Bi; img += gridDim.y) {
     float l = 0.f, a = 0.f;
     for (int c = 0; c < nch; ++c) {
       const int n = min(CHs, p.Rpad - c * CHs);
-      const long long krow0 = (long long)img * p.Rpad + c * CHs;
-      stage_tile(Kh, kKBlk, p.kh, D, krow0, krow0 + n, CHs, 0, D / 64);
-      stage_tile(Kl, kKBlk, p.kl, D, krow0, krow0 + n, CHs, 0, D / 64);
+      if (tid == 0) {                                           // region chunk (rows past Rpad arrive as zeros)
+        mbar_expect_tx(&ctl->ld, 2 * (D / 64) * kKBlk);
+        tma_tile(Kh, kKBlk, &maps.kh, 0, D / 64, c * CHs, img, &ctl->ld);
+        tma_tile(Kl, kKBlk, &maps.kl, 0, D / 64, c * CHs, img, &ctl->ld);
+      }
       if (tid < CHs) rn_s[tid] = (has_rn && tid < n) ? __ldg(p.rnorm + (size_t)img * p.Rpad + c * CHs + tid) : 1.f;
-      cp_async_wait_all();
-      fence_proxy_async_smem();
+      mbar_wait(&ctl->ld, ld_phase, wc, 33); ld_phase ^= 1;
       __syncthreads();
       if (warp == 0) {
         if (elect_one()) {                                      // S = Q Khat^T, three MMAs per 16 features
@@ -281,9 +275,9 @@ __global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(SplitParams p
           float x[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) { x[e] = __uint_as_float(cv[8 * u + e]); c2 = fmaf(x[e], x[e], c2); }
-          if (grow < NQv && p.ch) {
-            uint4 hi, lo;
-            split8(x, hi, lo);
+          if (grow < p.NQ && p.ch) {                           // rows of a live tile past the count: zeros (the backward's TMA reads them)
+            uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+            if (grow < NQv) split8(x, hi, lo);
             *reinterpret_cast<uint4*>(p.ch + o + b * 32 + u * 8) = hi;
             *reinterpret_cast<uint4*>(p.cl + o + b * 32 + u * 8) = lo;
           }
@@ -329,7 +323,7 @@ struct BwdS {
 };
 
 template <int D>
-__global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p) {
+__global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_constant__ Maps maps, SplitParams p) {
   using L = BwdS<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1k(smem_raw);
@@ -351,24 +345,26 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
   const bool has_rn = p.rnorm != nullptr;
   const float c1 = p.rho1 * kLog2eS;
 
-  if (tid == 0) { ctl->abort_flag = 0; mbar_init(&ctl->bar, 1); fence_barrier_init(); }
+  if (tid == 0) { ctl->abort_flag = 0; mbar_init(&ctl->bar, 1); mbar_init(&ctl->ld, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(&ctl->tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ctl->tmem_slot;
   const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  uint32_t phase = 0;
+  uint32_t phase = 0, ld_phase = 0;
   bool dq_started = false;
   XMC_PHASE_INIT();
 
-  // one feature half of a [128 x D] operand (planes hi / lo, row-major, leading dimension D) -> the A buffer
-  auto stage_half = [&](const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long row0, long long n_valid, int h) {
-    stage_tile(Ah, kABlk, hi, D, row0, n_valid, TMs, h * L::kHalf, L::kHB);
-    stage_tile(Al, kABlk, lo, D, row0, n_valid, TMs, h * L::kHalf, L::kHB);
-    cp_async_wait_all();
-    fence_proxy_async_smem();
-    __syncthreads();
+  // one feature half of a [128 x D] operand (hi / lo planes) -> the A buffer.  Every MMA that read the buffer has been
+  // waited for by all threads (issue()), so one thread may refill it.
+  auto stage_half = [&](const CUtensorMap* hi, const CUtensorMap* lo, int row0, int outer, int h) {
+    if (tid == 0) {
+      mbar_expect_tx(&ctl->ld, 2 * L::kHB * kABlk);
+      tma_tile(Ah, kABlk, hi, h * L::kHB, L::kHB, row0, outer, &ctl->ld);
+      tma_tile(Al, kABlk, lo, h * L::kHB, L::kHB, row0, outer, &ctl->ld);
+    }
+    mbar_wait(&ctl->ld, ld_phase, wc, 40); ld_phase ^= 1;
   };
   auto issue = [&](auto&& body) {                       // one elected thread issues, everybody waits for completion
     if (warp == 0) {
@@ -408,25 +404,26 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
       gam = p.grel[o] * inv_cn;
       ngrl = -gam * p.rel[o] * inv_cn * inv_l;          // the saved context is the unscaled sum C = l c
     }
-    const long long crow0 = (long long)img * p.NQ + m0, cvalid = (long long)img * p.NQ + NQv;
     for (int c = 0; c < nch; ++c) {
       const int n = min(CHs, p.Rpad - c * CHs);
-      const long long krow0 = (long long)img * p.Rpad + c * CHs;
-      if (tid < CHs) bulk_wait_read<0>();               // the previous chunk's reduce-adds have read their staging (the region tiles' bytes)
-      __syncthreads();
-      stage_tile(Kh, kKBlk, p.kh, D, krow0, krow0 + n, CHs, 0, D / 64);
-      stage_tile(Kl, kKBlk, p.kl, D, krow0, krow0 + n, CHs, 0, D / 64);
+      if (tid == 0) {
+        mbar_expect_tx(&ctl->ld, 2 * (D / 64) * kKBlk);
+        tma_tile(Kh, kKBlk, &maps.kh, 0, D / 64, c * CHs, img, &ctl->ld);
+        tma_tile(Kl, kKBlk, &maps.kl, 0, D / 64, c * CHs, img, &ctl->ld);
+      }
       if (tid < CHs) rn_s[tid] = (has_rn && tid < n) ? __ldg(p.rnorm + (size_t)img * p.Rpad + c * CHs + tid) : (has_rn ? 0.f : 1.f);
+      mbar_wait(&ctl->ld, ld_phase, wc, 42); ld_phase ^= 1;
+      __syncthreads();                                  // rn_s visible
       XMC_PHASE(0);
       // ---- S = Q Khat^T and W = C Khat^T, each over the two feature halves ----
       for (int h = 0; h < 2; ++h) {
-        stage_half(p.qh, p.ql, m0, NQv, h);
+        stage_half(&maps.qh, &maps.ql, m0, 0, h);
         XMC_PHASE(1);
         issue([&] { scores_half(L::kColS, h, h == 0); });
         XMC_PHASE(2);
       }
       for (int h = 0; h < 2; ++h) {
-        stage_half(p.ch, p.cl, crow0, cvalid, h);
+        stage_half(&maps.ch, &maps.cl, m0, img, h);
         XMC_PHASE(3);
         issue([&] { scores_half(L::kColW, h, h == 0); });
         XMC_PHASE(4);
@@ -486,43 +483,35 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(SplitParams p
       // ---- the rest of dK^T, one feature half (= one M-tile) at a time: + Q_1^T X | drain | Q_0^T X + C_0^T Y | drain ----
       for (int step = 0; step < 2; ++step) {
         const int h = 1 - step;
-        stage_half(p.qh, p.ql, m0, NQv, h);
+        stage_half(&maps.qh, &maps.ql, m0, 0, h);
         XMC_PHASE(7);
         issue([&] { dk_half(Xh, Xl, h == 0); });
         XMC_PHASE(8);
         if (h == 0) {
-          stage_half(p.ch, p.cl, crow0, cvalid, 0);
+          stage_half(&maps.ch, &maps.cl, m0, img, 0);
           XMC_PHASE(7);
           issue([&] { dk_half(Yh, Yl, false); });
           XMC_PHASE(8);
         }
-        {   // dK^T[half h] [128 features x 64 regions] -> fp32 adds into dkn.  The region tiles are dead by now (dQ has
-            // executed), so their bytes stage the tile TRANSPOSED ([64 regions][128 features], one 32 KB buffer per half)
-            // and one bulk reduce-add per region row (512 contiguous bytes of dkn) carries it out asynchronously: scalar
-            // red instructions (64 per thread and chunk) were 40 % of this kernel's time.
-          float* stg = reinterpret_cast<float*>(Kh) + (size_t)h * CHs * L::kHalf;          // h = 1 -> second 32 KB
+        {   // thread = feature (TMEM lane) x 32 regions: a warp adds 32 consecutive features of one region row (128 bytes).
+            // (Staging the tile transposed in the dead region buffers and sending it out as one bulk reduce-add per
+            // region row was tried: 4.03 ms instead of 3.74 ms for the kernel.)
           uint32_t dv[32];
           tmem_ld32(lane_base + L::kColDK + half * 32, dv);
           tmem_wait_ld();
+          float* dst = p.dkn + ((size_t)img * p.Rpad + c * CHs + half * 32) * D + h * L::kHalf + row;
+          const int nr = p.R - (c * CHs + half * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg[(half * 32 + j) * L::kHalf + row] = __uint_as_float(dv[j]);   // bank = feature mod 32
-          fence_proxy_async_smem();
-          tc_fence_before();
-          __syncthreads();
-          tc_fence_after();
-          if (tid < CHs) {
-            const int r = c * CHs + tid;
-            if (r < p.R) bulk_reduce_add_f32(p.dkn + ((size_t)img * p.Rpad + r) * D + h * L::kHalf, stg + tid * L::kHalf, L::kHalf * 4);
-            bulk_commit();
-          }
+          for (int j = 0; j < 32; ++j)
+            if (j < nr) atomicAdd(dst + (size_t)j * D, __uint_as_float(dv[j]));
         }
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        XMC_PHASE(9);
       }
     }
   }
-  if (tid < CHs) bulk_wait<0>();                       // every reduce-add into dkn has been performed
   // ---- dQ of this word tile (summed over the CTA's images) -> fp32 adds ----
   if (dq_started) {
 #pragma unroll 1
@@ -564,6 +553,31 @@ int split_operands(const WrParams& w, int D, const Planes& pl, cudaStream_t st) 
   return cuda_fail(cudaGetLastError(), "split_planes_kernel launch");
 }
 
+typedef CUresult (*PFN_encodeTiledS)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// bf16 plane [outer][rows][D] as a 3-D tensor (feature, row, outer); box = 64 features x box_rows x 1, 128B swizzle
+int make_plane_map(CUtensorMap* m, const void* base, int outer, int rows, int D, int box_rows) {
+  static PFN_encodeTiledS enc = nullptr;
+  if (!enc) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<PFN_encodeTiledS>(ptr);
+  }
+  XMC_REQUIRE(enc != nullptr, XMC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)rows, (cuuint64_t)outer};
+  cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)rows * D * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XMC_REQUIRE(r == CUDA_SUCCESS, XMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return XMC_OK;
+}
+
 // A CTA keeps one word tile and walks every `groups`-th image.  The number of live tiles is only known on the device
 // (compacted rows), so the grid cannot be sized to whole waves; four images per CTA keeps the tail below a few percent
 // (~1 500 CTAs at COCO-256) while a tile's operands (128 KB) are staged once per four images (320 KB of region chunks each).
@@ -581,15 +595,28 @@ SplitParams fill(const WrParams& w, const Planes& pl, void* ws, int D) {
   return p;
 }
 
+int make_maps(Maps* m, const SplitParams& p, const WrParams& w, int D) {
+  if (int rc = make_plane_map(&m->qh, p.qh, 1, w.NQ, D, TMs)) return rc;
+  if (int rc = make_plane_map(&m->ql, p.ql, 1, w.NQ, D, TMs)) return rc;
+  if (int rc = make_plane_map(&m->kh, p.kh, w.Bi, w.Rpad, D, CHs)) return rc;
+  if (int rc = make_plane_map(&m->kl, p.kl, w.Bi, w.Rpad, D, CHs)) return rc;
+  // without saved contexts (forward only, no gradient wanted) the two maps are never used: point them at the words
+  if (int rc = make_plane_map(&m->ch, p.ch ? p.ch : p.qh, p.ch ? w.Bi : 1, w.NQ, D, TMs)) return rc;
+  if (int rc = make_plane_map(&m->cl, p.cl ? p.cl : p.ql, p.cl ? w.Bi : 1, w.NQ, D, TMs)) return rc;
+  return XMC_OK;
+}
+
 template <int D>
 int launch_fwd(const WrParams& w, void* ws, cudaStream_t st) {
   const Planes pl = carve(ws, w.NQ, w.Bi, w.Rpad, D);
   if (int rc = split_operands(w, D, pl, st)) return rc;
   SplitParams p = fill(w, pl, ws, D);
+  Maps maps;
+  if (int rc = make_maps(&maps, p, w, D)) return rc;
   const int tiles = (w.NQ + TMs - 1) / TMs;
   dim3 grid(tiles, grid_groups(w.Bi));
   XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_fwd_split_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdS<D>::kBytes));
-  wr_fwd_split_kernel<D><<<grid, kThreads, FwdS<D>::kBytes, st>>>(p);
+  wr_fwd_split_kernel<D><<<grid, kThreads, FwdS<D>::kBytes, st>>>(maps, p);
   return cuda_fail(cudaGetLastError(), "wr_fwd_split_kernel launch");
 }
 
@@ -598,10 +625,12 @@ int launch_bwd(const WrParams& w, void* ws, cudaStream_t st) {
   const Planes pl = carve(ws, w.NQ, w.Bi, w.Rpad, D);
   if (int rc = split_operands(w, D, pl, st)) return rc;
   SplitParams p = fill(w, pl, ws, D);
+  Maps maps;
+  if (int rc = make_maps(&maps, p, w, D)) return rc;
   const int tiles = (w.NQ + TMs - 1) / TMs;
   dim3 grid(tiles, grid_groups(w.Bi));
   XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(wr_bwd_split_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdS<D>::kBytes));
-  wr_bwd_split_kernel<D><<<grid, kThreads, BwdS<D>::kBytes, st>>>(p);
+  wr_bwd_split_kernel<D><<<grid, kThreads, BwdS<D>::kBytes, st>>>(maps, p);
   return cuda_fail(cudaGetLastError(), "wr_bwd_split_kernel launch");
 }
 
