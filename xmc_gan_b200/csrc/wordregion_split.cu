@@ -119,7 +119,8 @@ struct SplitParams {
 
 struct Ctl {
   uint64_t bar;            // MMA completion
-  uint64_t ld;             // TMA completion
+  uint64_t ld;             // TMA completion (word / context tiles)
+  uint64_t ldk;            // TMA completion (region chunks: in flight under other work in the backward)
   uint32_t tmem_slot;
   int abort_flag;
 };
@@ -345,14 +346,14 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
   const bool has_rn = p.rnorm != nullptr;
   const float c1 = p.rho1 * kLog2eS;
 
-  if (tid == 0) { ctl->abort_flag = 0; mbar_init(&ctl->bar, 1); mbar_init(&ctl->ld, 1); fence_barrier_init(); }
+  if (tid == 0) { ctl->abort_flag = 0; mbar_init(&ctl->bar, 1); mbar_init(&ctl->ld, 1); mbar_init(&ctl->ldk, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(&ctl->tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ctl->tmem_slot;
   const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  uint32_t phase = 0, ld_phase = 0;
+  uint32_t phase = 0, ld_phase = 0, ldk_phase = 0;
   bool dq_started = false;
   XMC_PHASE_INIT();
 
@@ -395,6 +396,28 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
     }
   };
 
+  // Region chunk (c_, img_) -> the region buffers, asynchronously (TMA); its norms -> rn_s.  Called once the previous
+  // chunk's dQ product has executed (the last reader of the buffers); wait_regions() before the first use.
+  auto load_regions = [&](int img_, int c_) {
+    const int n_ = min(CHs, p.Rpad - c_ * CHs);
+    if (tid == 0) {
+      mbar_expect_tx(&ctl->ldk, 2 * (D / 64) * kKBlk);
+      tma_tile(Kh, kKBlk, &maps.kh, 0, D / 64, c_ * CHs, img_, &ctl->ldk);
+      tma_tile(Kl, kKBlk, &maps.kl, 0, D / 64, c_ * CHs, img_, &ctl->ldk);
+    }
+    if (tid < CHs) rn_s[tid] = (has_rn && tid < n_) ? __ldg(p.rnorm + (size_t)img_ * p.Rpad + c_ * CHs + tid) : (has_rn ? 0.f : 1.f);
+  };
+  auto wait_regions = [&]() { mbar_wait(&ctl->ldk, ldk_phase, wc, 42); ldk_phase ^= 1; };
+
+  // Order of one chunk c (S, W of the chunk already in tensor memory, the A buffer holding the second half of C):
+  //   elementwise X, Y | dQ(c) + dK^T[1] = C_1^T Y | prefetch regions(c+1)
+  //   A <- Q_1:  dK^T[1] += Q_1^T X,  S(c+1)  = Q_1 K_1^T      | drain dK^T[1]
+  //   A <- Q_0:  dK^T[0]  = Q_0^T X,  S(c+1) += Q_0 K_0^T
+  //   A <- C_0:  dK^T[0] += C_0^T Y,  W(c+1)  = C_0 K_0^T      | drain dK^T[0]
+  //   A <- C_1:                       W(c+1) += C_1 K_1^T
+  // so every staged half serves a dK^T product of chunk c AND a score product of chunk c+1: four stagings per chunk
+  // instead of seven, and the region chunk arrives under them.  The first chunk of an image computes its scores alone.
+  bool regions_pending = false;
   for (int img = blockIdx.y; img < p.Bi; img += gridDim.y) {
     float inv_l = 1.f, gam = 0.f, ngrl = 0.f;
     if (grow < NQv) {
@@ -404,30 +427,27 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
       gam = p.grel[o] * inv_cn;
       ngrl = -gam * p.rel[o] * inv_cn * inv_l;          // the saved context is the unscaled sum C = l c
     }
+    // ---- scores of the image's first chunk ----
+    if (!regions_pending) load_regions(img, 0);
+    wait_regions();
+    regions_pending = false;
+    XMC_PHASE(0);
+    for (int h = 0; h < 2; ++h) {
+      stage_half(&maps.qh, &maps.ql, m0, 0, h);
+      XMC_PHASE(1);
+      issue([&] { scores_half(L::kColS, h, h == 0); });
+      XMC_PHASE(2);
+    }
+    for (int h = 0; h < 2; ++h) {
+      stage_half(&maps.ch, &maps.cl, m0, img, h);
+      XMC_PHASE(3);
+      issue([&] { scores_half(L::kColW, h, h == 0); });
+      XMC_PHASE(4);
+    }
     for (int c = 0; c < nch; ++c) {
       const int n = min(CHs, p.Rpad - c * CHs);
-      if (tid == 0) {
-        mbar_expect_tx(&ctl->ld, 2 * (D / 64) * kKBlk);
-        tma_tile(Kh, kKBlk, &maps.kh, 0, D / 64, c * CHs, img, &ctl->ld);
-        tma_tile(Kl, kKBlk, &maps.kl, 0, D / 64, c * CHs, img, &ctl->ld);
-      }
-      if (tid < CHs) rn_s[tid] = (has_rn && tid < n) ? __ldg(p.rnorm + (size_t)img * p.Rpad + c * CHs + tid) : (has_rn ? 0.f : 1.f);
-      mbar_wait(&ctl->ld, ld_phase, wc, 42); ld_phase ^= 1;
-      __syncthreads();                                  // rn_s visible
-      XMC_PHASE(0);
-      // ---- S = Q Khat^T and W = C Khat^T, each over the two feature halves ----
-      for (int h = 0; h < 2; ++h) {
-        stage_half(&maps.qh, &maps.ql, m0, 0, h);
-        XMC_PHASE(1);
-        issue([&] { scores_half(L::kColS, h, h == 0); });
-        XMC_PHASE(2);
-      }
-      for (int h = 0; h < 2; ++h) {
-        stage_half(&maps.ch, &maps.cl, m0, img, h);
-        XMC_PHASE(3);
-        issue([&] { scores_half(L::kColW, h, h == 0); });
-        XMC_PHASE(4);
-      }
+      const bool more = c + 1 < nch;                    // another chunk of this image follows: its scores ride along
+      __syncthreads();                                  // rn_s of this chunk visible
       // ---- X = dS + gamma alpha', Y = -gamma rel alpha' / (l |c|): this thread's 32 columns, split into hi / lo tiles ----
       {
         uint32_t sv[32], wv[32];
@@ -480,35 +500,52 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
       });
       dq_started = true;
       XMC_PHASE(6);
-      // ---- the rest of dK^T, one feature half (= one M-tile) at a time: + Q_1^T X | drain | Q_0^T X + C_0^T Y | drain ----
-      for (int step = 0; step < 2; ++step) {
-        const int h = 1 - step;
-        stage_half(&maps.qh, &maps.ql, m0, 0, h);
-        XMC_PHASE(7);
-        issue([&] { dk_half(Xh, Xl, h == 0); });
-        XMC_PHASE(8);
-        if (h == 0) {
-          stage_half(&maps.ch, &maps.cl, m0, img, 0);
-          XMC_PHASE(7);
-          issue([&] { dk_half(Yh, Yl, false); });
-          XMC_PHASE(8);
-        }
-        {   // thread = feature (TMEM lane) x 32 regions: a warp adds 32 consecutive features of one region row (128 bytes).
-            // (Staging the tile transposed in the dead region buffers and sending it out as one bulk reduce-add per
-            // region row was tried: 4.03 ms instead of 3.74 ms for the kernel.)
-          uint32_t dv[32];
-          tmem_ld32(lane_base + L::kColDK + half * 32, dv);
-          tmem_wait_ld();
-          float* dst = p.dkn + ((size_t)img * p.Rpad + c * CHs + half * 32) * D + h * L::kHalf + row;
-          const int nr = p.R - (c * CHs + half * 32);
+      // the region buffers are free: the next chunk (of this image, or the first of the CTA's next image) lands under the rest
+      {
+        const int nimg = more ? img : img + (int)gridDim.y, nc = more ? c + 1 : 0;
+        if (nimg < p.Bi) { load_regions(nimg, nc); regions_pending = true; }
+      }
+      // ---- A <- Q_1: dK^T[1] += Q_1^T X; S(c+1) = Q_1 K_1^T ----
+      stage_half(&maps.qh, &maps.ql, m0, 0, 1);
+      if (more) { wait_regions(); regions_pending = false; }    // both loads were in flight together
+      XMC_PHASE(7);
+      issue([&] { dk_half(Xh, Xl, false); if (more) scores_half(L::kColS, 1, true); });
+      XMC_PHASE(8);
+      auto drain = [&](int h) {   // thread = feature (TMEM lane) x 32 regions: a warp adds 32 consecutive features of one region
+                                  // row (128 bytes).  (Staging the tile transposed in the dead region buffers and one bulk
+                                  // reduce-add per region row was tried: 4.03 ms instead of 3.74 ms for the kernel.)
+        uint32_t dv[32];
+        tmem_ld32(lane_base + L::kColDK + half * 32, dv);
+        tmem_wait_ld();
+        float* dst = p.dkn + ((size_t)img * p.Rpad + c * CHs + half * 32) * D + h * L::kHalf + row;
+        const int nr = p.R - (c * CHs + half * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nr) atomicAdd(dst + (size_t)j * D, __uint_as_float(dv[j]));
-        }
+        for (int j = 0; j < 32; ++j)
+          if (j < nr) atomicAdd(dst + (size_t)j * D, __uint_as_float(dv[j]));
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        XMC_PHASE(9);
+      };
+      drain(1);
+      XMC_PHASE(9);
+      // ---- A <- Q_0: dK^T[0] = Q_0^T X; S(c+1) += Q_0 K_0^T ----
+      stage_half(&maps.qh, &maps.ql, m0, 0, 0);
+      XMC_PHASE(7);
+      issue([&] { dk_half(Xh, Xl, true); if (more) scores_half(L::kColS, 0, false); });
+      XMC_PHASE(8);
+      // ---- A <- C_0: dK^T[0] += C_0^T Y; W(c+1) = C_0 K_0^T ----
+      stage_half(&maps.ch, &maps.cl, m0, img, 0);
+      XMC_PHASE(7);
+      issue([&] { dk_half(Yh, Yl, false); if (more) scores_half(L::kColW, 0, true); });
+      XMC_PHASE(8);
+      drain(0);
+      XMC_PHASE(9);
+      // ---- A <- C_1: W(c+1) += C_1 K_1^T (and the buffer is where the next chunk's dK^T[1] expects the second half of C) ----
+      if (more) {
+        stage_half(&maps.ch, &maps.cl, m0, img, 1);
+        XMC_PHASE(3);
+        issue([&] { scores_half(L::kColW, 1, false); });
+        XMC_PHASE(4);
       }
     }
   }
