@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define XMC_ABI_VERSION 5
+#define XMC_ABI_VERSION 6
 
 typedef enum {
   XMC_OK = 0,
@@ -210,6 +210,29 @@ int xmc_normalize_rows(const void* x, int B, int D, int L, int Lpad, int in_dtyp
 int xmc_normalize_rows_backward(const void* xn, const float* norm, const float* dxn, const float* dnorm,
                                 int B, int D, int L, int Lpad, int xn_dtype, int out_dtype,
                                 const int* error_word, void* dx, void* stream);
+
+/* Region head fused into the word loss's prologue.  The regions the word loss attends over are a 1x1
+ * convolution of the discriminator's 16 x 16 stage (xmc_gan/model/df_gan.py:106-132 produces the [B, Cin, 16, 16] map;
+ * the head is the region-side counterpart of proj_match, df_gan.py:143-145, 165-168; the consumer is the word loss named
+ * at xmc_gan/train_gan.py:220-222, 267-269).  One tcgen05 kernel computes y_b = feat_b^T W^T + bias per image and leaves
+ * ONLY what the word-region kernels read: kn[B, Rpad, D] bf16 unit rows and rnorm[B, Rpad] = max(||y_r||, 1e-12)
+ * (rows R..Rpad-1 zero) — the same outputs as xmc_normalize_rows on y, without y ever reaching HBM.
+ *   feat   [B, Cin, R]  fp32 or bf16, NCHW as the discriminator writes it (R = H*W contiguous)
+ *   weight [D, Cin]     fp32 or bf16 (a Conv2d(Cin, D, 1) weight, or its spectral-normalised value), bias [D] fp32 or NULL
+ * D = 256; operands are rounded to bf16 on the way into shared memory, fp32 accumulation (the bf16 tolerance, 2e-2).
+ * A timed-out pipeline wait inside the kernel turns rnorm (hence the loss) into NaN. */
+int xmc_region_head_forward(const void* feat, int feat_dtype, const void* weight, int weight_dtype,
+                            const float* bias, int B, int Cin, int R, int Rpad, int D,
+                            void* kn, float* rnorm, void* stream);
+/* Backward of the head given dy[B, R, D] bf16 = d loss / d y (xmc_normalize_rows_backward applied to the word-region
+ * kernels' dkn / drnorm, out_dtype XMC_BF16):
+ *   _input : dfeat[B, Cin, R] = W^T dy_b^T, written in feat's layout and in out_dtype;
+ *   _weight: dweight[D, Cin] fp32 = sum_b dy_b^T feat_b^T and dbias[D] fp32 = sum_{b,r} dy (nullable); both are
+ *            zero-filled by the call (cudaMemsetAsync on `stream`) and accumulated with fp32 reductions. */
+int xmc_region_head_backward_input(const void* weight, int weight_dtype, const void* dy, int B, int Cin, int R,
+                                   int D, void* dfeat, int out_dtype, void* stream);
+int xmc_region_head_backward_weight(const void* feat, int feat_dtype, const void* dy, int B, int Cin, int R, int D,
+                                    float* dweight, float* dbias, void* stream);
 
 size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad, int D);
 

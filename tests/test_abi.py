@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_version_and_error_string(built):
     L = _lib.lib()
-    assert L.xmc_version() == 5
+    assert L.xmc_version() == 6
     assert isinstance(L.xmc_last_error(), bytes)
 
 

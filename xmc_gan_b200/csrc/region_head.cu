@@ -1,0 +1,483 @@
+// region_head.cu — the producer of the word loss's region operand, fused into the loss prologue.
+//
+// The word loss attends over region features that a 1x1 convolution ("region head") projects out of the
+// discriminator's 16 x 16 stage (xmc_gan/model/df_gan.py:106-132 produces the [B, 512, 16, 16] map; the head is the
+// region-side counterpart of proj_match, df_gan.py:143-145, 165-168).  Unfused, that is a convolution writing
+// y[B, D, H, W], a layout kernel re-reading it and writing unit rows — the region map crosses HBM three times.  Here
+//
+//   forward   y_b = feat_b^T W^T + bias   (M = pixels, N = D = 256, K = Cin)  ->  epilogue: ||y_r||, unit rows
+//             kn[B, Rpad, D] bf16 + rnorm[B, Rpad] fp32, exactly what wr_fwd_tc_kernel / wr_bwd_tc_kernel consume;
+//             y itself never reaches HBM.
+//   backward  dy[B, R, D] (bf16, from xmc_normalize_rows_backward on the word-region kernels' dkn / drnorm):
+//             dfeat_b = W^T dy_b^T        (M = Cin, N = pixels, K = D)        written in feat's own [B, Cin, H, W] layout
+//             dW      = sum_b dy_b^T feat_b^T (M = D, N = Cin, K = B * R)     split over CTAs, fp32 red into dW
+//             dbias   = sum_{b,r} dy      column sums taken from the staged A tiles of the dW kernel
+//
+// All three products have ONE operand form on the tensor cores: C[m, n] = sum_k A[k, m] * B[n, k] with A stored
+// [K rows][M contiguous] (MN-major smem tile) and B stored [N rows][K contiguous] (K-major tile) — feat_b is
+// [Cin][pixels], W is [D][Cin], dy_b is [pixels][D]: every operand is consumed where it lies, no transposes.
+// Operands are fp32 or bf16 in HBM and always bf16 in shared memory: the CTA's staging warps convert on the way
+// (global -> registers -> bf16 -> 128B-swizzled smem), so an fp32 discriminator needs no cast pass.  fp32
+// accumulation in TMEM (two 256-column accumulators: the epilogue of one tile runs under the MMAs of the next).
+//
+// Roofline: HBM.  Forward at B = 256, 16 x 16, Cin = 512, D = 256: 134 MB (fp32 map) or 67 MB (bf16) in + 33.6 MB
+// out against 17.2 GFLOP (12 us of tensor time); the staging path is sized for bytes in flight, not for the MMAs.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace xmc {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kM = 128, kN = 256, kKB = 64, kStages = 4;
+constexpr int kABlock = kKB * 128;                 // [64 k rows x 64 m] bf16, 128-byte rows
+constexpr int kABytes = 2 * kABlock;               // 16 KB
+constexpr int kBBytes = kN * 128;                  // [256 n rows x 64 k] bf16 = 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;     // 48 KB
+constexpr int kEpiWarps = 4, kMmaWarp = 4, kStageWarp0 = 5, kStageWarps = 8;
+constexpr int kStageThreads = kStageWarps * 32;    // 256
+constexpr int kThreads = (kStageWarp0 + kStageWarps) * 32;   // 416
+constexpr int kAccCols = 256;
+
+enum Mode { kFwd = 0, kDFeat = 1, kDW = 2 };
+
+struct HeadParams {
+  const void* a; long long a_batch; int lda; int a_bf16;   // A_b[k][m], m contiguous
+  const void* b; long long b_batch; int ldb; int b_bf16;   // B_b[n][k], k contiguous
+  int M, N, K;                 // valid extents of one batch item's product
+  int m_tiles, n_tiles, batches, splits;
+  // forward
+  const float* bias; __nv_bfloat16* kn; float* rnorm; int R, Rpad;
+  // dfeat
+  void* dfeat; int out_bf16;   // [B, M = Cin, N = R]
+  // dW
+  float* dw; float* dbias;     // [M = D, N = Cin] fp32, [D]
+  int* err;
+};
+
+struct HeadShared {
+  uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+  uint32_t tmem_slot;
+  int abort_flag;
+  float bias[kN];
+  float colsum[kM];
+};
+
+// one work item = one accumulator tile: (m0, n0) and the batch items [b0, b1) it sums over
+struct Item { int m0, n0, b0, b1, out_b; };
+
+template <int MODE>
+__device__ __forceinline__ Item decode_item(const HeadParams& p, int item) {
+  Item it;
+  if (MODE == kDW) {
+    const int s = item % p.splits, t = item / p.splits;
+    const int per = (p.batches + p.splits - 1) / p.splits;
+    it.m0 = (t / p.n_tiles) * kM; it.n0 = (t % p.n_tiles) * kN;
+    it.b0 = s * per; it.b1 = min(p.batches, it.b0 + per); it.out_b = 0;
+  } else {
+    const int nt = item % p.n_tiles, t = item / p.n_tiles;
+    it.m0 = (t % p.m_tiles) * kM; it.n0 = nt * kN;
+    it.b0 = t / p.m_tiles; it.b1 = it.b0 + 1; it.out_b = it.b0;
+  }
+  return it;
+}
+
+// Four 8-element chunks of one operand, as they come out of global memory: fp32 -> two uint4 per chunk, bf16 -> one.
+struct Raw { uint4 v[8]; };
+
+// 8 elements src[0..8) of a row, `valid` (0..8) of them inside the matrix, rest zero
+__device__ __forceinline__ void load_chunk(const void* base, long long off, int valid, bool bf16, bool vec_ok, uint4& r0, uint4& r1) {
+  if (bf16) {
+    const __nv_bfloat16* s = static_cast<const __nv_bfloat16*>(base) + off;
+    if (valid >= 8 && vec_ok) { r0 = __ldg(reinterpret_cast<const uint4*>(s)); return; }
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (e < valid) w[e >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(s[e])) << ((e & 1) * 16);
+    r0 = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    const float* s = static_cast<const float*>(base) + off;
+    if (valid >= 8 && vec_ok) {
+      r0 = __ldg(reinterpret_cast<const uint4*>(s)); r1 = __ldg(reinterpret_cast<const uint4*>(s) + 1);
+      return;
+    }
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = e < valid ? __ldg(s + e) : 0.f;
+    r0 = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+    r1 = make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7]));
+  }
+}
+__device__ __forceinline__ uint4 to_bf16x8(bool bf16, const uint4& r0, const uint4& r1) {
+  if (bf16) return r0;
+  return make_uint4(pack_bf16(__uint_as_float(r0.x), __uint_as_float(r0.y)), pack_bf16(__uint_as_float(r0.z), __uint_as_float(r0.w)),
+                    pack_bf16(__uint_as_float(r1.x), __uint_as_float(r1.y)), pack_bf16(__uint_as_float(r1.z), __uint_as_float(r1.w)));
+}
+__device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, uint4 v) {
+  *reinterpret_cast<uint4*>(blk + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+}
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  HeadShared* sh = reinterpret_cast<HeadShared*>(smem + kStages * kStageBytes);
+  const WaitCtx wc{&sh->abort_flag, p.err};
+
+  const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
+  const int n_items = (MODE == kDW ? p.m_tiles * p.n_tiles * p.splits : p.batches * p.m_tiles * p.n_tiles);
+  const int kbpb = (p.K + kKB - 1) / kKB;                     // k-blocks per batch item
+
+  if (tid == 0) {
+    sh->abort_flag = 0;
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], kStageThreads); mbar_init(&sh->empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->acc_full[i], 1); mbar_init(&sh->acc_empty[i], kEpiWarps * 32); }
+    fence_barrier_init();
+  }
+  if (MODE == kFwd)
+    for (int i = tid; i < kN; i += kThreads) sh->bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+  if (MODE == kDW && tid < kM) sh->colsum[tid] = 0.f;
+  if (warp == kMmaWarp) tmem_alloc(&sh->tmem_slot, 2 * kAccCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_slot;
+
+  if (warp >= kStageWarp0) {
+    // =============================== staging warps: global -> bf16 -> swizzled smem ===============================
+    const int t = tid - kStageWarp0 * 32;                      // 0..255
+    const bool a_bf16 = p.a_bf16 != 0, b_bf16 = p.b_bf16 != 0;
+    const bool a_vec = (p.lda % (a_bf16 ? 8 : 4) == 0) && (p.a_batch % (a_bf16 ? 8 : 4) == 0);
+    const bool b_vec = (p.ldb % (b_bf16 ? 8 : 4) == 0) && (p.b_batch % (b_bf16 ? 8 : 4) == 0);
+    const int a_o = t & 15, a_k = t >> 4;                      // A chunk: m octet, k row (+16 per chunk)
+    const int b_j = t & 7, b_n = t >> 3;                       // B chunk: k octet, n row (+32 per chunk)
+    float cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+    uint32_t stage = 0, phase = 0;
+
+    // group g of a k-block: 0 = the four A chunks, 1 / 2 = B chunks 0-3 / 4-7
+    auto issue = [&](const Item& it, int step, int g, Raw& raw) {
+      const int b = it.b0 + step / kbpb, k0 = (step % kbpb) * kKB;
+      if (g == 0) {
+        const int m = it.m0 + a_o * 8;
+        const int valid_m = max(0, min(8, p.M - m));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = k0 + a_k + 16 * c;
+          const int valid = k < p.K ? valid_m : 0;
+          load_chunk(p.a, (long long)b * p.a_batch + (long long)k * p.lda + m, valid, a_bf16, a_vec, raw.v[2 * c], raw.v[2 * c + 1]);
+        }
+      } else {
+        const int k = k0 + b_j * 8;
+        const int valid_k = max(0, min(8, p.K - k));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int n = it.n0 + b_n + 32 * (c + 4 * (g - 1));
+          const int valid = n < p.N ? valid_k : 0;
+          load_chunk(p.b, (long long)b * p.b_batch + (long long)n * p.ldb + k, valid, b_bf16, b_vec, raw.v[2 * c], raw.v[2 * c + 1]);
+        }
+      }
+    };
+    auto commit = [&](const Item& it, int g, const Raw& raw) {
+      uint8_t* sa = smem + stage * kStageBytes;
+      uint8_t* sb = sa + kABytes;
+      if (g == 0) {
+        mbar_wait(&sh->empty[stage], phase ^ 1, wc, 11);        // the MMAs that read this stage are done
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 v = to_bf16x8(a_bf16, raw.v[2 * c], raw.v[2 * c + 1]);
+          st_chunk(sa + (a_o >> 3) * kABlock, a_k + 16 * c, a_o & 7, v);
+          if (MODE == kDW && p.dbias && it.n0 == 0) {           // column sums of dy: every dy element passes here once
+            cs[0] += bf16lo(v.x); cs[1] += bf16hi(v.x); cs[2] += bf16lo(v.y); cs[3] += bf16hi(v.y);
+            cs[4] += bf16lo(v.z); cs[5] += bf16hi(v.z); cs[6] += bf16lo(v.w); cs[7] += bf16hi(v.w);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          st_chunk(sb, b_n + 32 * (c + 4 * (g - 1)), b_j, to_bf16x8(b_bf16, raw.v[2 * c], raw.v[2 * c + 1]));
+        if (g == 2) {
+          fence_proxy_async_smem();
+          mbar_arrive(&sh->full[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    };
+
+    // rolling pipeline over all groups of all k-blocks of all items: the loads of group i+1 are issued before
+    // group i is converted and stored (two groups = 256 bytes per thread in flight); two register sets, ping-pong
+    struct Pos { Item it; int item, steps, step, g; };
+    auto advance = [&](Pos& q) -> bool {
+      if (++q.g == 3) { q.g = 0; ++q.step; }
+      if (q.step == q.steps) {
+        q.item += gridDim.x; q.step = 0;
+        if (q.item >= n_items) return false;
+        q.it = decode_item<MODE>(p, q.item); q.steps = (q.it.b1 - q.it.b0) * kbpb;
+      }
+      return true;
+    };
+    if ((int)blockIdx.x < n_items) {
+      Raw r0, r1;
+      Pos pos;
+      pos.item = blockIdx.x; pos.it = decode_item<MODE>(p, pos.item); pos.steps = (pos.it.b1 - pos.it.b0) * kbpb; pos.step = 0; pos.g = 0;
+      issue(pos.it, pos.step, pos.g, r0);
+      while (true) {
+        Pos np = pos;
+        bool more = advance(np);
+        if (more) issue(np.it, np.step, np.g, r1);
+        commit(pos.it, pos.g, r0);
+        if (!more) break;
+        pos = np;
+        more = advance(np);
+        if (more) issue(np.it, np.step, np.g, r0);
+        commit(pos.it, pos.g, r1);
+        if (!more) break;
+        pos = np;
+      }
+    }
+    if (MODE == kDW && p.dbias) {
+      // thread t holds partial sums of columns m0 + 8 a_o + e over its k rows; all items of a CTA share m0 (one item per CTA)
+      const Item it0 = decode_item<MODE>(p, blockIdx.x);
+      if (blockIdx.x < n_items && it0.n0 == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&sh->colsum[a_o * 8 + e], cs[e]);
+        asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");
+        if (t < kM && it0.m0 + t < p.M) atomicAdd(p.dbias + it0.m0 + t, sh->colsum[t]);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // =============================== MMA issue: one elected thread ===============================
+    if (elect_one()) {
+      constexpr uint32_t idesc = idesc_bf16(kM, kN, true, false);
+      uint32_t stage = 0, phase = 0, n_acc = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_acc) {
+        const Item it = decode_item<MODE>(p, item);
+        const int steps = (it.b1 - it.b0) * kbpb;
+        const uint32_t buf = n_acc & 1;
+        mbar_wait(&sh->acc_empty[buf], ((n_acc >> 1) & 1) ^ 1, wc, 12);      // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem + buf * kAccCols;
+        for (int step = 0; step < steps; ++step) {
+          mbar_wait(&sh->full[stage], phase, wc, 13);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes), sb = sa + kABytes;
+#pragma unroll
+          for (int ks = 0; ks < kKB / 16; ++ks) {
+            const Desc da = make_desc(sa + ks * 2048, kABlock, 1024);       // MN-major: 16 k rows = 2048 bytes per step
+            const Desc db = make_desc(sb + ks * 32, 16, 1024);              // K-major: 16 k = 32 bytes inside the row
+            mma_ss(acc, da, db, idesc, step > 0 || ks > 0);
+          }
+          mma_commit(&sh->empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&sh->acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue warps 0..3: TMEM lane = tile row ===============================
+    uint32_t n_acc = 0;
+    const int rl = warp * 32 + lane;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_acc) {
+      const Item it = decode_item<MODE>(p, item);
+      const uint32_t buf = n_acc & 1;
+      mbar_wait(&sh->acc_full[buf], (n_acc >> 1) & 1, wc, 14);
+      tc_fence_after();
+      const uint32_t acc = tmem + buf * kAccCols + (static_cast<uint32_t>(warp * 32) << 16);
+      const int m = it.m0 + rl;
+      if (MODE == kFwd) {
+        // row = pixel m of image out_b: y = acc + bias, ||y||, unit row (bf16) + norm; pad rows [R, Rpad) are zeros
+        float ss = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < kN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(acc + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { const float y = __uint_as_float(v[e]) + sh->bias[c * 32 + e]; ss = fmaf(y, y, ss); }
+        }
+        // a timed-out pipeline wait (abort flag) must not pass for a result: NaN norms poison the loss downstream
+        const float nrm = *wc.abort_flag ? __int_as_float(0x7fc00000) : fmaxf(sqrtf(ss), kEps), inv = (m < p.R) ? 1.f / nrm : 0.f;
+        const bool wr = m < p.Rpad;
+        __nv_bfloat16* dst = p.kn + ((size_t)it.out_b * p.Rpad + m) * kN;
+#pragma unroll 1
+        for (int c = 0; c < kN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(acc + c * 32, v);
+          tmem_wait_ld();
+          if (wr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int col = q * 8 + e * 2;
+                w[e] = pack_bf16((__uint_as_float(v[col]) + sh->bias[c * 32 + col]) * inv,
+                                 (__uint_as_float(v[col + 1]) + sh->bias[c * 32 + col + 1]) * inv);
+              }
+              *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+        if (wr) p.rnorm[(size_t)it.out_b * p.Rpad + m] = (m < p.R) ? nrm : 0.f;
+      } else if (MODE == kDFeat) {
+        // row = input channel m, columns = pixels n0 + c: dfeat[b][m][n]
+        const bool row_ok = m < p.M;
+        const size_t row_off = ((size_t)it.out_b * p.M + m) * p.N;
+        const bool vec = (p.N % 8 == 0);
+#pragma unroll 1
+        for (int c = 0; c < kN / 32; ++c) {
+          const int n = it.n0 + c * 32;
+          if (n >= p.N) break;                                   // uniform over the warp
+          uint32_t v[32];
+          tmem_ld32(acc + c * 32, v);
+          tmem_wait_ld();
+          if (!row_ok) continue;
+          if (*wc.abort_flag) v[0] = 0x7fc00000u;                // timed-out wait: never a plausible gradient
+          if (vec && n + 32 <= p.N) {
+            if (p.out_bf16) {
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.dfeat) + row_off + n;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(dst + q * 8) =
+                    make_uint4(pack_bf16(__uint_as_float(v[q * 8]), __uint_as_float(v[q * 8 + 1])),
+                               pack_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])),
+                               pack_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])),
+                               pack_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])));
+            } else {
+              float* dst = static_cast<float*>(p.dfeat) + row_off + n;
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4*>(dst + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (n + e < p.N) {
+                if (p.out_bf16) static_cast<__nv_bfloat16*>(p.dfeat)[row_off + n + e] = __float2bfloat16_rn(__uint_as_float(v[e]));
+                else static_cast<float*>(p.dfeat)[row_off + n + e] = __uint_as_float(v[e]);
+              }
+          }
+        }
+      } else {
+        // row = output feature m (d), columns = input channels n0 + c: partial dW over this CTA's batch items
+        const bool row_ok = m < p.M;
+#pragma unroll 1
+        for (int c = 0; c < kN / 32; ++c) {
+          const int n = it.n0 + c * 32;
+          if (n >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(acc + c * 32, v);
+          tmem_wait_ld();
+          if (!row_ok) continue;
+          if (*wc.abort_flag) v[0] = 0x7fc00000u;
+          float* dst = p.dw + (size_t)m * p.N + n;
+          if (n + 32 <= p.N && p.N % 4 == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(v[4 * q])),
+                           "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])), "f"(__uint_as_float(v[4 * q + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (n + e < p.N) atomicAdd(dst + e, __uint_as_float(v[e]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sh->acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem, 2 * kAccCols);
+}
+
+constexpr int kHeadSmem = kStages * kStageBytes + (int)sizeof(HeadShared) + 1024;
+
+template <int MODE>
+int launch_head(const HeadParams& p, int n_items, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  XMC_RETURN_IF_CUDA(cudaGetDevice(&dev));
+  XMC_RETURN_IF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(region_head_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
+  const int grid = n_items < sms ? n_items : sms;
+  region_head_kernel<MODE><<<grid, kThreads, kHeadSmem, st>>>(p);
+  return cuda_fail(cudaGetLastError(), "region_head_kernel launch");
+}
+
+int check_dt(int dt) { return dt == XMC_F32 || dt == XMC_BF16; }
+
+}  // namespace
+}  // namespace xmc
+
+using namespace xmc;
+
+extern "C" int xmc_region_head_forward(const void* feat, int feat_dtype, const void* weight, int weight_dtype,
+                                       const float* bias, int B, int Cin, int R, int Rpad, int D,
+                                       void* kn, float* rnorm, void* stream) {
+  XMC_REQUIRE(feat && weight && kn && rnorm, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(check_dt(feat_dtype) && check_dt(weight_dtype), XMC_ERR_UNSUPPORTED, "dtype must be XMC_F32 or XMC_BF16");
+  XMC_REQUIRE(B > 0 && Cin > 0 && R > 0 && Rpad >= R && Rpad % 16 == 0, XMC_ERR_INVALID_ARG, "bad shape B=%d Cin=%d R=%d Rpad=%d", B, Cin, R, Rpad);
+  XMC_REQUIRE(D == kN, XMC_ERR_UNSUPPORTED, "region head: D=%d unsupported (256)", D);
+  XMC_REQUIRE(aligned16(feat) && aligned16(weight) && aligned16(kn), XMC_ERR_ALIGNMENT, "pointers must be 16-byte aligned");
+  HeadParams p{};
+  p.a = feat; p.a_batch = (long long)Cin * R; p.lda = R; p.a_bf16 = feat_dtype == XMC_BF16;
+  p.b = weight; p.b_batch = 0; p.ldb = Cin; p.b_bf16 = weight_dtype == XMC_BF16;
+  p.M = R; p.N = D; p.K = Cin;
+  p.m_tiles = (Rpad + kM - 1) / kM; p.n_tiles = 1; p.batches = B; p.splits = 1;
+  p.bias = bias; p.kn = static_cast<__nv_bfloat16*>(kn); p.rnorm = rnorm; p.R = R; p.Rpad = Rpad;
+  return launch_head<kFwd>(p, B * p.m_tiles, as_stream(stream));
+}
+
+extern "C" int xmc_region_head_backward_input(const void* weight, int weight_dtype, const void* dy, int B, int Cin, int R,
+                                              int D, void* dfeat, int out_dtype, void* stream) {
+  XMC_REQUIRE(weight && dy && dfeat, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(check_dt(weight_dtype) && check_dt(out_dtype), XMC_ERR_UNSUPPORTED, "dtype must be XMC_F32 or XMC_BF16");
+  XMC_REQUIRE(B > 0 && Cin > 0 && R > 0, XMC_ERR_INVALID_ARG, "bad shape B=%d Cin=%d R=%d", B, Cin, R);
+  XMC_REQUIRE(D == kN, XMC_ERR_UNSUPPORTED, "region head: D=%d unsupported (256)", D);
+  XMC_REQUIRE(aligned16(weight) && aligned16(dy) && aligned16(dfeat), XMC_ERR_ALIGNMENT, "pointers must be 16-byte aligned");
+  HeadParams p{};
+  p.a = weight; p.a_batch = 0; p.lda = Cin; p.a_bf16 = weight_dtype == XMC_BF16;      // A[k = d][m = channel]
+  p.b = dy; p.b_batch = (long long)R * D; p.ldb = D; p.b_bf16 = 1;                    // B[n = pixel][k = d]
+  p.M = Cin; p.N = R; p.K = D;
+  p.m_tiles = (Cin + kM - 1) / kM; p.n_tiles = (R + kN - 1) / kN; p.batches = B; p.splits = 1;
+  p.dfeat = dfeat; p.out_bf16 = out_dtype == XMC_BF16;
+  return launch_head<kDFeat>(p, B * p.m_tiles * p.n_tiles, as_stream(stream));
+}
+
+extern "C" int xmc_region_head_backward_weight(const void* feat, int feat_dtype, const void* dy, int B, int Cin, int R, int D,
+                                               float* dweight, float* dbias, void* stream) {
+  XMC_REQUIRE(feat && dy && dweight, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(check_dt(feat_dtype), XMC_ERR_UNSUPPORTED, "dtype must be XMC_F32 or XMC_BF16");
+  XMC_REQUIRE(B > 0 && Cin > 0 && R > 0, XMC_ERR_INVALID_ARG, "bad shape B=%d Cin=%d R=%d", B, Cin, R);
+  XMC_REQUIRE(D == kN, XMC_ERR_UNSUPPORTED, "region head: D=%d unsupported (256)", D);
+  XMC_REQUIRE(aligned16(feat) && aligned16(dy) && aligned16(dweight), XMC_ERR_ALIGNMENT, "pointers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  XMC_RETURN_IF_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * (size_t)D * Cin, st));
+  if (dbias) XMC_RETURN_IF_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)D, st));
+  HeadParams p{};
+  p.a = dy; p.a_batch = (long long)R * D; p.lda = D; p.a_bf16 = 1;                    // A[k = pixel][m = d]
+  p.b = feat; p.b_batch = (long long)Cin * R; p.ldb = R; p.b_bf16 = feat_dtype == XMC_BF16;   // B[n = channel][k = pixel]
+  p.M = D; p.N = Cin; p.K = R;
+  p.m_tiles = D / kM; p.n_tiles = (Cin + kN - 1) / kN; p.batches = B;
+  int dev = 0, sms = 148;
+  XMC_RETURN_IF_CUDA(cudaGetDevice(&dev));
+  XMC_RETURN_IF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int tiles = p.m_tiles * p.n_tiles;
+  int splits = sms / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > B) splits = B;
+  // every split must own at least one batch item (an empty split would publish an unwritten accumulator)
+  const int per = (B + splits - 1) / splits;
+  splits = (B + per - 1) / per;
+  p.splits = splits;
+  p.dw = dweight; p.dbias = dbias;
+  return launch_head<kDW>(p, tiles * splits, st);
+}

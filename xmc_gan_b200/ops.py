@@ -361,6 +361,41 @@ class CudaOps:
         self.launches += 1
         return dx
 
+    # -- region head fused into the word loss's prologue -------------------------
+    def region_head_forward(self, feat, weight, bias, Rpad):
+        """feat [B, Cin, R] (fp32 / bf16, NCHW), weight [D, Cin], bias [D] or None -> unit rows kn [B, Rpad, D] bf16 +
+        norms [B, Rpad] of y = conv1x1(feat); y itself is never written."""
+        _cuda(feat, weight, bias)
+        B, Cin, R = feat.shape
+        D = weight.shape[0]
+        kn = torch.empty(B, Rpad, D, device=feat.device, dtype=torch.bfloat16)
+        rnorm = torch.empty(B, Rpad, device=feat.device, dtype=torch.float32)
+        with _on(feat), self._timed("region_head_fwd"):
+            self._check(self.L.xmc_region_head_forward(_p(feat), _dt(feat), _p(weight), _dt(weight), _p(bias), B, Cin, R, Rpad, D,
+                                                       _p(kn), _p(rnorm), _stream()))
+        self.launches += 1
+        return kn, rnorm
+
+    def region_head_backward(self, feat, weight, dy, need_feat, need_weight, need_bias):
+        """dy [B, R, D] bf16 -> (dfeat like feat or None, dweight [D, Cin] fp32 or None, dbias [D] fp32 or None)."""
+        _cuda(feat, weight, dy)
+        B, Cin, R = feat.shape
+        D = weight.shape[0]
+        dfeat = dweight = dbias = None
+        with _on(feat), self._timed("region_head_bwd"):
+            if need_feat:
+                dfeat = torch.empty_like(feat)
+                self._check(self.L.xmc_region_head_backward_input(_p(weight), _dt(weight), _p(dy), B, Cin, R, D, _p(dfeat),
+                                                                  _dt(dfeat), _stream()))
+                self.launches += 1
+            if need_weight or need_bias:
+                dweight = torch.empty(D, Cin, device=feat.device, dtype=torch.float32)
+                dbias = torch.empty(D, device=feat.device, dtype=torch.float32) if need_bias else None
+                self._check(self.L.xmc_region_head_backward_weight(_p(feat), _dt(feat), _p(dy), B, Cin, R, D, _p(dweight),
+                                                                   _p(dbias), _stream()))
+                self.launches += 1
+        return dfeat, dweight, dbias
+
     def _check_error_word(self, ws, what):
         """XMC_CHECK_ERRORS=1 (tests): synchronise and raise if a bounded mbarrier wait of the tcgen05 kernel
         timed out (word 0 of its workspace).  Off by default: the product path never synchronises."""
