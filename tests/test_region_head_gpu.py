@@ -84,3 +84,81 @@ def test_full_size_head_against_torch_on_gpu():
     n = y.norm(dim=-1)
     assert float((rnorm - n).abs().max() / n.max()) < 1e-3
     assert float((kn.float() - y / n.unsqueeze(-1)).abs().max()) < 8e-3
+
+
+def _head_inputs(B, Cin, H, W, T_, seed):
+    """Feature map whose projection leans towards the caption's words (so the attention is not uniform)."""
+    g = torch.Generator().manual_seed(seed)
+    D = 256
+    words = torch.randn(B, D, T_, generator=g)
+    w = torch.randn(D, Cin, generator=g) / Cin ** 0.5
+    bias = torch.randn(D, generator=g) * 0.05
+    feat = torch.randn(B, Cin, H, W, generator=g)
+    # add a component that projects onto a random word of the own caption: feat += W^+ e_t (least squares through W^T)
+    pick = torch.randint(0, T_, (H * W,), generator=g)
+    target = words[:, :, pick]                                        # [B, D, R]
+    feat = feat + 0.5 * torch.einsum("dc,bdr->bcr", w, target).view(B, Cin, H, W)
+    lens = torch.randint(max(1, T_ // 3), T_ + 1, (B,), generator=g)
+    mask = torch.arange(T_).unsqueeze(0) >= lens.unsqueeze(1)
+    return feat, w, bias, words, mask
+
+
+@pytest.mark.parametrize("B,Cin,H,W,T_,fdt", [(16, 512, 16, 16, 18, torch.float32), (24, 512, 16, 16, 12, torch.bfloat16),
+                                             (6, 256, 17, 17, 18, torch.float32)])
+def test_word_loss_with_fused_head_vs_oracle(B, Cin, H, W, T_, fdt):
+    """word_loss(feature map, region_head=(W, b), precision='bf16') == oracle.word_loss(conv1x1(map)) on the bf16-rounded
+    operands: loss and the gradients of the map, the head's weight and bias, and the words (rel 2e-2)."""
+    import oracle
+    from util import TOL_BF16, lerr, nerr
+    from xmc_gan_b200 import train_gan as T
+    feat, w, bias, words, mask = _head_inputs(B, Cin, H, W, T_, seed=B + Cin)
+    feat = feat.to(fdt)
+    labels = T.make_labels(B, None, False)
+    f = feat.clone().cuda().requires_grad_()
+    wg = w.clone().cuda().view(256, Cin, 1, 1).requires_grad_()       # a Conv2d weight
+    bg = bias.clone().cuda().requires_grad_()
+    wd = words.bfloat16().cuda().requires_grad_()
+    loss = T.word_loss(f, wd, mask.cuda(), labels, False, precision="bf16", region_head=(wg, bg))
+    loss.backward()
+    fo, wo, bo = _r(feat).requires_grad_(), _r(w).requires_grad_(), bias.double().requires_grad_()
+    wdo = _r(words).requires_grad_()
+    y = torch.einsum("bchw,dc->bdhw", fo, wo) + bo.view(1, -1, 1, 1)
+    lo = oracle.word_loss(y, wdo, mask, torch.eye(B), False)
+    lo.backward()
+    assert lerr(loss, lo) <= TOL_BF16, (float(loss), float(lo))
+    assert f.grad.dtype == fdt and wg.grad.shape == wg.shape
+    for name, a, b in (("feat", f.grad, fo.grad), ("weight", wg.grad.view(256, Cin), wo.grad), ("bias", bg.grad, bo.grad),
+                       ("words", wd.grad, wdo.grad)):
+        assert nerr(a, b) <= TOL_BF16, (name, nerr(a, b))
+
+
+def test_fused_head_equals_unfused_projection():
+    """Same loss as projecting with PyTorch's convolution first (the fp32 fallback of region_head=) within the bf16 tolerance,
+    through contrastive_losses as well."""
+    from util import TOL_BF16, lerr, nerr
+    from xmc_gan_b200 import train_gan as T
+    B, Cin, H, W, T_ = 32, 512, 16, 16, 18
+    feat, w, bias, words, mask = _head_inputs(B, Cin, H, W, T_, seed=5)
+    labels = T.make_labels(B, None, False)
+    conv = torch.nn.Conv2d(Cin, 256, 1).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(w.view(256, Cin, 1, 1)); conv.bias.copy_(bias)
+    f1 = feat.clone().cuda().requires_grad_()
+    w1 = words.clone().cuda().requires_grad_()
+    l1 = T.contrastive_losses(regions=f1, words=w1, mask=mask.cuda(), labels=labels, b_global=False, precision="bf16",
+                              region_head=conv)[2]
+    l1.backward()
+    g_w, g_b = conv.weight.grad.clone(), conv.bias.grad.clone()
+    conv.zero_grad()
+    f2 = feat.clone().cuda().requires_grad_()
+    w2 = words.clone().cuda().requires_grad_()
+    l2 = T.word_loss(conv(f2), w2, mask.cuda(), labels, False, precision="bf16")
+    l2.backward()
+    assert lerr(l1, l2) <= TOL_BF16
+    assert nerr(f1.grad, f2.grad) <= TOL_BF16 and nerr(w1.grad, w2.grad) <= TOL_BF16
+    assert nerr(g_w, conv.weight.grad) <= TOL_BF16 and nerr(g_b, conv.bias.grad) <= TOL_BF16
+    # fp32 precision: region_head= falls back to the convolution in front of the loss (fp32 tolerance path)
+    f3 = feat.clone().cuda().requires_grad_()
+    l3 = T.word_loss(f3, words.clone().cuda(), mask.cuda(), labels, False, precision="fp32", region_head=conv)
+    l4 = T.word_loss(conv(f3), words.clone().cuda(), mask.cuda(), labels, False, precision="fp32")
+    assert lerr(l3, l4) <= 1e-6

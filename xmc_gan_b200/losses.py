@@ -303,7 +303,7 @@ def _ceil_to(x, m):
 class _Word:
     __slots__ = ("path", "R", "T", "rho1", "rho2", "rho3", "qn", "qnorm", "kn", "rnorm", "has_rn", "lsum", "cnorm", "rel",
                  "scores", "m_all", "chat", "row_of", "cap_ptr", "compact", "bufs", "tail", "reg_shape", "reg_dtype", "w_dtype",
-                 "Bc", "fwd_ws", "rows_layout")
+                 "Bc", "fwd_ws", "rows_layout", "head", "dhead")
 
 
 def _rows_view(regions):
@@ -317,9 +317,32 @@ def _rows_view(regions):
     return None
 
 
-def _word_prepare_regions(ops, regions, precision):
+def _head_operands(regions, head):
+    """(feat [B, Cin, R] contiguous, weight [D, Cin], bias [D] fp32 or None) of a fused region head."""
+    weight, bias = head
+    feat = regions.detach().flatten(2).contiguous()
+    w2 = weight.detach().reshape(weight.shape[0], -1).contiguous()
+    if w2.shape[1] != feat.shape[1]:
+        raise ValueError(f"region_head weight {tuple(weight.shape)} does not take {feat.shape[1]} input channels")
+    b1 = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    return feat, w2, b1
+
+
+def _word_prepare_regions(ops, regions, precision, head=None):
     """Region prologue (independent of the gathered words: runs while the all-gather is in flight).
-    -> (shape [Bi, D, R], input dtype, precision, operand dtype, Rpad, unit rows kn, norms, rows_layout)."""
+    -> (shape [Bi, D, R], input dtype, precision, operand dtype, Rpad, unit rows kn, norms, rows_layout, head operands).
+
+    head = (weight, bias): ``regions`` is the discriminator's feature map [B, Cin, H, W] and the region features are its
+    1x1 projection — one tcgen05 kernel writes their unit rows and norms directly; bf16 tolerance."""
+    if head is not None:
+        if precision not in (None, "bf16"):
+            raise ValueError("a fused region head runs on the bf16 tensor-core path (precision=None or 'bf16')")
+        feat, w2, b1 = _head_operands(regions, head)
+        Bi, _, R = feat.shape
+        D = w2.shape[0]
+        Rpad = _ceil_to(R, 16)
+        kn, rnorm = ops.region_head_forward(feat, w2, b1, Rpad)              # [Bi, Rpad, D] bf16, [Bi, Rpad]
+        return (Bi, D, R), None, "bf16", torch.bfloat16, Rpad, kn, rnorm, True, (feat, w2)
     regions = regions.detach()
     rows = _rows_view(regions) if hasattr(ops, "normalize_rows") else None
     if precision is None:
@@ -336,13 +359,13 @@ def _word_prepare_regions(ops, regions, precision):
         Bi, D, R = reg.shape
         Rpad = _ceil_to(R, 16)                                               # zero rows up to the MMA's N granularity
         kn, rnorm = ops.normalize_transpose(reg, Rpad, op_dtype)             # [Bi, Rpad, D]
-    return (Bi, D, R), regions.dtype, precision, op_dtype, Rpad, kn, rnorm, rows is not None
+    return (Bi, D, R), regions.dtype, precision, op_dtype, Rpad, kn, rnorm, rows is not None, None
 
 
 def _word_local(ops, comm, prep, regions, w_all, m_all, labels, b_global, rho1, rho2, rho3, normalize_values, need_grad,
                 packet):
-    (Bi, D, R), reg_dtype, precision, op_dtype, Rpad, kn, rnorm, rows_layout = prep
-    if reg_dtype != w_all.dtype:
+    (Bi, D, R), reg_dtype, precision, op_dtype, Rpad, kn, rnorm, rows_layout, head_ops = prep
+    if reg_dtype is not None and reg_dtype != w_all.dtype:
         raise TypeError(f"operand dtypes differ: {reg_dtype} vs {w_all.dtype}")
     Bc, _, T = w_all.shape
     if precision == "bf16":
@@ -403,12 +426,14 @@ def _word_local(ops, comm, prep, regions, w_all, m_all, labels, b_global, rho1, 
     st.qn, st.qnorm, st.kn, st.rnorm, st.has_rn = qn, qnorm, kn, rnorm, rn is not None
     st.m_all, st.compact, st.tail, st.Bc = m_all, compact, tl, Bc
     st.reg_shape, st.reg_dtype, st.w_dtype, st.rows_layout = tuple(regions.shape), regions.dtype, w_all.dtype, rows_layout
+    st.head, st.dhead = head_ops, None
     return st
 
 
-def _word_backward(ops, st: _Word, go, need_reg, need_w):
+def _word_backward(ops, st: _Word, go, need_reg, need_w, need_head=(False, False)):
     """-> (d regions in the caller's layout or None, d gathered words [Bc_g, D, T] fp32 or None).  The word-side layout
-    epilogue runs on the side stream; the caller joins it (``_join_side``) before using the second result."""
+    epilogue runs on the side stream; the caller joins it (``_join_side``) before using the second result.  With a fused
+    region head ``st.dhead`` = (d weight [D, Cin] fp32, d bias [D] fp32) afterwards (``need_head``)."""
     tl = st.tail
     bufs, st.bufs = st.bufs, None             # single use: the kernels accumulate into them
     cap = {"cap_ptr": st.cap_ptr} if st.compact else {}
@@ -441,13 +466,29 @@ def _word_backward(ops, st: _Word, go, need_reg, need_w):
         with _side_scope(ops, dev):
             dw_all = ops.normalize_transpose_backward(qn, st.qnorm, dqn.view(qn.shape), None, T, torch.float32, error_word=ws,
                                                       **({"row_of": st.row_of} if st.compact else {}))
-    if need_reg and st.rows_layout:            # gradient in the producer's own (channels-last) layout, no transpose
+    if st.head is not None:                    # fused region head: d y rows (bf16) -> the head's two backward products
+        if need_reg or any(need_head):
+            feat, w2 = st.head
+            dy = ops.normalize_rows_backward(kn, st.rnorm, dkn, drnorm, st.R, torch.bfloat16, error_word=ws)
+            dfeat, dwgt, dbias = ops.region_head_backward(feat, w2, dy, need_reg, need_head[0], need_head[1])
+            dreg = dfeat.view(st.reg_shape) if dfeat is not None else None
+            st.dhead = (dwgt, dbias)
+    elif need_reg and st.rows_layout:          # gradient in the producer's own (channels-last) layout, no transpose
         B_, D_, H_, W_ = st.reg_shape
         dreg = ops.normalize_rows_backward(kn, st.rnorm, dkn, drnorm, st.R, st.reg_dtype, error_word=ws)
         dreg = dreg.view(B_, H_, W_, D_).permute(0, 3, 1, 2)
     elif need_reg:
         dreg = ops.normalize_transpose_backward(kn, st.rnorm, dkn, drnorm, st.R, st.reg_dtype, error_word=ws).view(st.reg_shape)
     return dreg, dw_all
+
+
+def _head_grads(st, meta, need_head):
+    """(d weight, d bias) of a fused region head in the parameters' own shapes and dtypes."""
+    if meta is None or st is None or st.dhead is None:
+        return (None, None)
+    (wshape, wdtype, bdtype), (dwgt, dbias) = meta, st.dhead
+    return (dwgt.view(wshape).to(wdtype) if need_head[0] and dwgt is not None else None,
+            dbias.to(bdtype) if need_head[1] and dbias is not None else None)
 
 
 def _mask_u8(mask):
@@ -459,12 +500,13 @@ class WordLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, regions, words, mask, labels, b_global, rho1, rho2, rho3, normalize_values,
-                precision, group, ops):
+                precision, group, ops, head_w=None, head_b=None):
         comm = as_comm(group)
         (w_all, m_all), work = comm.gather_begin([words.detach(), _mask_u8(mask)])      # in flight during the region prologue
-        prep = _word_prepare_regions(ops, regions, precision)
+        prep = _word_prepare_regions(ops, regions, precision, None if head_w is None else (head_w, head_b))
         work.wait()
-        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 12, 13))
+        ctx.head_meta = None if head_w is None else (head_w.shape, head_w.dtype, None if head_b is None else head_b.dtype)
         packet = (torch.empty(_packet_floats(w_all.shape[0]), device=regions.device, dtype=torch.float32)
                   if comm.active else None)
         st = _word_local(ops, comm, prep, regions, w_all.contiguous(), m_all, labels, b_global, rho1, rho2, rho3,
@@ -476,17 +518,18 @@ class WordLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         need_reg, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if not (need_reg or need_w):
-            return (None,) * 12
+        need_head = (ctx.needs_input_grad[12], ctx.needs_input_grad[13])
+        if not (need_reg or need_w or any(need_head)):
+            return (None,) * 14
         st = ctx.st
         ops, comm = ctx.ops, ctx.comm
         go = grad_out.detach().to(torch.float32).contiguous()
-        dreg, dw_all = _word_backward(ops, st, go, need_reg, need_w)
+        dreg, dw_all = _word_backward(ops, st, go, need_reg, need_w, need_head)
         dwords = None
         if need_w:
             _join_side(ops, dreg.device if dreg is not None else dw_all.device, dw_all)
             dwords = comm.reduce_scatter_sum(dw_all).to(st.w_dtype)
-        return (dreg, dwords) + (None,) * 10
+        return (dreg, dwords) + (None,) * 10 + _head_grads(st, ctx.head_meta, need_head)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -500,7 +543,7 @@ class FusedLossesFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, imgs, txts, real_imgs, fake_imgs, regions, words, mask, labels, b_global,
-                tau, rho1, rho2, rho3, normalize_values, precision, group, ops):
+                tau, rho1, rho2, rho3, normalize_values, precision, group, ops, head_w=None, head_b=None):
         comm = as_comm(group)
         has_sent = imgs is not None and txts is not None
         has_img = real_imgs is not None and fake_imgs is not None
@@ -509,7 +552,9 @@ class FusedLossesFn(torch.autograd.Function):
         (txt_all, fake_all, w_all, m_all), work = comm.gather_begin(
             [det(txts) if has_sent else None, det(fake_imgs) if has_img else None,
              det(words) if has_word else None, _mask_u8(mask) if has_word else None])
-        prep = _word_prepare_regions(ops, regions, precision) if has_word else None       # overlaps the gather
+        head = None if head_w is None else (head_w, head_b)
+        prep = _word_prepare_regions(ops, regions, precision, head) if has_word else None  # overlaps the gather
+        ctx.head_meta = None if head_w is None else (head_w.shape, head_w.dtype, None if head_b is None else head_b.dtype)
         work.wait()
         dev = (imgs if has_sent else real_imgs if has_img else regions).device
         Bk = [t.shape[0] if h else 0 for t, h in ((txt_all, has_sent), (fake_all, has_img), (w_all, has_word))]
@@ -527,7 +572,7 @@ class FusedLossesFn(torch.autograd.Function):
                     marks[k] = mark
         wst = None
         if has_word:
-            need_grad = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+            need_grad = any(ctx.needs_input_grad[i] for i in (4, 5, 17, 18))
             wst = _word_local(ops, comm, prep, regions, w_all.contiguous(), m_all, labels, b_global, rho1, rho2, rho3,
                               normalize_values, need_grad, sl(2))
         for k in range(2):
@@ -562,8 +607,9 @@ class FusedLossesFn(torch.autograd.Function):
         if s_img is not None and g_img is not None and (need[2] or need[3]):
             with _side_scope(ops, dev, 2):
                 d_real, d_fake_all = _sim_backward(ops, s_img, f32(g_img), need[2], need[3])
-        if wst is not None and g_word is not None and (need[4] or need[5]):
-            dreg_pending = _word_backward(ops, wst, f32(g_word), need[4], need[5])
+        need_head = (need[17], need[18])
+        if wst is not None and g_word is not None and (need[4] or need[5] or any(need_head)):
+            dreg_pending = _word_backward(ops, wst, f32(g_word), need[4], need[5], need_head)
             dreg, dw_all = dreg_pending
             if dw_all is not None:
                 _join_side(ops, dev, dw_all)
@@ -573,7 +619,7 @@ class FusedLossesFn(torch.autograd.Function):
         work.wait()
         if d_words is not None:
             d_words = d_words.to(wst.w_dtype)
-        return (d_imgs, d_txt, d_real, d_fake, dreg, d_words) + (None,) * 11
+        return (d_imgs, d_txt, d_real, d_fake, dreg, d_words) + (None,) * 11 + _head_grads(wst, ctx.head_meta, need_head)
 
 
 # ------------------------------------------------------------------------------------------------

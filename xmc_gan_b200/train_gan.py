@@ -79,8 +79,23 @@ def img_loss(real_imgs, fake_imgs, labels, b_global, *, tau=1.0, group=None, _op
     return _L.SimLossFn.apply(real_imgs, fake_imgs, labels, bool(b_global), 1.0 / tau, group, _ops or default_ops())
 
 
+def _head_args(imgs, region_head, precision):
+    """region_head = (weight, bias) or a module with .weight / .bias (a Conv2d(Cin, D, 1)).  -> (imgs, weight, bias):
+    fused (weight given back) on the bf16 tensor-core path, otherwise the projection is applied here with PyTorch's
+    convolution and the loss sees ordinary region features."""
+    if region_head is None:
+        return imgs, None, None
+    weight, bias = ((region_head.weight, region_head.bias) if hasattr(region_head, "weight") else region_head)
+    fused = (precision == "bf16" or (precision is None and imgs.dtype == torch.bfloat16)) and weight.shape[0] == 256
+    if fused:
+        return imgs, weight, bias
+    w4 = weight.reshape(weight.shape[0], -1, 1, 1)
+    x = imgs if imgs.dim() == 4 else imgs.unsqueeze(-1)
+    return torch.nn.functional.conv2d(x, w4.to(x.dtype), None if bias is None else bias.to(x.dtype)), None, None
+
+
 def word_loss(imgs, words, mask, labels, b_global, *, rho1=5.0, rho2=5.0, rho3=10.0,
-              normalize_values=False, precision=None, group=None, _ops=None):
+              normalize_values=False, precision=None, group=None, region_head=None, _ops=None):
     """Word–region attention contrastive loss (name pinned by ``train_gan.py:222, 269``).
 
     imgs: region features ``[B, D, H, W]`` (or ``[B, D, R]``); words ``[B, D, T]`` and
@@ -89,22 +104,32 @@ def word_loss(imgs, words, mask, labels, b_global, *, rho1=5.0, rho2=5.0, rho3=1
     ``precision``: ``"fp32"`` (rel 1e-4: tcgen05 with every operand carried as a hi + lo bf16 pair for D = 256,
     CUDA-core fp32 kernels otherwise or with ``"fp32-simt"``) or ``"bf16"`` (tcgen05, bf16 operands, fp32
     accumulate, rel 2e-2); default follows the input dtype.
+    ``region_head``: ``(weight [D, Cin(,1,1)], bias [D] or None)`` or a ``Conv2d(Cin, D, 1)`` — ``imgs`` is then the
+    discriminator's feature map ``[B, Cin, H, W]`` (``xmc_gan/model/df_gan.py:106-132``) and the regions are its 1x1
+    projection.  With ``precision="bf16"`` (or bf16 features) and D = 256 the projection, the normalisation and the bf16 cast
+    are ONE tensor-core kernel in the loss prologue and the gradients of the map, the weight and the bias
+    come out of the loss's backward; otherwise the projection runs as a PyTorch convolution in front of the loss.
     """
+    imgs, head_w, head_b = _head_args(imgs, region_head, precision)
     return _L.WordLossFn.apply(imgs, words, mask, labels, bool(b_global), float(rho1), float(rho2), float(rho3),
-                               bool(normalize_values), precision, group, _ops or default_ops())
+                               bool(normalize_values), precision, group, _ops or default_ops(), head_w, head_b)
 
 
 def contrastive_losses(imgs=None, txts=None, real_imgs=None, fake_imgs=None, regions=None, words=None, mask=None,
                        labels=None, b_global=False, *, tau=1.0, rho1=5.0, rho2=5.0, rho3=10.0, normalize_values=False,
-                       precision=None, group=None, _ops=None):
+                       precision=None, group=None, region_head=None, _ops=None):
     """``(sent_loss(imgs, txts), img_loss(real_imgs, fake_imgs), word_loss(regions, words, mask))`` of one training
     step (``xmc_gan/train_gan.py:218/265, :278, :220-222/267-269``), evaluated together: same numbers as the three
     calls, but with a process ``group`` the collectives are grouped (one all-gather of all column operands, one
     statistics exchange, one reduce-scatter of the gradients) and the similarity losses run on side streams beside
-    the word-region kernels.  A pair left ``None`` is skipped and its loss is a constant 0."""
+    the word-region kernels.  A pair left ``None`` is skipped and its loss is a constant 0.  ``region_head``: as in
+    :func:`word_loss` (``regions`` is then the discriminator's feature map)."""
+    head_w = head_b = None
+    if regions is not None:
+        regions, head_w, head_b = _head_args(regions, region_head, precision)
     return _L.FusedLossesFn.apply(imgs, txts, real_imgs, fake_imgs, regions, words, mask, labels, bool(b_global),
                                   float(tau), float(rho1), float(rho2), float(rho3), bool(normalize_values), precision,
-                                  group, _ops or default_ops())
+                                  group, _ops or default_ops(), head_w, head_b)
 
 
 def magp_penalty(grads, *, power=6.0, weight=2.0, _ops=None):
