@@ -219,20 +219,22 @@ int xmc_normalize_rows_backward(const void* xn, const float* norm, const float* 
  * (rows R..Rpad-1 zero) — the same outputs as xmc_normalize_rows on y, without y ever reaching HBM.
  *   feat   [B, Cin, R]  fp32 or bf16, NCHW as the discriminator writes it (R = H*W contiguous)
  *   weight [D, Cin]     fp32 or bf16 (a Conv2d(Cin, D, 1) weight, or its spectral-normalised value), bias [D] fp32 or NULL
- * D = 256; operands are rounded to bf16 on the way into shared memory, fp32 accumulation (the bf16 tolerance, 2e-2).
+ * D = 256; bf16 operands run as bf16 MMAs, fp32 operands as tf32 MMAs (fp32 map AND fp32 weight; a mixed pair is rounded
+ * to bf16 in registers), fp32 accumulation: the bf16 mode's tolerance, 2e-2.
  * A timed-out pipeline wait inside the kernel turns rnorm (hence the loss) into NaN. */
 int xmc_region_head_forward(const void* feat, int feat_dtype, const void* weight, int weight_dtype,
                             const float* bias, int B, int Cin, int R, int Rpad, int D,
                             void* kn, float* rnorm, void* stream);
-/* Backward of the head given dy[B, R, D] bf16 = d loss / d y (xmc_normalize_rows_backward applied to the word-region
- * kernels' dkn / drnorm, out_dtype XMC_BF16):
+/* Backward of the head given dy[B, R, D] (bf16 or fp32) = d loss / d y (xmc_normalize_rows_backward applied to the
+ * word-region kernels' dkn / drnorm).  Fast path (cp.async staging) when the two operands of a product have one dtype
+ * and 16-byte aligned rows — bf16 runs as kind::f16, fp32 as kind::tf32 —; otherwise a generic path converts in registers:
  *   _input : dfeat[B, Cin, R] = W^T dy_b^T, written in feat's layout and in out_dtype;
  *   _weight: dweight[D, Cin] fp32 = sum_b dy_b^T feat_b^T and dbias[D] fp32 = sum_{b,r} dy (nullable); both are
  *            zero-filled by the call (cudaMemsetAsync on `stream`) and accumulated with fp32 reductions. */
-int xmc_region_head_backward_input(const void* weight, int weight_dtype, const void* dy, int B, int Cin, int R,
-                                   int D, void* dfeat, int out_dtype, void* stream);
-int xmc_region_head_backward_weight(const void* feat, int feat_dtype, const void* dy, int B, int Cin, int R, int D,
-                                    float* dweight, float* dbias, void* stream);
+int xmc_region_head_backward_input(const void* weight, int weight_dtype, const void* dy, int dy_dtype, int B, int Cin,
+                                   int R, int D, void* dfeat, int out_dtype, void* stream);
+int xmc_region_head_backward_weight(const void* feat, int feat_dtype, const void* dy, int dy_dtype, int B, int Cin, int R,
+                                    int D, float* dweight, float* dbias, void* stream);
 
 size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad, int D);
 

@@ -1,9 +1,10 @@
 """Region head fused into the word loss's prologue: the three tcgen05 products of
 ``xmc_gan_b200/csrc/region_head.cu`` through the C ABI against plain fp64 PyTorch on the bf16-rounded operands.
 
-Forward: kn / rnorm of y = conv1x1(feat) + bias; backward: dfeat, dweight, dbias of a given dy.  Tolerances are the
-bf16 mode's (operands rounded to bf16, fp32 accumulation): unit rows to bf16 resolution, norms and gradients 1e-3
-relative to the tensor's scale (the CPU side uses the same rounded operands, so only accumulation order differs)."""
+Forward: kn / rnorm of y = conv1x1(feat) + bias; backward: dfeat, dweight, dbias of a given dy.  bf16 operands are
+exact inputs of the bf16 MMAs (the CPU side uses the same values: only accumulation order differs, 1e-3 of the
+tensor's scale); an fp32 pair runs as tf32 MMAs (operands truncated to 10 mantissa bits: 2e-3); a mixed pair is rounded to
+bf16 in registers (generic path; compared against the rounded values).  Unit rows are bf16: half an ulp of 1 on top."""
 import pytest
 import torch
 
@@ -15,8 +16,14 @@ def _ops():
     return default_ops()
 
 
-def _r(x):   # what the kernel sees: bf16-rounded values
+def _r(x):   # bf16-rounded values
     return x.bfloat16().double()
+
+
+def _seen(a, b):
+    """What the kernel multiplies: an fp32 pair with aligned rows stays fp32 (tf32 MMAs), anything else is bf16."""
+    both_f32 = a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape[-1] % 4 == 0 and b.shape[-1] % 4 == 0
+    return (a.double(), b.double(), 2e-3) if both_f32 else (_r(a), _r(b), 1e-3)
 
 
 CASES = [  # B, Cin, H, W, feat dtype, weight dtype, bias
@@ -38,12 +45,13 @@ def test_forward_matches_conv_plus_normalize(B, Cin, H, W, fdt, wdt, has_bias):
     bias = torch.randn(D, generator=g) * 0.1 if has_bias else None
     Rpad = (R + 15) // 16 * 16
     kn, rnorm = ops.region_head_forward(feat.cuda(), w.cuda(), None if bias is None else bias.cuda(), Rpad)
-    y = torch.einsum("bcr,dc->brd", _r(feat), _r(w)) + (0 if bias is None else bias.double())
+    fs, ws, tol = _seen(feat, w)
+    y = torch.einsum("bcr,dc->brd", fs, ws) + (0 if bias is None else bias.double())
     n = y.norm(dim=-1)
     assert kn.shape == (B, Rpad, D) and kn.dtype == torch.bfloat16
     err_n = float((rnorm[:, :R].double().cpu() - n).abs().max() / n.max())
     err_k = float((kn[:, :R].double().cpu() - y / n.unsqueeze(-1)).abs().max())
-    assert err_n < 1e-4, err_n
+    assert err_n < tol, err_n
     assert err_k < 6e-3, err_k            # bf16 resolution of a unit row's entries (|x| <= 1: half an ulp = 2^-9)
     if Rpad > R:
         assert float(kn[:, R:].float().abs().max()) == 0.0 and float(rnorm[:, R:].abs().max()) == 0.0
@@ -56,15 +64,17 @@ def test_backward_matches_einsum(B, Cin, H, W, fdt, wdt, has_bias):
     D, R = 256, H * W
     feat = torch.randn(B, Cin, R, generator=g).to(fdt)
     w = (torch.randn(D, Cin, generator=g) / Cin ** 0.5).to(wdt)
-    dy = (torch.randn(B, R, D, generator=g) * 0.01).bfloat16()
+    dy = (torch.randn(B, R, D, generator=g) * 0.01).to(fdt)          # as the loss hands it over: in the map's dtype
     dfeat, dw, db = ops.region_head_backward(feat.cuda(), w.cuda(), dy.cuda(), True, True, has_bias)
-    ref_f = torch.einsum("brd,dc->bcr", dy.double(), _r(w))
-    ref_w = torch.einsum("brd,bcr->dc", dy.double(), _r(feat))
+    wa, dya, tol_i = _seen(w, dy)
+    fa, dyb, tol_w = _seen(feat, dy)
+    ref_f = torch.einsum("brd,dc->bcr", dya, wa)
+    ref_w = torch.einsum("brd,bcr->dc", dyb, fa)
     ref_b = dy.double().sum((0, 1))
     assert dfeat.dtype == fdt and dfeat.shape == feat.shape
-    tol_f = 1e-3 if fdt == torch.float32 else 6e-3                 # bf16 output: its own rounding
+    tol_f = tol_i if fdt == torch.float32 else 6e-3                # bf16 output: its own rounding
     assert float((dfeat.double().cpu() - ref_f).abs().max() / ref_f.abs().max()) < tol_f
-    assert float((dw.double().cpu() - ref_w).abs().max() / ref_w.abs().max()) < 1e-3
+    assert float((dw.double().cpu() - ref_w).abs().max() / ref_w.abs().max()) < tol_w
     if has_bias:
         assert float((db.double().cpu() - ref_b).abs().max() / ref_b.abs().max()) < 1e-3
     else:
@@ -80,9 +90,9 @@ def test_full_size_head_against_torch_on_gpu():
     w = torch.randn(D, Cin, generator=g, device="cuda") / Cin ** 0.5
     bias = torch.randn(D, generator=g, device="cuda") * 0.1
     kn, rnorm = ops.region_head_forward(feat, w, bias, R)
-    y = torch.einsum("bcr,dc->brd", feat.bfloat16().float(), w.bfloat16().float()) + bias
+    y = torch.einsum("bcr,dc->brd", feat.double(), w.double()).float() + bias
     n = y.norm(dim=-1)
-    assert float((rnorm - n).abs().max() / n.max()) < 1e-3
+    assert float((rnorm - n).abs().max() / n.max()) < 2e-3
     assert float((kn.float() - y / n.unsqueeze(-1)).abs().max()) < 8e-3
 
 

@@ -16,9 +16,15 @@
 // All three products have ONE operand form on the tensor cores: C[m, n] = sum_k A[k, m] * B[n, k] with A stored
 // [K rows][M contiguous] (MN-major smem tile) and B stored [N rows][K contiguous] (K-major tile) — feat_b is
 // [Cin][pixels], W is [D][Cin], dy_b is [pixels][D]: every operand is consumed where it lies, no transposes.
-// Operands are fp32 or bf16 in HBM and always bf16 in shared memory: the CTA's staging warps convert on the way
-// (global -> registers -> bf16 -> 128B-swizzled smem), so an fp32 discriminator needs no cast pass.  fp32
-// accumulation in TMEM (two 256-column accumulators: the epilogue of one tile runs under the MMAs of the next).
+// Staging (fast path: both operands of one dtype, rows 16-byte aligned): eight warps issue 16-byte cp.async copies
+// straight into the 128B-swizzled tiles of a 4-stage ring and hand each stage to the MMA thread through
+// cp.async.mbarrier.arrive — no registers hold data, up to 192 KB per SM is in flight.  bf16 operands run as
+// kind::f16 MMAs (64 k per stage); fp32 operands stay fp32 in shared memory and run as kind::tf32 MMAs (32 k per
+// stage, 10-bit mantissa: inside the bf16 tolerance), so an fp32 discriminator needs neither a cast pass nor a
+// conversion in registers.  (A first version converted in registers: one load round trip per group of four chunks
+// made it latency-bound, 100 us per launch.)  Generic path (mixed dtypes, unaligned rows such as a 17 x 17 map):
+// global -> registers -> bf16 -> swizzled smem by the same warps.  fp32 accumulation in TMEM (two 256-column
+// accumulators: the epilogue of one tile runs under the MMAs of the next).
 //
 // Roofline: HBM.  Forward at B = 256, 16 x 16, Cin = 512, D = 256: 134 MB (fp32 map) or 67 MB (bf16) in + 33.6 MB
 // out against 17.2 GFLOP (12 us of tensor time); the staging path is sized for bytes in flight, not for the MMAs.
@@ -31,10 +37,9 @@ using namespace tc;
 
 namespace {
 
-constexpr int kM = 128, kN = 256, kKB = 64, kStages = 4;
-constexpr int kABlock = kKB * 128;                 // [64 k rows x 64 m] bf16, 128-byte rows
-constexpr int kABytes = 2 * kABlock;               // 16 KB
-constexpr int kBBytes = kN * 128;                  // [256 n rows x 64 k] bf16 = 32 KB
+constexpr int kM = 128, kN = 256, kStages = 4;
+constexpr int kABytes = 128 * 128;                 // A tile: 128 m x (64 bf16 | 32 fp32) k = 16 KB
+constexpr int kBBytes = kN * 128;                  // B tile: 256 n rows x 128 bytes of k = 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;     // 48 KB
 constexpr int kEpiWarps = 4, kMmaWarp = 4, kStageWarp0 = 5, kStageWarps = 8;
 constexpr int kStageThreads = kStageWarps * 32;    // 256
@@ -62,7 +67,6 @@ struct HeadShared {
   uint32_t tmem_slot;
   int abort_flag;
   float bias[kN];
-  float colsum[kM];
 };
 
 // one work item = one accumulator tile: (m0, n0) and the batch items [b0, b1) it sums over
@@ -118,11 +122,14 @@ __device__ __forceinline__ uint4 to_bf16x8(bool bf16, const uint4& r0, const uin
 __device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, uint4 v) {
   *reinterpret_cast<uint4*>(blk + r * 128 + ((c ^ (r & 7)) << 4)) = v;
 }
-__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-template <int MODE>
+// FAST: cp.async staging (operands of one dtype, aligned); TF32: fp32 operands as kind::tf32 (FAST only)
+template <int MODE, bool FAST, bool TF32>
 __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadParams p) {
+  constexpr int KB = TF32 ? 32 : 64;                           // k per stage: 128 bytes of K per B row either way
+  constexpr int ES = TF32 ? 4 : 2;                             // element size in shared memory
+  constexpr int EPC = 16 / ES;                                 // elements per 16-byte chunk
+  constexpr int kABlk = KB * 128;                              // one MN block of the A tile: [KB k rows x 128 bytes of m]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   HeadShared* sh = reinterpret_cast<HeadShared*>(smem + kStages * kStageBytes);
@@ -130,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadPara
 
   const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
   const int n_items = (MODE == kDW ? p.m_tiles * p.n_tiles * p.splits : p.batches * p.m_tiles * p.n_tiles);
-  const int kbpb = (p.K + kKB - 1) / kKB;                     // k-blocks per batch item
+  const int kbpb = (p.K + KB - 1) / KB;                       // k-blocks per batch item
 
   if (tid == 0) {
     sh->abort_flag = 0;
@@ -140,7 +147,6 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadPara
   }
   if (MODE == kFwd)
     for (int i = tid; i < kN; i += kThreads) sh->bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
-  if (MODE == kDW && tid < kM) sh->colsum[tid] = 0.f;
   if (warp == kMmaWarp) tmem_alloc(&sh->tmem_slot, 2 * kAccCols);
   tc_fence_before();
   __syncthreads();
@@ -150,110 +156,130 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadPara
   if (warp >= kStageWarp0) {
     // =============================== staging warps: global -> bf16 -> swizzled smem ===============================
     const int t = tid - kStageWarp0 * 32;                      // 0..255
-    const bool a_bf16 = p.a_bf16 != 0, b_bf16 = p.b_bf16 != 0;
-    const bool a_vec = (p.lda % (a_bf16 ? 8 : 4) == 0) && (p.a_batch % (a_bf16 ? 8 : 4) == 0);
-    const bool b_vec = (p.ldb % (b_bf16 ? 8 : 4) == 0) && (p.b_batch % (b_bf16 ? 8 : 4) == 0);
-    const int a_o = t & 15, a_k = t >> 4;                      // A chunk: m octet, k row (+16 per chunk)
-    const int b_j = t & 7, b_n = t >> 3;                       // B chunk: k octet, n row (+32 per chunk)
-    float cs[8];
+    if (FAST) {
+      constexpr int CPR = 128 / EPC;                           // A chunks per k row (128 m)
+      const uint8_t* ga = static_cast<const uint8_t*>(p.a);
+      const uint8_t* gb = static_cast<const uint8_t*>(p.b);
+      uint32_t stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item<MODE>(p, item);
+        const int steps = (it.b1 - it.b0) * kbpb;
+        for (int step = 0; step < steps; ++step) {
+          const int b = it.b0 + step / kbpb, k0 = (step % kbpb) * KB;
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes), sb = sa + kABytes;
+          mbar_wait(&sh->empty[stage], phase ^ 1, wc, 11);      // the MMAs that read this stage are done
+          const long long abase = (long long)b * p.a_batch, bbase = (long long)b * p.b_batch;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) cs[e] = 0.f;
-    uint32_t stage = 0, phase = 0;
-
-    // group g of a k-block: 0 = the four A chunks, 1 / 2 = B chunks 0-3 / 4-7
-    auto issue = [&](const Item& it, int step, int g, Raw& raw) {
-      const int b = it.b0 + step / kbpb, k0 = (step % kbpb) * kKB;
-      if (g == 0) {
-        const int m = it.m0 + a_o * 8;
-        const int valid_m = max(0, min(8, p.M - m));
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int k = k0 + a_k + 16 * c;
-          const int valid = k < p.K ? valid_m : 0;
-          load_chunk(p.a, (long long)b * p.a_batch + (long long)k * p.lda + m, valid, a_bf16, a_vec, raw.v[2 * c], raw.v[2 * c + 1]);
-        }
-      } else {
-        const int k = k0 + b_j * 8;
-        const int valid_k = max(0, min(8, p.K - k));
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int n = it.n0 + b_n + 32 * (c + 4 * (g - 1));
-          const int valid = n < p.N ? valid_k : 0;
-          load_chunk(p.b, (long long)b * p.b_batch + (long long)n * p.ldb + k, valid, b_bf16, b_vec, raw.v[2 * c], raw.v[2 * c + 1]);
-        }
-      }
-    };
-    auto commit = [&](const Item& it, int g, const Raw& raw) {
-      uint8_t* sa = smem + stage * kStageBytes;
-      uint8_t* sb = sa + kABytes;
-      if (g == 0) {
-        mbar_wait(&sh->empty[stage], phase ^ 1, wc, 11);        // the MMAs that read this stage are done
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint4 v = to_bf16x8(a_bf16, raw.v[2 * c], raw.v[2 * c + 1]);
-          st_chunk(sa + (a_o >> 3) * kABlock, a_k + 16 * c, a_o & 7, v);
-          if (MODE == kDW && p.dbias && it.n0 == 0) {           // column sums of dy: every dy element passes here once
-            cs[0] += bf16lo(v.x); cs[1] += bf16hi(v.x); cs[2] += bf16lo(v.y); cs[3] += bf16hi(v.y);
-            cs[4] += bf16lo(v.z); cs[5] += bf16hi(v.z); cs[6] += bf16lo(v.w); cs[7] += bf16hi(v.w);
+          for (int c = 0; c < 4; ++c) {                         // A: [KB k rows][128 m], 16-byte chunks along m
+            const int q = t + kStageThreads * c, row = q / CPR, o = q % CPR;
+            const int k = k0 + row, m = it.m0 + o * EPC;
+            const int valid = k < p.K ? max(0, min(EPC, p.M - m)) : 0;
+            const uint8_t* src = valid ? ga + (abase + (long long)k * p.lda + m) * ES : ga;
+            // bf16: 16-byte chunk ^ (row mod 8) (SWIZZLE_128B); fp32: 32-byte chunk ^ (row mod 4) (SWIZZLE_128B_BASE32B)
+            const int j = o & 7, js = TF32 ? ((((j >> 1) ^ (row & 3)) << 1) | (j & 1)) : (j ^ (row & 7));
+            cp_async16(sa + (o >> 3) * kABlk + row * 128 + (js << 4), src, valid * ES);
           }
-        }
-      } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          st_chunk(sb, b_n + 32 * (c + 4 * (g - 1)), b_j, to_bf16x8(b_bf16, raw.v[2 * c], raw.v[2 * c + 1]));
-        if (g == 2) {
-          fence_proxy_async_smem();
-          mbar_arrive(&sh->full[stage]);
+          for (int c = 0; c < 8; ++c) {                         // B: [256 n rows][KB k], 16-byte chunks along k
+            const int q = t + kStageThreads * c, n = q >> 3, j = q & 7;
+            const int k = k0 + j * EPC;
+            const int valid = (it.n0 + n) < p.N ? max(0, min(EPC, p.K - k)) : 0;
+            const uint8_t* src = valid ? gb + (bbase + (long long)(it.n0 + n) * p.ldb + k) * ES : gb;
+            cp_async16(sb + n * 128 + ((j ^ (n & 7)) << 4), src, valid * ES);
+          }
+          cp_async_arrive_noinc(&sh->full[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-    };
+    } else {
+      const bool a_bf16 = p.a_bf16 != 0, b_bf16 = p.b_bf16 != 0;
+      const bool a_vec = (p.lda % (a_bf16 ? 8 : 4) == 0) && (p.a_batch % (a_bf16 ? 8 : 4) == 0);
+      const bool b_vec = (p.ldb % (b_bf16 ? 8 : 4) == 0) && (p.b_batch % (b_bf16 ? 8 : 4) == 0);
+      const int a_o = t & 15, a_k = t >> 4;                      // A chunk: m octet, k row (+16 per chunk)
+      const int b_j = t & 7, b_n = t >> 3;                       // B chunk: k octet, n row (+32 per chunk)
+      uint32_t stage = 0, phase = 0;
 
-    // rolling pipeline over all groups of all k-blocks of all items: the loads of group i+1 are issued before
-    // group i is converted and stored (two groups = 256 bytes per thread in flight); two register sets, ping-pong
-    struct Pos { Item it; int item, steps, step, g; };
-    auto advance = [&](Pos& q) -> bool {
-      if (++q.g == 3) { q.g = 0; ++q.step; }
-      if (q.step == q.steps) {
-        q.item += gridDim.x; q.step = 0;
-        if (q.item >= n_items) return false;
-        q.it = decode_item<MODE>(p, q.item); q.steps = (q.it.b1 - q.it.b0) * kbpb;
-      }
-      return true;
-    };
-    if ((int)blockIdx.x < n_items) {
-      Raw r0, r1;
-      Pos pos;
-      pos.item = blockIdx.x; pos.it = decode_item<MODE>(p, pos.item); pos.steps = (pos.it.b1 - pos.it.b0) * kbpb; pos.step = 0; pos.g = 0;
-      issue(pos.it, pos.step, pos.g, r0);
-      while (true) {
-        Pos np = pos;
-        bool more = advance(np);
-        if (more) issue(np.it, np.step, np.g, r1);
-        commit(pos.it, pos.g, r0);
-        if (!more) break;
-        pos = np;
-        more = advance(np);
-        if (more) issue(np.it, np.step, np.g, r0);
-        commit(pos.it, pos.g, r1);
-        if (!more) break;
-        pos = np;
-      }
-    }
-    if (MODE == kDW && p.dbias) {
-      // thread t holds partial sums of columns m0 + 8 a_o + e over its k rows; all items of a CTA share m0 (one item per CTA)
-      const Item it0 = decode_item<MODE>(p, blockIdx.x);
-      if (blockIdx.x < n_items && it0.n0 == 0) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(&sh->colsum[a_o * 8 + e], cs[e]);
-        asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");
-        if (t < kM && it0.m0 + t < p.M) atomicAdd(p.dbias + it0.m0 + t, sh->colsum[t]);
+      // group g of a k-block: 0 = the four A chunks, 1 / 2 = B chunks 0-3 / 4-7
+      auto issue = [&](const Item& it, int step, int g, Raw& raw) {
+        const int b = it.b0 + step / kbpb, k0 = (step % kbpb) * KB;
+        if (g == 0) {
+          const int m = it.m0 + a_o * 8;
+          const int valid_m = max(0, min(8, p.M - m));
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int k = k0 + a_k + 16 * c;
+            const int valid = k < p.K ? valid_m : 0;
+            load_chunk(p.a, (long long)b * p.a_batch + (long long)k * p.lda + m, valid, a_bf16, a_vec, raw.v[2 * c], raw.v[2 * c + 1]);
+          }
+        } else {
+          const int k = k0 + b_j * 8;
+          const int valid_k = max(0, min(8, p.K - k));
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int n = it.n0 + b_n + 32 * (c + 4 * (g - 1));
+            const int valid = n < p.N ? valid_k : 0;
+            load_chunk(p.b, (long long)b * p.b_batch + (long long)n * p.ldb + k, valid, b_bf16, b_vec, raw.v[2 * c], raw.v[2 * c + 1]);
+          }
+        }
+      };
+      auto commit = [&](int g, const Raw& raw) {
+        uint8_t* sa = smem + stage * kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        if (g == 0) {
+          mbar_wait(&sh->empty[stage], phase ^ 1, wc, 11);        // the MMAs that read this stage are done
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 v = to_bf16x8(a_bf16, raw.v[2 * c], raw.v[2 * c + 1]);
+            st_chunk(sa + (a_o >> 3) * kABlk, a_k + 16 * c, a_o & 7, v);
+          }
+        } else {
+  #pragma unroll
+          for (int c = 0; c < 4; ++c)
+            st_chunk(sb, b_n + 32 * (c + 4 * (g - 1)), b_j, to_bf16x8(b_bf16, raw.v[2 * c], raw.v[2 * c + 1]));
+          if (g == 2) {
+            fence_proxy_async_smem();
+            mbar_arrive(&sh->full[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      };
+
+      // rolling pipeline over all groups of all k-blocks of all items: the loads of group i+1 are issued before
+      // group i is converted and stored (two groups = 256 bytes per thread in flight); two register sets, ping-pong
+      struct Pos { Item it; int item, steps, step, g; };
+      auto advance = [&](Pos& q) -> bool {
+        if (++q.g == 3) { q.g = 0; ++q.step; }
+        if (q.step == q.steps) {
+          q.item += gridDim.x; q.step = 0;
+          if (q.item >= n_items) return false;
+          q.it = decode_item<MODE>(p, q.item); q.steps = (q.it.b1 - q.it.b0) * kbpb;
+        }
+        return true;
+      };
+      if ((int)blockIdx.x < n_items) {
+        Raw r0, r1;
+        Pos pos;
+        pos.item = blockIdx.x; pos.it = decode_item<MODE>(p, pos.item); pos.steps = (pos.it.b1 - pos.it.b0) * kbpb; pos.step = 0; pos.g = 0;
+        issue(pos.it, pos.step, pos.g, r0);
+        while (true) {
+          Pos np = pos;
+          bool more = advance(np);
+          if (more) issue(np.it, np.step, np.g, r1);
+          commit(pos.g, r0);
+          if (!more) break;
+          pos = np;
+          more = advance(np);
+          if (more) issue(np.it, np.step, np.g, r0);
+          commit(pos.g, r1);
+          if (!more) break;
+          pos = np;
+        }
       }
     }
   } else if (warp == kMmaWarp) {
     // =============================== MMA issue: one elected thread ===============================
     if (elect_one()) {
-      constexpr uint32_t idesc = idesc_bf16(kM, kN, true, false);
+      constexpr uint32_t idesc = TF32 ? idesc_tf32(kM, kN, true, false) : idesc_bf16(kM, kN, true, false);
       uint32_t stage = 0, phase = 0, n_acc = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_acc) {
         const Item it = decode_item<MODE>(p, item);
@@ -264,13 +290,16 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadPara
         const uint32_t acc = tmem + buf * kAccCols;
         for (int step = 0; step < steps; ++step) {
           mbar_wait(&sh->full[stage], phase, wc, 13);
+          if (FAST) fence_proxy_async_smem();                                // cp.async wrote through the generic proxy
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes), sb = sa + kABytes;
 #pragma unroll
-          for (int ks = 0; ks < kKB / 16; ++ks) {
-            const Desc da = make_desc(sa + ks * 2048, kABlock, 1024);       // MN-major: 16 k rows = 2048 bytes per step
-            const Desc db = make_desc(sb + ks * 32, 16, 1024);              // K-major: 16 k = 32 bytes inside the row
-            mma_ss(acc, da, db, idesc, step > 0 || ks > 0);
+          for (int ks = 0; ks < 4; ++ks) {                                   // 16 k (bf16) / 8 k (tf32) per MMA
+            // MN-major: a quarter of the k rows per step; tf32: 4-row swizzle groups (512 bytes), bf16: 8-row groups
+            const Desc da = TF32 ? smem_desc_base32b(sa + ks * (kABlk / 4), kABlk, 512) : make_desc(sa + ks * (kABlk / 4), kABlk, 1024);
+            const Desc db = make_desc(sb + ks * 32, 16, 1024);              // K-major: 32 bytes inside the row per step
+            if (TF32) mma_ss_tf32(acc, da, db, idesc, step > 0 || ks > 0);
+            else mma_ss(acc, da, db, idesc, step > 0 || ks > 0);
           }
           mma_commit(&sh->empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -401,15 +430,52 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadPara
 
 constexpr int kHeadSmem = kStages * kStageBytes + (int)sizeof(HeadShared) + 1024;
 
+// column sums of dy[rows, 256] -> dbias (fp32 atomics into a zero-filled vector): thread = (8 columns, one of 8 row lanes)
+template <typename T>
+__global__ void __launch_bounds__(256) head_colsum_kernel(const T* __restrict__ dy, long long rows, float* __restrict__ dbias) {
+  __shared__ float part[8][kN];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 4
+  for (long long r = r0 + rl; r < r1; r += 8) {
+    const float4 a = ld4_nc(dy + r * kN + cg * 8), b = ld4_nc(dy + r * kN + cg * 8 + 4);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[rl][cg * 8 + e] = acc[e];
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x];
+  atomicAdd(dbias + threadIdx.x, s);
+}
+
+// fast path: both operands of one dtype, every row start 16-byte aligned (cp.async)
+bool fast_ok(const HeadParams& p) {
+  if (p.a_bf16 != p.b_bf16) return false;
+  const int epc = p.a_bf16 ? 8 : 4;
+  return p.lda % epc == 0 && p.ldb % epc == 0 && p.a_batch % epc == 0 && p.b_batch % epc == 0;
+}
+
+template <int MODE, bool FAST, bool TF32>
+int launch_head_as(const HeadParams& p, int grid, cudaStream_t st) {
+  XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(region_head_kernel<MODE, FAST, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
+  region_head_kernel<MODE, FAST, TF32><<<grid, kThreads, kHeadSmem, st>>>(p);
+  return cuda_fail(cudaGetLastError(), "region_head_kernel launch");
+}
+
 template <int MODE>
 int launch_head(const HeadParams& p, int n_items, cudaStream_t st) {
   int dev = 0, sms = 148;
   XMC_RETURN_IF_CUDA(cudaGetDevice(&dev));
   XMC_RETURN_IF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(region_head_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
   const int grid = n_items < sms ? n_items : sms;
-  region_head_kernel<MODE><<<grid, kThreads, kHeadSmem, st>>>(p);
-  return cuda_fail(cudaGetLastError(), "region_head_kernel launch");
+  if (!fast_ok(p)) return launch_head_as<MODE, false, false>(p, grid, st);
+  return p.a_bf16 ? launch_head_as<MODE, true, false>(p, grid, st) : launch_head_as<MODE, true, true>(p, grid, st);
 }
 
 int check_dt(int dt) { return dt == XMC_F32 || dt == XMC_BF16; }
@@ -436,34 +502,41 @@ extern "C" int xmc_region_head_forward(const void* feat, int feat_dtype, const v
   return launch_head<kFwd>(p, B * p.m_tiles, as_stream(stream));
 }
 
-extern "C" int xmc_region_head_backward_input(const void* weight, int weight_dtype, const void* dy, int B, int Cin, int R,
-                                              int D, void* dfeat, int out_dtype, void* stream) {
+extern "C" int xmc_region_head_backward_input(const void* weight, int weight_dtype, const void* dy, int dy_dtype, int B, int Cin,
+                                              int R, int D, void* dfeat, int out_dtype, void* stream) {
   XMC_REQUIRE(weight && dy && dfeat, XMC_ERR_INVALID_ARG, "null pointer");
-  XMC_REQUIRE(check_dt(weight_dtype) && check_dt(out_dtype), XMC_ERR_UNSUPPORTED, "dtype must be XMC_F32 or XMC_BF16");
+  XMC_REQUIRE(check_dt(weight_dtype) && check_dt(out_dtype) && check_dt(dy_dtype), XMC_ERR_UNSUPPORTED, "dtype must be XMC_F32 or XMC_BF16");
   XMC_REQUIRE(B > 0 && Cin > 0 && R > 0, XMC_ERR_INVALID_ARG, "bad shape B=%d Cin=%d R=%d", B, Cin, R);
   XMC_REQUIRE(D == kN, XMC_ERR_UNSUPPORTED, "region head: D=%d unsupported (256)", D);
   XMC_REQUIRE(aligned16(weight) && aligned16(dy) && aligned16(dfeat), XMC_ERR_ALIGNMENT, "pointers must be 16-byte aligned");
   HeadParams p{};
   p.a = weight; p.a_batch = 0; p.lda = Cin; p.a_bf16 = weight_dtype == XMC_BF16;      // A[k = d][m = channel]
-  p.b = dy; p.b_batch = (long long)R * D; p.ldb = D; p.b_bf16 = 1;                    // B[n = pixel][k = d]
+  p.b = dy; p.b_batch = (long long)R * D; p.ldb = D; p.b_bf16 = dy_dtype == XMC_BF16;  // B[n = pixel][k = d]
   p.M = Cin; p.N = R; p.K = D;
   p.m_tiles = (Cin + kM - 1) / kM; p.n_tiles = (R + kN - 1) / kN; p.batches = B; p.splits = 1;
   p.dfeat = dfeat; p.out_bf16 = out_dtype == XMC_BF16;
   return launch_head<kDFeat>(p, B * p.m_tiles * p.n_tiles, as_stream(stream));
 }
 
-extern "C" int xmc_region_head_backward_weight(const void* feat, int feat_dtype, const void* dy, int B, int Cin, int R, int D,
-                                               float* dweight, float* dbias, void* stream) {
+extern "C" int xmc_region_head_backward_weight(const void* feat, int feat_dtype, const void* dy, int dy_dtype, int B, int Cin, int R,
+                                               int D, float* dweight, float* dbias, void* stream) {
   XMC_REQUIRE(feat && dy && dweight, XMC_ERR_INVALID_ARG, "null pointer");
-  XMC_REQUIRE(check_dt(feat_dtype), XMC_ERR_UNSUPPORTED, "dtype must be XMC_F32 or XMC_BF16");
+  XMC_REQUIRE(check_dt(feat_dtype) && check_dt(dy_dtype), XMC_ERR_UNSUPPORTED, "dtype must be XMC_F32 or XMC_BF16");
   XMC_REQUIRE(B > 0 && Cin > 0 && R > 0, XMC_ERR_INVALID_ARG, "bad shape B=%d Cin=%d R=%d", B, Cin, R);
   XMC_REQUIRE(D == kN, XMC_ERR_UNSUPPORTED, "region head: D=%d unsupported (256)", D);
   XMC_REQUIRE(aligned16(feat) && aligned16(dy) && aligned16(dweight), XMC_ERR_ALIGNMENT, "pointers must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   XMC_RETURN_IF_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * (size_t)D * Cin, st));
-  if (dbias) XMC_RETURN_IF_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)D, st));
+  if (dbias) {
+    XMC_RETURN_IF_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)D, st));
+    const long long rows = (long long)B * R;
+    const unsigned grid = (unsigned)(rows < 296 * 8 ? (rows + 7) / 8 : 296);
+    if (dy_dtype == XMC_BF16) head_colsum_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), rows, dbias);
+    else head_colsum_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(dy), rows, dbias);
+    XMC_RETURN_IF_CUDA(cudaGetLastError());
+  }
   HeadParams p{};
-  p.a = dy; p.a_batch = (long long)R * D; p.lda = D; p.a_bf16 = 1;                    // A[k = pixel][m = d]
+  p.a = dy; p.a_batch = (long long)R * D; p.lda = D; p.a_bf16 = dy_dtype == XMC_BF16;   // A[k = pixel][m = d]
   p.b = feat; p.b_batch = (long long)Cin * R; p.ldb = R; p.b_bf16 = feat_dtype == XMC_BF16;   // B[n = channel][k = pixel]
   p.M = D; p.N = Cin; p.K = R;
   p.m_tiles = D / kM; p.n_tiles = (Cin + kN - 1) / kN; p.batches = B;

@@ -102,6 +102,14 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
+// 16-byte asynchronous copy global -> shared (no registers); src_bytes < 16 zero-fills the rest of the chunk
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+// the executing thread's earlier cp.async copies arrive on `bar` when they have landed (counts as one pending arrival)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / TMA reading smem)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -173,9 +181,25 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
          (1ull << 46) |      // descriptor version (Blackwell)
          (2ull << 61);       // SWIZZLE_128B
 }
+// MN-major operand of 32-bit elements (kind::tf32): layout type SWIZZLE_128B_BASE32B — rows of 128 bytes (32 MN elements),
+// 4-K-row groups SBO apart, next 32-element MN block LBO apart; inside a group the 32-BYTE chunk index is XORed with
+// (row mod 4) (address bits [5,7) ^= bits [7,9)).
+__device__ __forceinline__ uint64_t smem_desc_base32b(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) |
+         (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+         (1ull << 46) |
+         (1ull << 61);       // SWIZZLE_128B_BASE32B
+}
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, M x N, per-operand major-ness.
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// kind::tf32: fp32 storage read as tf32 (10-bit mantissa, K = 8 per instruction) -> fp32
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
@@ -211,6 +235,13 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, Desc a, Desc b, uint32_t
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate ? 1u : 0u)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ss_tf32(uint32_t d_tmem, Desc a, Desc b, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate ? 1u : 0u)
       : "memory");
 }

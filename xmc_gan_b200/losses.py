@@ -321,7 +321,7 @@ def _head_operands(regions, head):
     """(feat [B, Cin, R] contiguous, weight [D, Cin], bias [D] fp32 or None) of a fused region head."""
     weight, bias = head
     feat = regions.detach().flatten(2).contiguous()
-    w2 = weight.detach().reshape(weight.shape[0], -1).contiguous()
+    w2 = weight.detach().reshape(weight.shape[0], -1).to(feat.dtype).contiguous()    # one dtype per product: the cp.async path
     if w2.shape[1] != feat.shape[1]:
         raise ValueError(f"region_head weight {tuple(weight.shape)} does not take {feat.shape[1]} input channels")
     b1 = None if bias is None else bias.detach().to(torch.float32).contiguous()
@@ -469,7 +469,7 @@ def _word_backward(ops, st: _Word, go, need_reg, need_w, need_head=(False, False
     if st.head is not None:                    # fused region head: d y rows (bf16) -> the head's two backward products
         if need_reg or any(need_head):
             feat, w2 = st.head
-            dy = ops.normalize_rows_backward(kn, st.rnorm, dkn, drnorm, st.R, torch.bfloat16, error_word=ws)
+            dy = ops.normalize_rows_backward(kn, st.rnorm, dkn, drnorm, st.R, feat.dtype, error_word=ws)    # [B, R, D]
             dfeat, dwgt, dbias = ops.region_head_backward(feat, w2, dy, need_reg, need_head[0], need_head[1])
             dreg = dfeat.view(st.reg_shape) if dfeat is not None else None
             st.dhead = (dwgt, dbias)

@@ -377,7 +377,7 @@ class CudaOps:
         return kn, rnorm
 
     def region_head_backward(self, feat, weight, dy, need_feat, need_weight, need_bias):
-        """dy [B, R, D] bf16 -> (dfeat like feat or None, dweight [D, Cin] fp32 or None, dbias [D] fp32 or None)."""
+        """dy [B, R, D] (bf16 / fp32) -> (dfeat like feat or None, dweight [D, Cin] fp32 or None, dbias [D] fp32 or None)."""
         _cuda(feat, weight, dy)
         B, Cin, R = feat.shape
         D = weight.shape[0]
@@ -385,15 +385,15 @@ class CudaOps:
         with _on(feat), self._timed("region_head_bwd"):
             if need_feat:
                 dfeat = torch.empty_like(feat)
-                self._check(self.L.xmc_region_head_backward_input(_p(weight), _dt(weight), _p(dy), B, Cin, R, D, _p(dfeat),
-                                                                  _dt(dfeat), _stream()))
+                self._check(self.L.xmc_region_head_backward_input(_p(weight), _dt(weight), _p(dy), _dt(dy), B, Cin, R, D,
+                                                                  _p(dfeat), _dt(dfeat), _stream()))
                 self.launches += 1
             if need_weight or need_bias:
                 dweight = torch.empty(D, Cin, device=feat.device, dtype=torch.float32)
                 dbias = torch.empty(D, device=feat.device, dtype=torch.float32) if need_bias else None
-                self._check(self.L.xmc_region_head_backward_weight(_p(feat), _dt(feat), _p(dy), B, Cin, R, D, _p(dweight),
-                                                                   _p(dbias), _stream()))
-                self.launches += 1
+                self._check(self.L.xmc_region_head_backward_weight(_p(feat), _dt(feat), _p(dy), _dt(dy), B, Cin, R, D,
+                                                                   _p(dweight), _p(dbias), _stream()))
+                self.launches += 1 + (1 if need_bias else 0)
         return dfeat, dweight, dbias
 
     def _check_error_word(self, ws, what):
