@@ -217,12 +217,16 @@ def run_step_workload(args):
     W, K = max(args.warmup, 3), args.steps
     res = {}
     for word in (False, True):
-        for name, ns, wkw in (("stock", stock_losses, None), ("xmc_gan_b200", T, {"precision": "bf16"})):
+        variants = [("stock", stock_losses, None, False), ("xmc_gan_b200", T, {"precision": "bf16"}, False)]
+        if word:       # N2: the region head inside the word loss's prologue instead of a convolution of the network
+            variants.append(("xmc_gan_b200_fused_head", T, {"precision": "bf16"}, True))
+        for name, ns, wkw, fused in variants:
             cfg = S.default_step_cfg()
             cfg.TRAIN.ENCODER_LOSS.WORD = word
             def one():
                 noise = torch.randn(B, 100, device=dev)
-                return S.gd_step(G, D, optG, optD, imgs, words, sent, mask, noise, cfg=cfg, losses=ns, word_kwargs=wkw)
+                return S.gd_step(G, D, optG, optD, imgs, words, sent, mask, noise, cfg=cfg, losses=ns, word_kwargs=wkw,
+                                 fused_region_head=fused)
             for _ in range(W):
                 out = one()
             torch.cuda.synchronize()
@@ -238,7 +242,7 @@ def run_step_workload(args):
                         "MA-GP, sent_loss + img_loss%s, batch %d, fp32 networks" % (" (+ word_loss T=18, R=16x16, bf16 tcgen05 path)", B),
             "n_gpus": 1, "steps": K, "warmup": W, "unit": "ms/step", "higher_is_better": False, "data": "synthetic",
             "sent+img": {n: res[("no_word", n)] for n in ("stock", "xmc_gan_b200")},
-            "sent+img+word": {n: res[("word", n)] for n in ("stock", "xmc_gan_b200")}}
+            "sent+img+word": {n: res[("word", n)] for n in ("stock", "xmc_gan_b200", "xmc_gan_b200_fused_head")}}
     for k in ("sent+img", "sent+img+word"):
         line[k]["speedup"] = line[k]["stock"]["ms_per_step"] / line[k]["xmc_gan_b200"]["ms_per_step"]
     print(json.dumps(line), flush=True)

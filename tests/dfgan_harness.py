@@ -155,6 +155,6 @@ class NetD(nn.Module):
         regions = None
         for i, blk in enumerate(self.downblocks):
             h = blk(h)
-            if with_regions and i == self.region_index:
-                regions = self.region_head(h)
+            if with_regions and i == self.region_index:     # "features": the stage's map, for a head fused into the loss
+                regions = h if with_regions == "features" else self.region_head(h)
         return (h, regions) if with_regions else h

@@ -34,7 +34,7 @@ def _setup(B, size, nch, nef, T_, seed=0):
     return G, D, imgs, words, sent.cuda(), mask, noise
 
 
-def _grads(G, D, inputs, losses, cfg, word_kwargs=None):
+def _grads(G, D, inputs, losses, cfg, word_kwargs=None, fused_region_head=False):
     from xmc_gan_b200 import step as S
     imgs, words, sent, mask, noise = inputs
     snap = {}
@@ -42,13 +42,14 @@ def _grads(G, D, inputs, losses, cfg, word_kwargs=None):
     def after_d():
         snap["D"] = {n: p.grad.detach().clone() for n, p in D.named_parameters() if p.grad is not None}
     out = S.gd_step(G, D, None, None, imgs, words, sent, mask, noise, cfg=cfg, losses=losses, do_step=False,
-                    after_d_backward=after_d, word_kwargs=word_kwargs)
+                    after_d_backward=after_d, word_kwargs=word_kwargs, fused_region_head=fused_region_head)
     snap["G"] = {n: p.grad.detach().clone() for n, p in G.named_parameters() if p.grad is not None}
     return snap, {k: float(v) for k, v in out.items()}
 
 
-@pytest.mark.parametrize("b_global,word_precision,tol", [(False, None, 1e-4), (True, None, 1e-4), (False, "bf16", 2e-2)])
-def test_swapping_the_loss_ops_leaves_the_step_gradients_unchanged(b_global, word_precision, tol):
+@pytest.mark.parametrize("b_global,word_precision,tol,fused", [(False, None, 1e-4, False), (True, None, 1e-4, False),
+                                                              (False, "bf16", 2e-2, False), (False, "bf16", 2e-2, True)])
+def test_swapping_the_loss_ops_leaves_the_step_gradients_unchanged(b_global, word_precision, tol, fused):
     import stock_losses
     from xmc_gan_b200 import step as S
     from xmc_gan_b200 import train_gan as T
@@ -61,7 +62,8 @@ def test_swapping_the_loss_ops_leaves_the_step_gradients_unchanged(b_global, wor
         cfg.TRAIN.ENCODER_LOSS.WORD = True
         cfg.TRAIN.SMOOTH.SENT = cfg.TRAIN.SMOOTH.DISC = cfg.TRAIN.SMOOTH.WORD = 1.0
         ref, ref_out = _grads(G, D, inputs, stock_losses, cfg)
-        got, got_out = _grads(G, D, inputs, T, cfg, word_kwargs={"precision": word_precision} if word_precision else None)
+        got, got_out = _grads(G, D, inputs, T, cfg, word_kwargs={"precision": word_precision} if word_precision else None,
+                              fused_region_head=fused)       # fused: the region head runs in the word loss's prologue (N2)
         for k in ("errD", "errG", "ds_loss", "gs_loss", "disc_loss", "dw_loss", "gw_loss"):
             assert abs(got_out[k] - ref_out[k]) <= tol * max(1.0, abs(ref_out[k])), (k, got_out[k], ref_out[k])
         for which in ("D", "G"):

@@ -11,7 +11,10 @@ check that swapping the ops leaves every parameter gradient unchanged.
 
 What the reference leaves as ``raise NotImplementedError`` (:220-222, :267-269) is filled in: with
 ``cfg.TRAIN.ENCODER_LOSS.WORD`` the word loss is evaluated on region features — ``netD(imgs, with_regions=True)``
-must then return ``(features, regions [B, NEF, H, W])``.
+must then return ``(features, regions [B, NEF, H, W])``.  With ``fused_region_head=True`` the 1x1 region head is not run
+by the network: ``netD(imgs, with_regions="features")`` returns the stage's feature map ``[B, Cin, H, W]`` and
+``netD.region_head.proj`` (a ``Conv2d(Cin, NEF, 1)``) goes to ``word_loss(region_head=...)``, which projects,
+normalises and casts in one tensor-core kernel of the loss prologue.
 """
 from __future__ import annotations
 
@@ -34,7 +37,7 @@ def default_step_cfg():
 
 
 def gd_step(netG, netD, optimizerG, optimizerD, imgs, words_embs, sent_embs, mask, noise, cfg=None, losses=None,
-            group=None, word_kwargs=None, do_step=True, after_d_backward=None):
+            group=None, word_kwargs=None, do_step=True, after_d_backward=None, fused_region_head=False):
     """-> dict of the step's scalars (tensors, no host sync): errD, errG, ds_loss, gs_loss, disc_loss, dw_loss, gw_loss, d_gp.
 
     ``do_step=False`` skips the optimiser updates and the gradient penalty (gradients stay in ``.grad``);
@@ -52,7 +55,11 @@ def gd_step(netG, netD, optimizerG, optimizerD, imgs, words_embs, sent_embs, mas
 
     # ---- discriminator ----
     want_regions = bool(E.WORD)
-    real_features = netD(imgs, with_regions=True) if want_regions else netD(imgs)       # :193
+    with_regions = True
+    if fused_region_head and want_regions:              # N2: the head runs inside the loss prologue
+        with_regions = "features"
+        wkw["region_head"] = netD.region_head.proj
+    real_features = netD(imgs, with_regions=with_regions) if want_regions else netD(imgs)       # :193
     real_features, real_regions = real_features if want_regions else (real_features, None)
     outputs_real = netD.COND_DNET(real_features, sent_embs=psent.detach())               # :194
     errD_real = F.relu(1.0 - outputs_real[0]).mean()                                     # :195
@@ -95,7 +102,7 @@ def gd_step(netG, netD, optimizerG, optimizerD, imgs, words_embs, sent_embs, mas
         out["d_gp"] = d_gp.detach()
 
     # ---- generator ----
-    features = netD(fake, with_regions=True) if want_regions else netD(fake)             # :259
+    features = netD(fake, with_regions=with_regions) if want_regions else netD(fake)     # :259
     features, fake_regions = features if want_regions else (features, None)
     outputs = netD.COND_DNET(features, sent_embs=psent)                                  # :260
     errG = -outputs[0].mean()                                                            # :261
