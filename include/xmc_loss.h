@@ -236,6 +236,13 @@ int xmc_region_head_backward_input(const void* weight, int weight_dtype, const v
 int xmc_region_head_backward_weight(const void* feat, int feat_dtype, const void* dy, int dy_dtype, int B, int Cin, int R,
                                     int D, float* dweight, float* dbias, void* stream);
 
+/* Pooled image embedding, the producer of sent_loss's image operand and of both img_loss operands:
+ * F.avg_pool2d(x, kernel_size = H).view(B, -1) on the discriminator's last stage (xmc_gan/model/df_gan.py:165-166,
+ * xmc_gan/train_gan.py:271-276).  x[B, C, P] (P = H*W pixels, contiguous) -> out[B, C] = mean over P, written in out_dtype
+ * (XMC_BF16 feeds the bf16 similarity path without a cast pass).  Backward: dx[b, c, p] = dout[b, c] / P. */
+int xmc_avgpool_rows(const void* x, int in_dtype, int B, int C, int P, void* out, int out_dtype, void* stream);
+int xmc_avgpool_rows_backward(const void* dout, int g_dtype, int B, int C, int P, void* dx, int out_dtype, void* stream);
+
 size_t xmc_wordregion_workspace_bytes(int path, int NQ, int Bi, int R, int Rpad, int D);
 
 /* qn[NQ,D]: unit word rows (NQ = Bc*T); kn[Bi,Rpad,D]: unit region rows; rnorm[Bi,Rpad]: region

@@ -172,3 +172,25 @@ def test_fused_head_equals_unfused_projection():
     l3 = T.word_loss(f3, words.clone().cuda(), mask.cuda(), labels, False, precision="fp32", region_head=conv)
     l4 = T.word_loss(conv(f3), words.clone().cuda(), mask.cuda(), labels, False, precision="fp32")
     assert lerr(l3, l4) <= 1e-6
+
+
+@pytest.mark.parametrize("B,C,H,dt", [(256, 512, 4, torch.float32), (7, 96, 4, torch.bfloat16), (5, 33, 3, torch.float32)])
+def test_pooled_features_match_avg_pool2d(B, C, H, dt):
+    """train_gan.pooled_features == F.avg_pool2d(x, H).view(B, -1) (df_gan.py:165-166, train_gan.py:271-276), forward and backward."""
+    import torch.nn.functional as F
+    from xmc_gan_b200 import train_gan as T
+    g = torch.Generator().manual_seed(B + C)
+    x0 = torch.randn(B, C, H, H, generator=g).to(dt)
+    go = torch.randn(B, C, generator=g).to(dt)
+    x = x0.clone().cuda().requires_grad_()
+    y = T.pooled_features(x)
+    y.backward(go.cuda())
+    xr = x0.clone().cuda().requires_grad_()
+    yr = F.avg_pool2d(xr, kernel_size=H).view(B, -1)
+    yr.backward(go.cuda())
+    tol = 1e-6 if dt == torch.float32 else 8e-3
+    assert y.dtype == dt and y.shape == (B, C)
+    assert float((y.float() - yr.float()).abs().max()) <= tol * max(1.0, float(yr.float().abs().max()))
+    assert float((x.grad.float() - xr.grad.float()).abs().max()) <= tol * max(1.0, float(xr.grad.float().abs().max()))
+    yb = T.pooled_features(x.detach(), out_dtype=torch.bfloat16)
+    assert yb.dtype == torch.bfloat16 and float((yb.float() - yr.float()).abs().max()) <= 8e-3 * max(1.0, float(yr.float().abs().max()))

@@ -58,6 +58,8 @@ SIGNATURES = {
     "xmc_region_head_forward": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "xmc_region_head_backward_input": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "xmc_region_head_backward_weight": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "xmc_avgpool_rows": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "xmc_avgpool_rows_backward": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "xmc_wordregion_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "xmc_wordregion_forward": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "xmc_wordregion_backward": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp,

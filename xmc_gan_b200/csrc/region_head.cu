@@ -454,6 +454,37 @@ __global__ void __launch_bounds__(256) head_colsum_kernel(const T* __restrict__ 
   atomicAdd(dbias + threadIdx.x, s);
 }
 
+// ---- pooled embedding: x[B, C, P] -> out[B, C] = mean over the P pixels ------------------------------------------
+// F.avg_pool2d(x, kernel_size = H).view(B, -1) on the discriminator's last 4 x 4 stage: the producer of sent_loss's image
+// operand (df_gan.py:165-166) and of both img_loss operands (train_gan.py:271-276).  One thread per (b, c): P
+// contiguous elements in, one out (optionally cast to bf16 for the bf16 similarity path); HBM-bound, 8.4 MB at
+// B = 256, C = 512, P = 16.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) avgpool_rows_kernel(const TI* __restrict__ x, long long n, int P, float inv, TO* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const TI* s = x + i * P;
+  float acc = 0.f;
+  if (P % 4 == 0) {
+    for (int q = 0; q < P; q += 4) { const float4 v = ld4_nc(s + q); acc += (v.x + v.y) + (v.z + v.w); }
+  } else {
+    for (int q = 0; q < P; ++q) acc += ld1(s + q);
+  }
+  st1(out + i, acc * inv);
+}
+template <typename TG, typename TO>
+__global__ void __launch_bounds__(256) avgpool_rows_bwd_kernel(const TG* __restrict__ dout, long long n, int P, float inv, TO* __restrict__ dx) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float g = ld1(dout + i) * inv;
+  TO* d = dx + i * P;
+  if (P % 4 == 0) {
+    for (int q = 0; q < P; q += 4) st4(d + q, make_float4(g, g, g, g));
+  } else {
+    for (int q = 0; q < P; ++q) st1(d + q, g);
+  }
+}
+
 // fast path: both operands of one dtype, every row start 16-byte aligned (cp.async)
 bool fast_ok(const HeadParams& p) {
   if (p.a_bf16 != p.b_bf16) return false;
@@ -553,4 +584,43 @@ extern "C" int xmc_region_head_backward_weight(const void* feat, int feat_dtype,
   p.splits = splits;
   p.dw = dweight; p.dbias = dbias;
   return launch_head<kDW>(p, tiles * splits, st);
+}
+
+/* pooled embedding and its backward (see avgpool_rows_kernel) */
+extern "C" int xmc_avgpool_rows(const void* x, int in_dtype, int B, int C, int P, void* out, int out_dtype, void* stream) {
+  XMC_REQUIRE(x && out, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(check_dt(in_dtype) && check_dt(out_dtype), XMC_ERR_UNSUPPORTED, "dtype must be XMC_F32 or XMC_BF16");
+  XMC_REQUIRE(B > 0 && C > 0 && P > 0, XMC_ERR_INVALID_ARG, "bad shape B=%d C=%d P=%d", B, C, P);
+  XMC_REQUIRE(aligned16(x), XMC_ERR_ALIGNMENT, "x must be 16-byte aligned");
+  const long long n = (long long)B * C;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  const float inv = 1.f / (float)P;
+  cudaStream_t st = as_stream(stream);
+  if (in_dtype == XMC_F32) {
+    if (out_dtype == XMC_F32) avgpool_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(x), n, P, inv, static_cast<float*>(out));
+    else avgpool_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(x), n, P, inv, static_cast<__nv_bfloat16*>(out));
+  } else {
+    if (out_dtype == XMC_F32) avgpool_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), n, P, inv, static_cast<float*>(out));
+    else avgpool_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), n, P, inv, static_cast<__nv_bfloat16*>(out));
+  }
+  return cuda_fail(cudaGetLastError(), "avgpool_rows_kernel launch");
+}
+
+extern "C" int xmc_avgpool_rows_backward(const void* dout, int g_dtype, int B, int C, int P, void* dx, int out_dtype, void* stream) {
+  XMC_REQUIRE(dout && dx, XMC_ERR_INVALID_ARG, "null pointer");
+  XMC_REQUIRE(check_dt(g_dtype) && check_dt(out_dtype), XMC_ERR_UNSUPPORTED, "dtype must be XMC_F32 or XMC_BF16");
+  XMC_REQUIRE(B > 0 && C > 0 && P > 0, XMC_ERR_INVALID_ARG, "bad shape B=%d C=%d P=%d", B, C, P);
+  XMC_REQUIRE(aligned16(dx), XMC_ERR_ALIGNMENT, "dx must be 16-byte aligned");
+  const long long n = (long long)B * C;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  const float inv = 1.f / (float)P;
+  cudaStream_t st = as_stream(stream);
+  if (g_dtype == XMC_F32) {
+    if (out_dtype == XMC_F32) avgpool_rows_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(dout), n, P, inv, static_cast<float*>(dx));
+    else avgpool_rows_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(dout), n, P, inv, static_cast<__nv_bfloat16*>(dx));
+  } else {
+    if (out_dtype == XMC_F32) avgpool_rows_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout), n, P, inv, static_cast<float*>(dx));
+    else avgpool_rows_bwd_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout), n, P, inv, static_cast<__nv_bfloat16*>(dx));
+  }
+  return cuda_fail(cudaGetLastError(), "avgpool_rows_bwd_kernel launch");
 }

@@ -677,3 +677,26 @@ class GradNormPenaltyFn(torch.autograd.Function):
         d0, d1 = ctx.ops.gradnorm_penalty_backward(a, b, power, weight, sumsq, go, ctx.needs_input_grad[0],
                                                    ctx.needs_input_grad[1])
         return (d0.view(s0) if d0 is not None else None, d1.view(s1) if d1 is not None else None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# pooled image embedding (df_gan.py:165-166, train_gan.py:271-276)
+# ------------------------------------------------------------------------------------------------
+class PooledFeaturesFn(torch.autograd.Function):
+    """``F.avg_pool2d(x, kernel_size=H).view(B, -1)`` of a ``[B, C, H, W]`` map with H == W == the window, as one kernel
+    (optionally emitting bf16 for the bf16 similarity path)."""
+
+    @staticmethod
+    def forward(ctx, x, out_dtype, ops):
+        B, C = x.shape[:2]
+        xc = x.detach().contiguous().view(B, C, -1)
+        ctx.ops, ctx.shape, ctx.dtype = ops, tuple(x.shape), x.dtype
+        return ops.avgpool_rows(xc, out_dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        P = 1
+        for d in ctx.shape[2:]:
+            P *= d
+        dx = ctx.ops.avgpool_rows_backward(g.detach().contiguous(), P, ctx.dtype)
+        return dx.view(ctx.shape), None, None

@@ -396,6 +396,25 @@ class CudaOps:
                 self.launches += 1 + (1 if need_bias else 0)
         return dfeat, dweight, dbias
 
+    def avgpool_rows(self, x, out_dtype=None):
+        """x [B, C, P] -> [B, C] mean over P (F.avg_pool2d over the whole map + view, df_gan.py:165-166, train_gan.py:271-276)."""
+        _cuda(x)
+        B, C, P = x.shape
+        out = torch.empty(B, C, device=x.device, dtype=out_dtype or x.dtype)
+        with _on(x):
+            self._check(self.L.xmc_avgpool_rows(_p(x), _dt(x), B, C, P, _p(out), _dt(out), _stream()))
+        self.launches += 1
+        return out
+
+    def avgpool_rows_backward(self, dout, P, out_dtype):
+        _cuda(dout)
+        B, C = dout.shape
+        dx = torch.empty(B, C, P, device=dout.device, dtype=out_dtype)
+        with _on(dout):
+            self._check(self.L.xmc_avgpool_rows_backward(_p(dout), _dt(dout), B, C, P, _p(dx), _dt(dx), _stream()))
+        self.launches += 1
+        return dx
+
     def _check_error_word(self, ws, what):
         """XMC_CHECK_ERRORS=1 (tests): synchronise and raise if a bounded mbarrier wait of the tcgen05 kernel
         timed out (word 0 of its workspace).  Off by default: the product path never synchronises."""

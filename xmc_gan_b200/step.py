@@ -113,9 +113,10 @@ def gd_step(netG, netD, optimizerG, optimizerD, imgs, words_embs, sent_embs, mas
         out["gw_loss"] = L.word_loss(fake_regions, words_embs, mask, labels, E.B_GLOBAL, **wkw, **kw)
         errG = errG + S.WORD * out["gw_loss"]
     if E.DISC:                                                                           # :270-279
+        pool = getattr(L, "pooled_features", None) or (lambda x: F.avg_pool2d(x, kernel_size=4).view(B, -1))
         with torch.no_grad():
-            real_pooled = F.avg_pool2d(netD(imgs), kernel_size=4).view(B, -1)
-        fake_pooled = F.avg_pool2d(features, kernel_size=4).view(B, -1)
+            real_pooled = pool(netD(imgs))                                               # :271-273
+        fake_pooled = pool(features)                                                     # :275-276
         out["disc_loss"] = L.img_loss(real_imgs=real_pooled, fake_imgs=fake_pooled, labels=labels, b_global=E.B_GLOBAL, **kw)
         errG = errG + S.DISC * out["disc_loss"]
     netG.zero_grad(); netD.zero_grad()

@@ -132,6 +132,14 @@ def contrastive_losses(imgs=None, txts=None, real_imgs=None, fake_imgs=None, reg
                                   group, _ops or default_ops(), head_w, head_b)
 
 
+def pooled_features(features, *, out_dtype=None, _ops=None):
+    """``F.avg_pool2d(features, kernel_size=H).view(B, -1)`` for a ``[B, C, H, H]`` map — the pooled image embedding that
+    feeds ``sent_loss`` (``xmc_gan/model/df_gan.py:165-166``) and both operands of ``img_loss``
+    (``xmc_gan/train_gan.py:271-276``) — as one kernel; ``out_dtype=torch.bfloat16`` hands the bf16 similarity path its
+    operand without a cast pass."""
+    return _L.PooledFeaturesFn.apply(features, out_dtype, _ops or default_ops())
+
+
 def magp_penalty(grads, *, power=6.0, weight=2.0, _ops=None):
     """Matching-aware gradient penalty reduction, ``xmc_gan/train_gan.py:244-249``.
 
