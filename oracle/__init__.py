@@ -22,9 +22,11 @@ Parity status
   ``word_loss`` (``xmc_gan/train_gan.py:220-222, 267-269``) but only raises
   ``NotImplementedError``; the restatement here follows the XMC-GAN paper's
   word-region formulation and the reference's surrounding conventions (see
-  ``oracle/word_region.py``).
+  ``oracle/word_region.py``).  Stage pins: ``word_region.attend`` (cosines, softmax over the keys, contexts) against the
+  reference's attention block ``xmc_gan/model/concept_gan.py:532-555`` (``tests/golden/ref_attn_*.npz``), the InfoNCE tail
+  against ``sent_loss``.
 """
 from .ref_losses import (  # noqa: F401
     cosine_scores, make_labels, infonce_tail, sent_loss, img_loss, num_pos_of, magp_penalty,
 )
-from .word_region import word_scores, word_loss  # noqa: F401
+from .word_region import attend, word_scores, word_loss  # noqa: F401

@@ -78,3 +78,33 @@ def load_reference_magp():
         exec(code, ns)
         return ns["d_loss"]
     return d_loss
+
+
+ATTENTION_FILE = "/root/reference/xmc_gan/model/concept_gan.py"
+
+
+def load_reference_attention():
+    """The reference's attention block ``CondConceptSampler.get_context_embs`` (``xmc_gan/model/concept_gan.py:532-555``)
+    as a plain callable ``(queries [bs, D, Tq], keys [bs, D, Tk], mask [bs, Tk] bool) -> contexts [bs, Tq, D]``: cosine
+    similarities of queries and keys (``F.normalize`` over the feature axis, ``matmul``), ``-inf`` on masked keys, softmax
+    over the keys, sum of the UNIT keys.  The method's ``FunctionDef`` is lifted out of its class with ``ast`` and run
+    with ``self = None`` (it uses no attribute) — unmodified, nothing copied.  The method averages the contexts over its
+    query axis (``:553``), so it is called with ONE query per batch item and one group (``[bs*Tq, 1, D, 1]`` against
+    ``[bs*Tq, 1, D, Tk]``), which makes that mean the identity.  (The sibling ``OutConceptBlock.get_context_embs``
+    ``:374-394`` has the same body but multiplies ``[bs, p', C] x [bs, p', T]`` without transposing and only runs when
+    the state count equals the feature width.)"""
+    with open(ATTENTION_FILE, "r") as f:
+        tree = ast.parse(f.read(), ATTENTION_FILE)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "CondConceptSampler")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "get_context_embs")
+    ns = {"torch": torch, "nn": torch.nn, "F": F}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), ATTENTION_FILE, "exec"), ns)
+
+    def attention(queries, keys, mask):
+        bs, D, Tq = queries.shape
+        Tk = keys.shape[2]
+        q = queries.transpose(1, 2).reshape(bs * Tq, 1, D, 1)                       # one query per item, one group
+        k = keys.unsqueeze(1).expand(bs, Tq, D, Tk).reshape(bs * Tq, 1, D, Tk).clone()
+        m = mask.unsqueeze(1).expand(bs, Tq, Tk).reshape(bs * Tq, Tk)
+        return ns["get_context_embs"](None, q, k, m).view(bs, Tq, D)
+    return attention

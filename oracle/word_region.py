@@ -4,6 +4,10 @@ TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  **PARITY UNPINNED**: the
 reference only names this loss and raises ``NotImplementedError``
 (``xmc_gan/train_gan.py:220-222, 267-269``); no reference code, test or golden
 vector computes it.  The definition below is this repo's frozen specification.
+Two of its stages ARE checked against reference code: the attention stage (``attend``)
+against ``CondConceptSampler.get_context_embs`` (``xmc_gan/model/concept_gan.py:532-555``) at
+``rho1 = 1`` with unit values, and the InfoNCE tail against ``sent_loss``
+(``xmc_gan/train_gan.py:93-115``); the composition is what stays unpinned.
 It follows
 
 * the XMC-GAN paper's word–region score (attention of each word over the image
@@ -40,6 +44,22 @@ def _unit_last(x: torch.Tensor) -> torch.Tensor:
     return x / x.norm(dim=-1, keepdim=True).clamp_min(_EPS)
 
 
+def attend(en: torch.Tensor, vn: torch.Tensor, vals: torch.Tensor, rho1: float):
+    """The attention stage: unit words ``en [Bc, T, D]`` over unit regions ``vn [Bi, R, D]`` with values ``vals [Bi, R, D]``
+    -> (cosines ``s [Bi, Bc, T, R]``, attention ``a`` = softmax over the regions of ``rho1 * s``, contexts ``[Bi, Bc, T, D]``).
+
+    PINNED for ``rho1 = 1`` with unit values: the reference's own attention block
+    ``CondConceptSampler.get_context_embs`` (``xmc_gan/model/concept_gan.py:532-555``: ``F.normalize`` of queries and keys,
+    ``matmul``, ``-inf`` mask fill, ``Softmax`` over the key axis, ``matmul`` with the unit keys) computes exactly this with
+    queries = the words of one caption and keys = the regions of one image (``tests/golden/ref_attn_*.npz``,
+    ``tests/test_oracle.py::test_attention_stage_matches_reference_*``).  The temperature, the raw-value variant and the
+    composition with the steps around it are this repo's specification."""
+    s = torch.einsum('ctd,ird->ictr', en, vn)                 # cosines
+    a = torch.softmax(rho1 * s, dim=-1)
+    ctx = torch.einsum('ictr,ird->ictd', a, vals)
+    return s, a, ctx
+
+
 def word_scores(regions: torch.Tensor, words: torch.Tensor, mask: torch.Tensor | None,
                 rho1: float = 5.0, rho2: float = 5.0, normalize_values: bool = False,
                 img_block: int = 16) -> torch.Tensor:
@@ -61,9 +81,7 @@ def word_scores(regions: torch.Tensor, words: torch.Tensor, mask: torch.Tensor |
     out = []
     for i0 in range(0, v.shape[0], img_block):
         vb, vnb, valb = v[i0:i0 + img_block], vn[i0:i0 + img_block], vals[i0:i0 + img_block]
-        s = torch.einsum('ctd,ird->ictr', en, vnb)            # cosines
-        a = torch.softmax(rho1 * s, dim=-1)
-        ctx = torch.einsum('ictr,ird->ictd', a, valb)
+        _, _, ctx = attend(en, vnb, valb, rho1)
         rel = (en.unsqueeze(0) * _unit_last(ctx)).sum(-1)     # [i, c, t]
         z = (rho2 * rel).masked_fill(mask.unsqueeze(0), float('-inf'))
         z = torch.where(empty.view(1, -1, 1), torch.zeros_like(z), z)   # keep LSE finite

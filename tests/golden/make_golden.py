@@ -7,6 +7,8 @@ Run in the build container (needs /root/reference):
 * ``ref_*.npz``  — inputs and outputs of the REFERENCE's own functions
   (``xmc_gan/train_gan.py:72-139``, AST-loaded unmodified, CPU fp32 and fp64).
   These pin the oracle restatement and, on the GPU box, the CUDA path.
+* ``ref_attn_*.npz`` — the reference's attention block (``xmc_gan/model/concept_gan.py:532-555``, AST-loaded) on
+  (image, caption) pairs: pins the attention stage of the word–region restatement (``oracle.attend``).
 * ``word_*.npz`` — outputs of this repo's word–region restatement in float64
   (PARITY UNPINNED: the reference has no word loss); they only guard against
   regressions of the oracle itself.
@@ -111,6 +113,30 @@ def magp_case(name, B, shape_img, D, seed, scale):
     print(f"ref_magp_{name}: loss={float(out['loss64']):.12f}")
 
 
+def attn_case(name, Bi, Bc, D, T, R, seed):
+    """The reference's attention block (concept_gan.py:532-555, AST-loaded) on every (image, caption) pair: queries = the
+    caption's words [D, T], keys = the image's regions [D, R], no key masked -> contexts [Bi, Bc, T, D] (sum of unit keys)."""
+    g = torch.Generator().manual_seed(seed)
+    ref = LR.load_reference_attention()
+    words = torch.randn(Bc, D, T, generator=g)
+    regions = torch.randn(Bi, D, R, generator=g) + 0.5 * words[torch.arange(Bi) % Bc][:, :, torch.randint(0, T, (R,), generator=g)]
+    out = {}
+    for dt, tag in ((torch.float32, "32"), (torch.float64, "64")):
+        q = words.to(dt).unsqueeze(0).expand(Bi, Bc, D, T).reshape(Bi * Bc, D, T)
+        k = regions.to(dt).unsqueeze(1).expand(Bi, Bc, D, R).reshape(Bi * Bc, D, R)
+        mask = torch.zeros(Bi * Bc, R, dtype=torch.bool)
+        ctx = ref(q.clone(), k.clone(), mask)                      # [bs, T, D]
+        out["ctx" + tag] = ctx.reshape(Bi, Bc, T, D).numpy()
+    # one masked variant: the last R // 3 keys of every pair masked (the -inf convention)
+    maskk = torch.zeros(Bi * Bc, R, dtype=torch.bool); maskk[:, R - R // 3:] = True
+    q = words.double().unsqueeze(0).expand(Bi, Bc, D, T).reshape(Bi * Bc, D, T)
+    k = regions.double().unsqueeze(1).expand(Bi, Bc, D, R).reshape(Bi * Bc, D, R)
+    out["ctx64_masked"] = ref(q.clone(), k.clone(), maskk).reshape(Bi, Bc, T, D).numpy()
+    np.savez_compressed(os.path.join(HERE, f"ref_attn_{name}.npz"), words=words.numpy(), regions=regions.numpy(),
+                        masked_from=R - R // 3, **out)
+    print(f"ref_attn_{name}: |ctx|={float(np.linalg.norm(out['ctx64'])):.12f}")
+
+
 if __name__ == "__main__":
     assert LR.reference_available(), "needs /root/reference"
     torch.set_num_threads(1)
@@ -122,6 +148,8 @@ if __name__ == "__main__":
     sim_case("img_b40_d512_soft05", "img", 40, 512, True, 0.5, 6, need=(False, True))
     magp_case("b6_3x8x8_d16", 6, (3, 8, 8), 16, 21, 0.08)
     magp_case("b5_3x7x9_d10", 5, (3, 7, 9), 10, 22, 0.11)        # row lengths not multiples of 4
+    attn_case("i3_c4_d64_t6_r20", 3, 4, 64, 6, 20, 31)
+    attn_case("i2_c3_d256_t18_r289", 2, 3, 256, 18, 289, 32)
     word_case("b6_d64_t7_r20", 6, 64, 7, 20, 11)
     word_case("b4_d256_t18_r289", 4, 256, 18, 289, 12, lean=0.15)
     word_case("b6_d128_t12_r64_nv", 6, 128, 12, 64, 13, normalize_values=True)

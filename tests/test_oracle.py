@@ -19,7 +19,7 @@ def _t(x, dtype=None):
 
 
 def _ref_cases(golden_dir):
-    return sorted(p for p in glob.glob(os.path.join(golden_dir, "ref_*.npz")) if "ref_magp_" not in p)
+    return sorted(p for p in glob.glob(os.path.join(golden_dir, "ref_*.npz")) if "ref_magp_" not in p and "ref_attn_" not in p)
 
 
 def test_golden_files_present(golden_dir):
@@ -109,6 +109,45 @@ def test_closed_form_gradient_of_tail():
     nr, nc = n.double().view(-1, 1), n.double().view(1, -1)       # column j divided by n[j] (row count of row j)
     dS = ((pc * L.sum(0, keepdim=True) - L) / nc + (pr * L.sum(1, keepdim=True) - L) / nr) / Bq
     assert torch.allclose(S.grad, dS, atol=1e-14)
+
+
+def _unit(x):
+    return x / x.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+
+
+@pytest.mark.parametrize("dtype,tag,tol", [(torch.float32, "32", 2e-6), (torch.float64, "64", 1e-13)])
+def test_attention_stage_matches_reference_golden(golden_dir, dtype, tag, tol):
+    """oracle.attend (cosines -> softmax over the regions -> contexts) against the reference's own attention block
+    (concept_gan.py:532-555) on every (image, caption) pair: rho1 = 1, unit values."""
+    paths = sorted(glob.glob(os.path.join(golden_dir, "ref_attn_*.npz")))
+    assert len(paths) >= 2
+    for path in paths:
+        g = np.load(path)
+        en = _unit(_t(g["words"], dtype).transpose(1, 2))
+        vn = _unit(_t(g["regions"], dtype).transpose(1, 2))
+        _, a, ctx = oracle.attend(en, vn, vn, 1.0)
+        ref = _t(g["ctx" + tag], dtype)
+        assert float((ctx - ref).abs().max()) <= tol, path
+        assert torch.allclose(a.sum(-1), torch.ones_like(a.sum(-1)), atol=10 * tol)
+        if tag == "64":        # masked keys (the -inf convention) == attending over the unmasked prefix only
+            m = int(g["masked_from"])
+            _, _, ctx_m = oracle.attend(en, vn[:, :m], vn[:, :m], 1.0)
+            assert float((ctx_m - _t(g["ctx64_masked"], dtype)).abs().max()) <= tol, path
+
+
+@pytest.mark.skipif(not LR.reference_available(), reason="needs /root/reference (build container only)")
+def test_attention_stage_matches_reference_live():
+    ref = LR.load_reference_attention()
+    g = torch.Generator().manual_seed(9)
+    Bi, Bc, D, T, R = 2, 3, 32, 5, 17
+    words = torch.randn(Bc, D, T, generator=g, dtype=torch.float64)
+    regions = torch.randn(Bi, D, R, generator=g, dtype=torch.float64)
+    q = words.unsqueeze(0).expand(Bi, Bc, D, T).reshape(Bi * Bc, D, T).clone()
+    k = regions.unsqueeze(1).expand(Bi, Bc, D, R).reshape(Bi * Bc, D, R).clone()
+    want = ref(q, k, torch.zeros(Bi * Bc, R, dtype=torch.bool)).reshape(Bi, Bc, T, D)
+    en, vn = _unit(words.transpose(1, 2)), _unit(regions.transpose(1, 2))
+    _, _, ctx = oracle.attend(en, vn, vn, 1.0)
+    assert float((ctx - want).abs().max()) <= 1e-13
 
 
 def test_word_oracle_regression(golden_dir):

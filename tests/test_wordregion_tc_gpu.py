@@ -299,3 +299,33 @@ def test_word_loss_is_cuda_graph_capturable():
     # fp32 atomics: summation order differs from run to run
     assert float((r.grad.float() - ref_r.float()).norm() / ref_r.float().norm()) < 1e-2
     assert float((w.grad.float() - ref_w.float()).norm() / ref_w.float().norm()) < 1e-2
+
+
+def test_attention_stage_of_the_kernels_against_the_reference_attention_block(ops):
+    """The forward kernels' attention stage — cosines, softmax over the regions, contexts — against the REFERENCE's own
+    attention code (xmc_gan/model/concept_gan.py:532-555, run on every (image, caption) pair by tests/golden/make_golden.py):
+    rho1 = 1, unit values.  The tcgen05 kernel saves C = l * context (bf16) and ||context||; the fp32-tolerance kernel the
+    same as a hi + lo pair.  This pins the CUDA path's attention on reference code, not on this repo's oracle."""
+    import glob
+    import os
+    import numpy as np
+    from xmc_gan_b200 import _lib
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_attn_*.npz"))):
+        g = np.load(path)
+        words, regions = torch.from_numpy(g["words"]), torch.from_numpy(g["regions"])
+        ref = torch.from_numpy(g["ctx64"])                                  # [Bi, Bc, T, D]
+        Bi, Bc, T_, D = ref.shape
+        R = regions.shape[2]
+        Rpad = (R + 15) // 16 * 16
+        for path_id, dt, tol in ((_lib.PATH_BF16_TCGEN05, torch.bfloat16, 1.5e-2), (_lib.PATH_FP32_TCGEN05, torch.float32, 1e-4)):
+            if path_id == _lib.PATH_FP32_TCGEN05 and D != 256:
+                continue
+            qn, _ = ops.normalize_transpose(words.cuda(), T_, dt)
+            kn, _ = ops.normalize_transpose(regions.cuda(), Rpad, dt)
+            lsum, cnorm, rel, chat = ops.wordregion_forward(path_id, qn.view(Bc * T_, D), kn, None, R, 1.0, save_context=True)
+            torch.cuda.synchronize()
+            c = chat.double().sum(0) if chat.dim() == 4 else chat.double()  # hi + lo planes
+            ctx = (c / lsum.double().unsqueeze(-1)).view(Bi, Bc, T_, D).cpu()
+            scale = float(ref.norm(dim=-1).mean())
+            assert float((ctx - ref).norm(dim=-1).max()) <= tol * max(1.0, scale) , (path, path_id, float((ctx - ref).norm(dim=-1).max()))
+            assert float((cnorm.double().view(Bi, Bc, T_).cpu() - ref.norm(dim=-1)).abs().max()) <= tol, (path, path_id)
