@@ -16,9 +16,10 @@
 // All three products have ONE operand form on the tensor cores: C[m, n] = sum_k A[k, m] * B[n, k] with A stored
 // [K rows][M contiguous] (MN-major smem tile) and B stored [N rows][K contiguous] (K-major tile) — feat_b is
 // [Cin][pixels], W is [D][Cin], dy_b is [pixels][D]: every operand is consumed where it lies, no transposes.
-// Staging (fast path: both operands of one dtype, rows 16-byte aligned): eight warps issue 16-byte cp.async copies
-// straight into the 128B-swizzled tiles of a 4-stage ring and hand each stage to the MMA thread through
-// cp.async.mbarrier.arrive — no registers hold data, up to 192 KB per SM is in flight.  bf16 operands run as
+// Staging (fast path: both operands of one dtype, rows 16-byte aligned): one thread issues TMA boxes ([k rows x 128 bytes],
+// 3-D maps built per call) straight into the swizzled tiles of a 4-stage ring, 192 KB per SM in flight.  (Two earlier
+// versions staged through the LSU — conversion in registers: 100 us per launch, bound by one load round trip per group of
+// chunks; 16-byte cp.async: 40-60 us, bound by the ~48 KB of requests an SM keeps outstanding on that path.)  bf16 operands run as
 // kind::f16 MMAs (64 k per stage); fp32 operands stay fp32 in shared memory and run as kind::tf32 MMAs (32 k per
 // stage, 10-bit mantissa: inside the bf16 tolerance), so an fp32 discriminator needs neither a cast pass nor a
 // conversion in registers.  (A first version converted in registers: one load round trip per group of four chunks
@@ -41,9 +42,9 @@ constexpr int kM = 128, kN = 256, kStages = 4;
 constexpr int kABytes = 128 * 128;                 // A tile: 128 m x (64 bf16 | 32 fp32) k = 16 KB
 constexpr int kBBytes = kN * 128;                  // B tile: 256 n rows x 128 bytes of k = 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;     // 48 KB
-constexpr int kEpiWarps = 4, kMmaWarp = 4, kStageWarp0 = 5, kStageWarps = 8;
+constexpr int kEpiWarps = 8, kMmaWarp = 8, kStageWarp0 = 9, kStageWarps = 8;
 constexpr int kStageThreads = kStageWarps * 32;    // 256
-constexpr int kThreads = (kStageWarp0 + kStageWarps) * 32;   // 416
+constexpr int kThreads = (kStageWarp0 + kStageWarps) * 32;   // 544
 constexpr int kAccCols = 256;
 
 enum Mode { kFwd = 0, kDFeat = 1, kDW = 2 };
@@ -62,7 +63,10 @@ struct HeadParams {
   int* err;
 };
 
+constexpr int kStgPitch = 20;    // words per staged row (16 + 4): rows stay 16-byte aligned, the row-per-lane writes are conflict-free
 struct HeadShared {
+  alignas(16) uint32_t stg[kEpiWarps][32 * kStgPitch];    // per epilogue warp: a [32 rows x 16 words] block on its way out
+  float ss_part[2][2][kM];                                // forward: partial sums of squares [accumulator][column half][row]
   uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
   uint32_t tmem_slot;
   int abort_flag;
@@ -71,6 +75,25 @@ struct HeadShared {
 
 // one work item = one accumulator tile: (m0, n0) and the batch items [b0, b1) it sums over
 struct Item { int m0, n0, b0, b1, out_b; };
+
+// Epilogue stores.  A thread owns one row of the accumulator tile (TMEM lane), so storing from registers sends each
+// 16-byte piece of a warp instruction to a different row: 32 half-used sectors (measured: the epilogues took as long
+// as loads + MMAs together).  Instead the warp parks its [32 rows x W words] block in shared memory, one row per lane, and
+// re-reads it as (row, 16-byte chunk): every instruction then covers whole 64- or 128-byte row segments.
+template <typename F>
+__device__ __forceinline__ void warp_rows_out(uint32_t* stg, int lane, const uint32_t* w, F&& emit) {
+  constexpr int W = 16, CH = W / 4, RPI = 32 / CH;           // 16 words = four 16-byte chunks per row; 8 rows per warp instruction
+  __syncwarp();                                              // the previous block has been read
+#pragma unroll
+  for (int q = 0; q < CH; ++q)
+    *reinterpret_cast<uint4*>(stg + lane * kStgPitch + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32 / RPI; ++i) {
+    const int r = i * RPI + lane / CH, ch = lane % CH;
+    emit(r, 4 * ch, *reinterpret_cast<const uint4*>(stg + r * kStgPitch + 4 * ch));
+  }
+}
 
 template <int MODE>
 __device__ __forceinline__ Item decode_item(const HeadParams& p, int item) {
@@ -125,10 +148,10 @@ __device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, uint4 v) {
 
 // FAST: cp.async staging (operands of one dtype, aligned); TF32: fp32 operands as kind::tf32 (FAST only)
 template <int MODE, bool FAST, bool TF32>
-__global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadParams p) {
+__global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const __grid_constant__ CUtensorMap tm_a,
+                                                                  const __grid_constant__ CUtensorMap tm_b, const HeadParams p) {
   constexpr int KB = TF32 ? 32 : 64;                           // k per stage: 128 bytes of K per B row either way
   constexpr int ES = TF32 ? 4 : 2;                             // element size in shared memory
-  constexpr int EPC = 16 / ES;                                 // elements per 16-byte chunk
   constexpr int kABlk = KB * 128;                              // one MN block of the A tile: [KB k rows x 128 bytes of m]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -141,7 +164,8 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadPara
 
   if (tid == 0) {
     sh->abort_flag = 0;
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], kStageThreads); mbar_init(&sh->empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], FAST ? 1 : kStageThreads); mbar_init(&sh->empty[s], 1); }
+    if (FAST) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sh->acc_full[i], 1); mbar_init(&sh->acc_empty[i], kEpiWarps * 32); }
     fence_barrier_init();
   }
@@ -157,40 +181,27 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadPara
     // =============================== staging warps: global -> bf16 -> swizzled smem ===============================
     const int t = tid - kStageWarp0 * 32;                      // 0..255
     if (FAST) {
-      constexpr int CPR = 128 / EPC;                           // A chunks per k row (128 m)
-      const uint8_t* ga = static_cast<const uint8_t*>(p.a);
-      const uint8_t* gb = static_cast<const uint8_t*>(p.b);
-      uint32_t stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const Item it = decode_item<MODE>(p, item);
-        const int steps = (it.b1 - it.b0) * kbpb;
-        for (int step = 0; step < steps; ++step) {
-          const int b = it.b0 + step / kbpb, k0 = (step % kbpb) * KB;
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes), sb = sa + kABytes;
-          mbar_wait(&sh->empty[stage], phase ^ 1, wc, 11);      // the MMAs that read this stage are done
-          const long long abase = (long long)b * p.a_batch, bbase = (long long)b * p.b_batch;
+      // ---- TMA producer: one thread; boxes of [KB k rows x 128 bytes] land in the swizzled layouts the MMAs read ----
+      if (warp == kStageWarp0 && elect_one()) {
+        constexpr int kBoxes = kABytes / kABlk;                  // A: 128 m in boxes of 128 bytes of m (2 bf16 / 4 fp32)
+        uint32_t stage = 0, phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+          const Item it = decode_item<MODE>(p, item);
+          const int steps = (it.b1 - it.b0) * kbpb;
+          for (int step = 0; step < steps; ++step) {
+            const int b = it.b0 + step / kbpb, k0 = (step % kbpb) * KB;
+            uint8_t* sa = smem + stage * kStageBytes;
+            mbar_wait(&sh->empty[stage], phase ^ 1, wc, 11);    // the MMAs that read this stage are done
+            mbar_expect_tx(&sh->full[stage], kStageBytes);       // out-of-range rows / columns arrive as zeros and count
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {                         // A: [KB k rows][128 m], 16-byte chunks along m
-            const int q = t + kStageThreads * c, row = q / CPR, o = q % CPR;
-            const int k = k0 + row, m = it.m0 + o * EPC;
-            const int valid = k < p.K ? max(0, min(EPC, p.M - m)) : 0;
-            const uint8_t* src = valid ? ga + (abase + (long long)k * p.lda + m) * ES : ga;
-            // bf16: 16-byte chunk ^ (row mod 8) (SWIZZLE_128B); fp32: 32-byte chunk ^ (row mod 4) (SWIZZLE_128B_BASE32B)
-            const int j = o & 7, js = TF32 ? ((((j >> 1) ^ (row & 3)) << 1) | (j & 1)) : (j ^ (row & 7));
-            cp_async16(sa + (o >> 3) * kABlk + row * 128 + (js << 4), src, valid * ES);
+            for (int bx = 0; bx < kBoxes; ++bx)
+              tma_load_3d(sa + bx * kABlk, &tm_a, it.m0 + bx * (128 / ES), k0, p.a_batch ? b : 0, &sh->full[stage]);
+            tma_load_3d(sa + kABytes, &tm_b, k0, it.n0, p.b_batch ? b : 0, &sh->full[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {                         // B: [256 n rows][KB k], 16-byte chunks along k
-            const int q = t + kStageThreads * c, n = q >> 3, j = q & 7;
-            const int k = k0 + j * EPC;
-            const int valid = (it.n0 + n) < p.N ? max(0, min(EPC, p.K - k)) : 0;
-            const uint8_t* src = valid ? gb + (bbase + (long long)(it.n0 + n) * p.ldb + k) * ES : gb;
-            cp_async16(sb + n * 128 + ((j ^ (n & 7)) << 4), src, valid * ES);
-          }
-          cp_async_arrive_noinc(&sh->full[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      __syncwarp();
     } else {
       const bool a_bf16 = p.a_bf16 != 0, b_bf16 = p.b_bf16 != 0;
       const bool a_vec = (p.lda % (a_bf16 ? 8 : 4) == 0) && (p.a_batch % (a_bf16 ? 8 : 4) == 0);
@@ -290,7 +301,6 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadPara
         const uint32_t acc = tmem + buf * kAccCols;
         for (int step = 0; step < steps; ++step) {
           mbar_wait(&sh->full[stage], phase, wc, 13);
-          if (FAST) fence_proxy_async_smem();                                // cp.async wrote through the generic proxy
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes), sb = sa + kABytes;
 #pragma unroll
@@ -309,81 +319,86 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadPara
     }
     __syncwarp();
   } else {
-    // =============================== epilogue warps 0..3: TMEM lane = tile row ===============================
+    // ======= epilogue warps 0..7: TMEM lane quadrant = warp & 3 (32 tile rows), column half = warp >> 2 (128 columns) =======
     uint32_t n_acc = 0;
-    const int rl = warp * 32 + lane;
+    const int quad = warp & 3, half = warp >> 2;
+    const int rl = quad * 32 + lane;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_acc) {
       const Item it = decode_item<MODE>(p, item);
       const uint32_t buf = n_acc & 1;
       mbar_wait(&sh->acc_full[buf], (n_acc >> 1) & 1, wc, 14);
       tc_fence_after();
-      const uint32_t acc = tmem + buf * kAccCols + (static_cast<uint32_t>(warp * 32) << 16);
+      const uint32_t acc = tmem + buf * kAccCols + (static_cast<uint32_t>(quad * 32) << 16);
       const int m = it.m0 + rl;
+      uint32_t* stg = sh->stg[warp];
       if (MODE == kFwd) {
         // row = pixel m of image out_b: y = acc + bias, ||y||, unit row (bf16) + norm; pad rows [R, Rpad) are zeros
         float ss = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < kN / 32; ++c) {
+        for (int c = half * 4; c < half * 4 + 4; ++c) {
           uint32_t v[32];
           tmem_ld32(acc + c * 32, v);
           tmem_wait_ld();
 #pragma unroll
           for (int e = 0; e < 32; ++e) { const float y = __uint_as_float(v[e]) + sh->bias[c * 32 + e]; ss = fmaf(y, y, ss); }
         }
+        sh->ss_part[buf][half][rl] = ss;                       // the other column half of this row lives in warp (warp ^ 4)
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        ss += sh->ss_part[buf][half ^ 1][rl];
         // a timed-out pipeline wait (abort flag) must not pass for a result: NaN norms poison the loss downstream
         const float nrm = *wc.abort_flag ? __int_as_float(0x7fc00000) : fmaxf(sqrtf(ss), kEps), inv = (m < p.R) ? 1.f / nrm : 0.f;
         const bool wr = m < p.Rpad;
-        __nv_bfloat16* dst = p.kn + ((size_t)it.out_b * p.Rpad + m) * kN;
+        const int mw = it.m0 + quad * 32;                      // first row of this warp's block
+        __nv_bfloat16* dstw = p.kn + ((size_t)it.out_b * p.Rpad + mw) * kN;
 #pragma unroll 1
-        for (int c = 0; c < kN / 32; ++c) {
+        for (int c = half * 4; c < half * 4 + 4; ++c) {
           uint32_t v[32];
           tmem_ld32(acc + c * 32, v);
           tmem_wait_ld();
-          if (wr) {
+          uint32_t w[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int col = q * 8 + e * 2;
-                w[e] = pack_bf16((__uint_as_float(v[col]) + sh->bias[c * 32 + col]) * inv,
-                                 (__uint_as_float(v[col + 1]) + sh->bias[c * 32 + col + 1]) * inv);
-              }
-              *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
+          for (int e = 0; e < 16; ++e)
+            w[e] = pack_bf16((__uint_as_float(v[2 * e]) + sh->bias[c * 32 + 2 * e]) * inv,
+                             (__uint_as_float(v[2 * e + 1]) + sh->bias[c * 32 + 2 * e + 1]) * inv);
+          warp_rows_out(stg, lane, w, [&](int r, int wo, uint4 val) {
+            if (mw + r < p.Rpad) *reinterpret_cast<uint4*>(dstw + (size_t)r * kN + c * 32 + 2 * wo) = val;
+          });
         }
-        if (wr) p.rnorm[(size_t)it.out_b * p.Rpad + m] = (m < p.R) ? nrm : 0.f;
+        if (wr && half == 0) p.rnorm[(size_t)it.out_b * p.Rpad + m] = (m < p.R) ? nrm : 0.f;
       } else if (MODE == kDFeat) {
         // row = input channel m, columns = pixels n0 + c: dfeat[b][m][n]
         const bool row_ok = m < p.M;
         const size_t row_off = ((size_t)it.out_b * p.M + m) * p.N;
         const bool vec = (p.N % 8 == 0);
 #pragma unroll 1
-        for (int c = 0; c < kN / 32; ++c) {
+        for (int c = half * 4; c < half * 4 + 4; ++c) {
           const int n = it.n0 + c * 32;
           if (n >= p.N) break;                                   // uniform over the warp
           uint32_t v[32];
           tmem_ld32(acc + c * 32, v);
           tmem_wait_ld();
-          if (!row_ok) continue;
           if (*wc.abort_flag) v[0] = 0x7fc00000u;                // timed-out wait: never a plausible gradient
-          if (vec && n + 32 <= p.N) {
+          if (vec && n + 32 <= p.N) {                            // warp-uniform: whole row segments through the staging block
+            const int mw = it.m0 + quad * 32;
+            const size_t roww = ((size_t)it.out_b * p.M + mw) * p.N + n;
             if (p.out_bf16) {
-              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.dfeat) + row_off + n;
+              uint32_t w[16];
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(dst + q * 8) =
-                    make_uint4(pack_bf16(__uint_as_float(v[q * 8]), __uint_as_float(v[q * 8 + 1])),
-                               pack_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])),
-                               pack_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])),
-                               pack_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])));
+              for (int e = 0; e < 16; ++e) w[e] = pack_bf16(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+              __nv_bfloat16* dstw = static_cast<__nv_bfloat16*>(p.dfeat) + roww;
+              warp_rows_out(stg, lane, w, [&](int r, int wo, uint4 val) {
+                if (mw + r < p.M) *reinterpret_cast<uint4*>(dstw + (size_t)r * p.N + 2 * wo) = val;
+              });
             } else {
-              float* dst = static_cast<float*>(p.dfeat) + row_off + n;
+              float* dstw = static_cast<float*>(p.dfeat) + roww;
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<uint4*>(dst + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+              for (int hf = 0; hf < 2; ++hf)                     // 32 fp32 columns = two blocks of 16 words
+                warp_rows_out(stg, lane, v + 16 * hf, [&](int r, int wo, uint4 val) {
+                  if (mw + r < p.M) *reinterpret_cast<uint4*>(dstw + (size_t)r * p.N + 16 * hf + wo) = val;
+                });
             }
+          } else if (!row_ok) {
+            continue;
           } else {
 #pragma unroll
             for (int e = 0; e < 32; ++e)
@@ -397,21 +412,27 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const HeadPara
         // row = output feature m (d), columns = input channels n0 + c: partial dW over this CTA's batch items
         const bool row_ok = m < p.M;
 #pragma unroll 1
-        for (int c = 0; c < kN / 32; ++c) {
+        for (int c = half * 4; c < half * 4 + 4; ++c) {
           const int n = it.n0 + c * 32;
           if (n >= p.N) break;
           uint32_t v[32];
           tmem_ld32(acc + c * 32, v);
           tmem_wait_ld();
-          if (!row_ok) continue;
           if (*wc.abort_flag) v[0] = 0x7fc00000u;
           float* dst = p.dw + (size_t)m * p.N + n;
-          if (n + 32 <= p.N && p.N % 4 == 0) {
+          if (n + 32 <= p.N && p.N % 4 == 0) {                   // warp-uniform: 128-byte row segments per reduction group
+            const int mw = it.m0 + quad * 32;
+            float* dstw = p.dw + (size_t)mw * p.N + n;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(v[4 * q])),
-                           "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])), "f"(__uint_as_float(v[4 * q + 3]))
-                           : "memory");
+            for (int hf = 0; hf < 2; ++hf)
+              warp_rows_out(stg, lane, v + 16 * hf, [&](int r, int wo, uint4 val) {
+                if (mw + r < p.M)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dstw + (size_t)r * p.N + 16 * hf + wo),
+                               "f"(__uint_as_float(val.x)), "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w))
+                               : "memory");
+              });
+          } else if (!row_ok) {
+            continue;
           } else {
 #pragma unroll
             for (int e = 0; e < 32; ++e)
@@ -492,10 +513,50 @@ bool fast_ok(const HeadParams& p) {
   return p.lda % epc == 0 && p.ldb % epc == 0 && p.a_batch % epc == 0 && p.b_batch % epc == 0;
 }
 
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled head_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// 3-D map over an operand stored [batch][rows][inner contiguous]: box = 128 bytes of the inner axis x box_rows x 1.
+// mn_major_f32: the MN-major fp32 operand of kind::tf32 needs the 32-byte-atom flavour of the 128-byte swizzle.
+int head_map(CUtensorMap* m, const void* base, bool bf16, int inner, int rows, int batches, long long row_stride,
+             long long batch_stride, int box_rows, bool mn_major_f32) {
+  PFN_encodeTiled enc = head_encode();
+  XMC_REQUIRE(enc != nullptr, XMC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int es = bf16 ? 2 : 4;
+  if (batch_stride == 0) { batches = 1; batch_stride = (long long)rows * row_stride; }
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * es, (cuuint64_t)batch_stride * es};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major_f32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XMC_REQUIRE(r == CUDA_SUCCESS, XMC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return XMC_OK;
+}
+
 template <int MODE, bool FAST, bool TF32>
 int launch_head_as(const HeadParams& p, int grid, cudaStream_t st) {
+  CUtensorMap ta{}, tb{};
+  if (FAST) {
+    // A_b[k][m]: inner = m (extent M), rows = K;  B_b[n][k]: inner = k (extent K), rows = N
+    if (int rc = head_map(&ta, p.a, !TF32, p.M, p.K, p.batches, p.lda, p.a_batch, TF32 ? 32 : 64, TF32)) return rc;
+    if (int rc = head_map(&tb, p.b, !TF32, p.K, p.N, p.batches, p.ldb, p.b_batch, kN, false)) return rc;
+  }
   XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(region_head_kernel<MODE, FAST, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
-  region_head_kernel<MODE, FAST, TF32><<<grid, kThreads, kHeadSmem, st>>>(p);
+  region_head_kernel<MODE, FAST, TF32><<<grid, kThreads, kHeadSmem, st>>>(ta, tb, p);
   return cuda_fail(cudaGetLastError(), "region_head_kernel launch");
 }
 
