@@ -6,7 +6,9 @@ import torch.nn.functional as F
 sys.path.insert(0, '.')
 from xmc_gan_b200.ops import default_ops
 ops = default_ops()
-flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+# L2 is flushed by READING a 512 MB buffer: a zero-fill leaves ~126 MB of dirty lines whose write-back is then charged to
+# the timed kernel (measured: +15-20 us on these HBM-bound kernels, enough to hide every difference between variants)
+flush = torch.zeros(512 << 18, dtype=torch.float32, device="cuda")
 PEAK = 6537.6   # GB/s, MEASURED_PEAKS.json
 
 
@@ -15,7 +17,7 @@ def timed(fn, n=20):
         fn()
     ms = []
     for _ in range(n):
-        flush.zero_()
+        flush.sum()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record()
         torch.cuda.synchronize()

@@ -194,3 +194,25 @@ def test_pooled_features_match_avg_pool2d(B, C, H, dt):
     assert float((x.grad.float() - xr.grad.float()).abs().max()) <= tol * max(1.0, float(xr.grad.float().abs().max()))
     yb = T.pooled_features(x.detach(), out_dtype=torch.bfloat16)
     assert yb.dtype == torch.bfloat16 and float((yb.float() - yr.float()).abs().max()) <= 8e-3 * max(1.0, float(yr.float().abs().max()))
+
+
+def test_cta_pair_variant_matches(monkeypatch):
+    """XMC_HEAD_PAIR=1: the 2-SM form of the kernel (thread-block clusters of two, one tcgen05.mma.cta_group::2 per 256-row
+    tile, each CTA staging its own A rows and half of the B rows) gives the same forward and dfeat as single CTAs."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, Cin, R, D = 6, 512, 256, 256
+    for dt in (torch.bfloat16, torch.float32):
+        feat = torch.randn(B, Cin, R, generator=g, device="cuda").to(dt)
+        w = (torch.randn(D, Cin, generator=g, device="cuda") / Cin ** 0.5).to(dt)
+        bias = torch.randn(D, generator=g, device="cuda") * 0.1
+        dy = (torch.randn(B, R, D, generator=g, device="cuda") * 0.01).to(dt)
+        monkeypatch.delenv("XMC_HEAD_PAIR", raising=False)
+        kn0, rn0 = ops.region_head_forward(feat, w, bias, R)
+        df0, _, _ = ops.region_head_backward(feat, w, dy, True, False, False)
+        monkeypatch.setenv("XMC_HEAD_PAIR", "1")
+        kn1, rn1 = ops.region_head_forward(feat, w, bias, R)
+        df1, _, _ = ops.region_head_backward(feat, w, dy, True, False, False)
+        torch.cuda.synchronize()
+        assert torch.equal(kn0, kn1) and torch.equal(rn0, rn1)          # same products in the same order
+        assert torch.equal(df0, df1)

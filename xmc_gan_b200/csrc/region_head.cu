@@ -29,6 +29,8 @@
 //
 // Roofline: HBM.  Forward at B = 256, 16 x 16, Cin = 512, D = 256: 134 MB (fp32 map) or 67 MB (bf16) in + 33.6 MB
 // out against 17.2 GFLOP (12 us of tensor time); the staging path is sized for bytes in flight, not for the MMAs.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -147,7 +149,14 @@ __device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, uint4 v) {
 }
 
 // FAST: cp.async staging (operands of one dtype, aligned); TF32: fp32 operands as kind::tf32 (FAST only)
-template <int MODE, bool FAST, bool TF32>
+// CL = 2 (FAST only, opt-in): CTA pairs (thread-block clusters of two, cta_group::2) on two items that share their B operand
+// (the weights in the forward, the image's dy tile in dfeat).  One tcgen05.mma of the pair's leader multiplies a 256-row
+// tile over both SMs: each CTA stages its own 128 A rows and HALF of the B rows, so a k-block brings 32 KB into an SM
+// instead of 48 KB.  The leader's full barrier collects the bytes of both CTAs, its commits release the stage / publish the
+// accumulator in both, and both epilogues arrive on the leader's accumulator-empty barrier.  (An earlier pair variant
+// multicast the B stage instead — half the L2 reads, the same bytes into each SM; neither variant is faster than single
+// CTAs: see launch_head.)
+template <int MODE, bool FAST, bool TF32, int CL>
 __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                   const __grid_constant__ CUtensorMap tm_b, const HeadParams p) {
   constexpr int KB = TF32 ? 32 : 64;                           // k per stage: 128 bytes of K per B row either way
@@ -160,20 +169,30 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const __grid_c
 
   const int tid = threadIdx.x, warp = warp_index(), lane = tid & 31;
   const int n_items = (MODE == kDW ? p.m_tiles * p.n_tiles * p.splits : p.batches * p.m_tiles * p.n_tiles);
+  // item walk: cluster c of the grid takes item pairs c, c + #clusters, ...; its CTA of rank r the r-th item of the pair
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int item0 = ((int)blockIdx.x / CL) * CL + crank, item_step = (int)gridDim.x;
   const int kbpb = (p.K + KB - 1) / KB;                       // k-blocks per batch item
 
   if (tid == 0) {
     sh->abort_flag = 0;
     for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], FAST ? 1 : kStageThreads); mbar_init(&sh->empty[s], 1); }
     if (FAST) { tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh->acc_full[i], 1); mbar_init(&sh->acc_empty[i], kEpiWarps * 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->acc_full[i], 1); mbar_init(&sh->acc_empty[i], CL * kEpiWarps * 32); }
     fence_barrier_init();
   }
   if (MODE == kFwd)
     for (int i = tid; i < kN; i += kThreads) sh->bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
-  if (warp == kMmaWarp) tmem_alloc(&sh->tmem_slot, 2 * kAccCols);
+  if (CL > 1) {
+    __syncthreads();
+    cluster_sync_all();                                       // both CTAs' barriers exist before the pair-wide allocation / any signal
+    if (warp == kMmaWarp) tmem_alloc_pair(&sh->tmem_slot, 2 * kAccCols);
+  } else if (warp == kMmaWarp) {
+    tmem_alloc(&sh->tmem_slot, 2 * kAccCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_slot;
 
@@ -185,18 +204,27 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const __grid_c
       if (warp == kStageWarp0 && elect_one()) {
         constexpr int kBoxes = kABytes / kABlk;                  // A: 128 m in boxes of 128 bytes of m (2 bf16 / 4 fp32)
         uint32_t stage = 0, phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int item = item0; item < n_items; item += item_step) {
           const Item it = decode_item<MODE>(p, item);
           const int steps = (it.b1 - it.b0) * kbpb;
           for (int step = 0; step < steps; ++step) {
             const int b = it.b0 + step / kbpb, k0 = (step % kbpb) * KB;
             uint8_t* sa = smem + stage * kStageBytes;
             mbar_wait(&sh->empty[stage], phase ^ 1, wc, 11);    // the MMAs that read this stage are done
-            mbar_expect_tx(&sh->full[stage], kStageBytes);       // out-of-range rows / columns arrive as zeros and count
+            if (CL > 1) {
+              // pair: own A rows + own half of the B rows into OWN shared memory; all bytes complete on the leader's barrier
+              if (crank == 0) mbar_expect_tx(&sh->full[stage], CL * (kABytes + kBBytes / CL));
 #pragma unroll
-            for (int bx = 0; bx < kBoxes; ++bx)
-              tma_load_3d(sa + bx * kABlk, &tm_a, it.m0 + bx * (128 / ES), k0, p.a_batch ? b : 0, &sh->full[stage]);
-            tma_load_3d(sa + kABytes, &tm_b, k0, it.n0, p.b_batch ? b : 0, &sh->full[stage]);
+              for (int bx = 0; bx < kBoxes; ++bx)
+                tma_load_3d_pair(sa + bx * kABlk, &tm_a, it.m0 + bx * (128 / ES), k0, p.a_batch ? b : 0, &sh->full[stage]);
+              tma_load_3d_pair(sa + kABytes, &tm_b, k0, it.n0 + crank * (kN / CL), p.b_batch ? b : 0, &sh->full[stage]);
+            } else {
+              mbar_expect_tx(&sh->full[stage], kStageBytes);     // out-of-range rows / columns arrive as zeros and count
+#pragma unroll
+              for (int bx = 0; bx < kBoxes; ++bx)
+                tma_load_3d(sa + bx * kABlk, &tm_a, it.m0 + bx * (128 / ES), k0, p.a_batch ? b : 0, &sh->full[stage]);
+              tma_load_3d(sa + kABytes, &tm_b, k0, it.n0, p.b_batch ? b : 0, &sh->full[stage]);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -289,10 +317,10 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const __grid_c
     }
   } else if (warp == kMmaWarp) {
     // =============================== MMA issue: one elected thread ===============================
-    if (elect_one()) {
-      constexpr uint32_t idesc = TF32 ? idesc_tf32(kM, kN, true, false) : idesc_bf16(kM, kN, true, false);
+    if ((CL == 1 || crank == 0) && elect_one()) {               // a pair's MMAs are issued by its leader alone
+      constexpr uint32_t idesc = TF32 ? idesc_tf32(kM * CL, kN, true, false) : idesc_bf16(kM * CL, kN, true, false);
       uint32_t stage = 0, phase = 0, n_acc = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_acc) {
+      for (int item = item0; item < n_items; item += item_step, ++n_acc) {
         const Item it = decode_item<MODE>(p, item);
         const int steps = (it.b1 - it.b0) * kbpb;
         const uint32_t buf = n_acc & 1;
@@ -308,13 +336,20 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const __grid_c
             // MN-major: a quarter of the k rows per step; tf32: 4-row swizzle groups (512 bytes), bf16: 8-row groups
             const Desc da = TF32 ? smem_desc_base32b(sa + ks * (kABlk / 4), kABlk, 512) : make_desc(sa + ks * (kABlk / 4), kABlk, 1024);
             const Desc db = make_desc(sb + ks * 32, 16, 1024);              // K-major: 32 bytes inside the row per step
-            if (TF32) mma_ss_tf32(acc, da, db, idesc, step > 0 || ks > 0);
-            else mma_ss(acc, da, db, idesc, step > 0 || ks > 0);
+            if (CL > 1) {
+              if (TF32) mma_ss_tf32_pair(acc, da, db, idesc, step > 0 || ks > 0);
+              else mma_ss_pair(acc, da, db, idesc, step > 0 || ks > 0);
+            } else {
+              if (TF32) mma_ss_tf32(acc, da, db, idesc, step > 0 || ks > 0);
+              else mma_ss(acc, da, db, idesc, step > 0 || ks > 0);
+            }
           }
-          mma_commit(&sh->empty[stage]);
+          if (CL > 1) mma_commit_pair(&sh->empty[stage]);                    // releases the stage in both CTAs
+          else mma_commit(&sh->empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        mma_commit(&sh->acc_full[buf]);
+        if (CL > 1) mma_commit_pair(&sh->acc_full[buf]);                     // both epilogues
+        else mma_commit(&sh->acc_full[buf]);
       }
     }
     __syncwarp();
@@ -323,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const __grid_c
     uint32_t n_acc = 0;
     const int quad = warp & 3, half = warp >> 2;
     const int rl = quad * 32 + lane;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_acc) {
+    for (int item = item0; item < n_items; item += item_step, ++n_acc) {
       const Item it = decode_item<MODE>(p, item);
       const uint32_t buf = n_acc & 1;
       mbar_wait(&sh->acc_full[buf], (n_acc >> 1) & 1, wc, 14);
@@ -441,12 +476,18 @@ __global__ void __launch_bounds__(kThreads, 1) region_head_kernel(const __grid_c
         }
       }
       tc_fence_before();
-      mbar_arrive(&sh->acc_empty[buf]);
+      if (CL > 1 && crank != 0) mbar_arrive_remote(&sh->acc_empty[buf], 0);   // the leader's MMA thread waits for both epilogues
+      else mbar_arrive(&sh->acc_empty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem, 2 * kAccCols);
+  if (CL > 1) {
+    cluster_sync_all();                                       // no CTA leaves while its peer may still signal into it
+    if (warp == kMmaWarp) tmem_dealloc_pair(tmem, 2 * kAccCols);
+  } else if (warp == kMmaWarp) {
+    tmem_dealloc(tmem, 2 * kAccCols);
+  }
 }
 
 constexpr int kHeadSmem = kStages * kStageBytes + (int)sizeof(HeadShared) + 1024;
@@ -547,16 +588,23 @@ int head_map(CUtensorMap* m, const void* base, bool bf16, int inner, int rows, i
   return XMC_OK;
 }
 
-template <int MODE, bool FAST, bool TF32>
+template <int MODE, bool FAST, bool TF32, int CL>
 int launch_head_as(const HeadParams& p, int grid, cudaStream_t st) {
   CUtensorMap ta{}, tb{};
   if (FAST) {
-    // A_b[k][m]: inner = m (extent M), rows = K;  B_b[n][k]: inner = k (extent K), rows = N
+    // A_b[k][m]: inner = m (extent M), rows = K;  B_b[n][k]: inner = k (extent K), rows = N (a pair loads half the rows each)
     if (int rc = head_map(&ta, p.a, !TF32, p.M, p.K, p.batches, p.lda, p.a_batch, TF32 ? 32 : 64, TF32)) return rc;
-    if (int rc = head_map(&tb, p.b, !TF32, p.K, p.N, p.batches, p.ldb, p.b_batch, kN, false)) return rc;
+    if (int rc = head_map(&tb, p.b, !TF32, p.K, p.N, p.batches, p.ldb, p.b_batch, kN / CL, false)) return rc;
   }
-  XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(region_head_kernel<MODE, FAST, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
-  region_head_kernel<MODE, FAST, TF32><<<grid, kThreads, kHeadSmem, st>>>(ta, tb, p);
+  auto kern = region_head_kernel<MODE, FAST, TF32, CL>;
+  XMC_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kHeadSmem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
+  XMC_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return cuda_fail(cudaGetLastError(), "region_head_kernel launch");
 }
 
@@ -565,9 +613,20 @@ int launch_head(const HeadParams& p, int n_items, cudaStream_t st) {
   int dev = 0, sms = 148;
   XMC_RETURN_IF_CUDA(cudaGetDevice(&dev));
   XMC_RETURN_IF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = n_items < sms ? n_items : sms;
-  if (!fast_ok(p)) return launch_head_as<MODE, false, false>(p, grid, st);
-  return p.a_bf16 ? launch_head_as<MODE, true, false>(p, grid, st) : launch_head_as<MODE, true, true>(p, grid, st);
+  int grid = n_items < sms ? n_items : sms;
+  if (!fast_ok(p)) return launch_head_as<MODE, false, false, 1>(p, grid, st);
+  // pairs: consecutive items must share their B operand and there must be an even number of them
+  //   forward: B = the weights, shared by every item;  dfeat: B = dy_b, shared by the channel tiles of one image
+  // Opt-in (XMC_HEAD_PAIR=1): measured no faster than one CTA per tile (forward 43.2 / 32.8 us against 42.0 / 31.7 us) — per
+  // staged byte the kernel writes shared memory once (TMA) and reads it once (MMA operands), 192 B/clk against the SM's
+  // 128 B/clk while the MMAs run, and pairing halves only the B part of it.  Kept as the tested 2-SM form of the kernel.
+  const bool pairs = MODE != kDW && n_items % 2 == 0 && n_items >= 2 && (MODE == kFwd || (p.n_tiles == 1 && p.m_tiles % 2 == 0)) &&
+                     getenv("XMC_HEAD_PAIR") != nullptr;
+  if (pairs) {
+    grid &= ~1;
+    return p.a_bf16 ? launch_head_as<MODE, true, false, 2>(p, grid, st) : launch_head_as<MODE, true, true, 2>(p, grid, st);
+  }
+  return p.a_bf16 ? launch_head_as<MODE, true, false, 1>(p, grid, st) : launch_head_as<MODE, true, true, 1>(p, grid, st);
 }
 
 int check_dt(int dt) { return dt == XMC_F32 || dt == XMC_BF16; }
