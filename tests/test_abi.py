@@ -48,6 +48,17 @@ def test_argument_validation_without_gpu(built):
     assert L.xmc_gradnorm_penalty_forward(16, 8, None, 0, 4, 0, 1.0, 2.0, 1, 16, 16, 16, None) == 1
     assert b"power" in L.xmc_last_error()
     assert L.xmc_gradnorm_penalty_backward(16, 8, 16, 8, 4, 0, 6.0, 2.0, 1, None, 16, 16, 16, None) == 1
+    # region head / pooled embedding: null pointers, widths other than 256, Rpad not a multiple of 16
+    assert L.xmc_region_head_forward(None, 0, 16, 0, None, 2, 64, 16, 16, 256, 16, 16, None) == 1
+    assert L.xmc_region_head_forward(16, 0, 16, 0, None, 2, 64, 16, 16, 128, 16, 16, None) == 2 and b"D=128" in L.xmc_last_error()
+    assert L.xmc_region_head_forward(16, 0, 16, 0, None, 2, 64, 16, 20, 256, 16, 16, None) == 1
+    assert L.xmc_region_head_forward(16, 7, 16, 0, None, 2, 64, 16, 16, 256, 16, 16, None) == 2
+    assert L.xmc_region_head_backward_input(16, 0, None, 0, 2, 64, 16, 256, 16, 0, None) == 1
+    assert L.xmc_region_head_backward_weight(16, 0, 16, 0, 0, 64, 16, 256, 16, None, None) == 1
+    assert L.xmc_region_head_backward_weight(8, 0, 16, 0, 2, 64, 16, 256, 16, None, None) == 3
+    assert L.xmc_avgpool_rows(None, 0, 2, 8, 16, 16, 0, None) == 1
+    assert L.xmc_avgpool_rows(16, 0, 2, 8, 0, 16, 0, None) == 1
+    assert L.xmc_avgpool_rows_backward(16, 5, 2, 8, 16, 16, 0, None) == 2
     # merge of per-rank column statistics
     assert L.xmc_infonce_combine_stats(None, 2, 8, 16, None) == 1
     assert L.xmc_infonce_combine_stats(16, 0, 8, 16, None) == 1
