@@ -1,0 +1,85 @@
+// Microbenchmark: issue rate of back-to-back tcgen05.mma (kind::f16, bf16 -> fp32, M = 128, K = 16) on one CTA per SM, as a
+// function of N, of the operand sources (A from shared or tensor memory) and of the shared-memory layouts (K-major / MN-major).
+// The question it answers: when is an MMA bound by its shared-memory operand reads instead of the tensor pipe (M*N/256 clk)?
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I ../../xmc_gan_b200/csrc -o mma_bench mma_bench.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include "tc_common.cuh"
+using namespace xmc::tc;
+
+template <int N, int A_TMEM, int A_MN, int B_MN, int CHAINS>
+__global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ int abort_flag;
+  // operands: A [128 x 64] bf16 (16 KB, 4 k-steps), B [256 x 64] bf16 (32 KB); contents are zeros (timing only)
+  for (int i = threadIdx.x; i < 49152 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  if (threadIdx.x == 0) { abort_flag = 0; mbar_init(&bar, 1); fence_barrier_init(); }
+  const int warp = warp_index();
+  if (warp == 0) tmem_alloc(&slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const WaitCtx wc{&abort_flag, nullptr};
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t sa = smem_u32(smem), sb = sa + 16384;
+      constexpr uint32_t idesc = idesc_bf16(128, N, A_MN != 0, B_MN != 0);
+      const Desc da0 = A_MN ? make_desc(sa, 8192, 1024) : make_desc(sa, 16, 1024);
+      const Desc db0 = B_MN ? make_desc(sb, 8192, 1024) : make_desc(sb, 16, 1024);
+      constexpr uint32_t astep = (A_MN ? 2048 : 32) >> 4, bstep = (B_MN ? 2048 : 32) >> 4;
+      // accumulators: chain j at columns j * N (CHAINS * N <= 256); A in tensor memory at column 256 (8 columns per k-step)
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+          for (int j = 0; j < CHAINS; ++j) {
+            if (A_TMEM) mma_ts(tmem + j * N, tmem + 256 + ks * 8, db0 + ks * bstep, idesc, true);
+            else mma_ss(tmem + j * N, da0 + ks * astep, db0 + ks * bstep, idesc, true);
+          }
+        }
+      }
+      mma_commit(&bar);
+      mbar_wait(&bar, 0, wc, 1);
+      out[blockIdx.x] = clock64() - t0;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+long long* d;
+template <int N, int A_TMEM, int A_MN, int B_MN, int CHAINS>
+void run() {
+  long long h[148];
+  const int iters = 256;
+  cudaFuncSetAttribute(k<N, A_TMEM, A_MN, B_MN, CHAINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 52000);
+  for (int rep = 0; rep < 2; ++rep) {
+    k<N, A_TMEM, A_MN, B_MN, CHAINS><<<148, 128, 52000>>>(iters, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
+  }
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  long long mx = 0, mn = 1LL << 60;
+  for (int i = 0; i < 148; ++i) { mx = h[i] > mx ? h[i] : mx; mn = h[i] < mn ? h[i] : mn; }
+  const double n = (double)iters * 4 * CHAINS;
+  const double bytes = (A_TMEM ? 0 : 4096) + N * 32.0;
+  printf("N=%3d A=%s/%s B=%s chains=%d: %6.1f clk per MMA (fastest CTA %6.1f), tensor-pipe nominal %3.0f, smem operand bytes %5.0f -> %5.1f B/clk\n", N,
+         A_TMEM ? "tmem" : "smem", A_MN ? "MN" : "K ", B_MN ? "MN" : "K ", CHAINS, mx / n, mn / n, 128.0 * N / 256, bytes, bytes / (mx / n));
+}
+
+int main() {
+  cudaMalloc(&d, 148 * 8);
+  run<64, 0, 0, 0, 1>(); run<64, 0, 0, 0, 2>(); run<64, 0, 1, 1, 1>(); run<64, 0, 1, 1, 2>(); run<64, 0, 0, 1, 1>(); run<64, 1, 0, 0, 1>(); run<64, 1, 0, 1, 1>();
+  run<128, 0, 0, 0, 1>(); run<128, 0, 1, 1, 1>(); run<128, 0, 0, 0, 2>(); run<128, 1, 0, 0, 1>();
+  run<256, 0, 0, 0, 1>(); run<256, 0, 0, 1, 1>(); run<256, 0, 1, 0, 1>(); run<256, 1, 0, 1, 1>();
+  run<48, 0, 0, 0, 1>(); run<32, 0, 0, 0, 1>(); run<16, 0, 0, 0, 1>();
+  return 0;
+}
