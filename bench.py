@@ -641,6 +641,18 @@ def main():
                     "frac": flops_fwd / (ms_fwd * 1e-3) / 1e12 / pk["tensor"]},
         "kernels_ms": {k: round(v[1], 4) for k, v in kern.items()},
     }
+    if precision == "bf16" and D_WORD == 256:
+        # what the kernel's structure allows: its SS-form N = 64 MMAs are bound by shared-memory operand reads,
+        # t = max(M*N/256, bytes/128) clk per MMA, measured by profiles/micro/mma_bench.cu; per 64-region chunk 432 KB of
+        # operand reads + 77 KB of tile fills = 3 980 clk against 2 560 clk of tensor time (2 048 of it algorithmic)
+        roofline["structure_bound"] = {
+            "limiter": "shared-memory operand bandwidth (128 B/clk/SM)", "clk_per_chunk_smem": 3980, "clk_per_chunk_tensor": 2560,
+            "frac_of_tensor_peak_at_that_bound": round(0.8 * 2560 / 3980 * R / (64 * ((R + 63) // 64 - 1) + ((R - 1) % 64 // 16 + 1) * 16)
+                                                       / (pk["tensor"] / 2061.0), 3) if pk["tensor"] else None,
+            "source": "profiles/r02_mma_bench.txt, DESIGN.md 4.6",
+            "note": "chunk period at the bound vs tensor time, x 0.8 (algorithmic share of the executed MMAs: S is recomputed), x R / padded R, "
+                    "against the same measured peak as `frac` (2061 TFLOP/s = 148 SMs x 8192 flop/clk x 1.70 GHz inside the kernel); "
+                    "the drain at every image boundary (about 3 000 clk per image) is on top of it"}
 
     def leave():
         """N > 1: the captured graphs hold NCCL kernels of the communicator and destroy_process_group() did not return
