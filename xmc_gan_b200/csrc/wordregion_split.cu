@@ -13,12 +13,15 @@
 //             (kept for the backward as a hi/lo bf16 pair: as many bytes as fp32)
 //   backward  S, W = C Khat^T -> X, Y (closed form) -> dQ += X Khat,  dK^T = C^T Y + Q^T X  -> fp32 reductions
 // Operands are split ONCE per call into hi / lo bf16 planes in the caller's workspace (split_planes_kernel); the CTAs
-// copy tiles of those planes into 128B-swizzled shared memory with cp.async (no arithmetic on the way) and ONE thread
-// issues the tcgen05 MMAs.  The schedule is synchronous — stage, multiply, wait — on purpose: this is the precise mode,
-// 12x faster than the CUDA-core kernels it replaces and simple enough to audit; the throughput path is wordregion_tc.cu.
+// fetch tiles of those planes by TMA (3-D plane maps, 128B swizzle: no arithmetic on the way) and ONE thread issues the
+// tcgen05 MMAs.  The schedule is mostly synchronous — stage, multiply, wait — : this is the precise mode, 12x faster than
+// the CUDA-core kernels it replaces and simple enough to audit; the throughput path is wordregion_tc.cu.  What is
+// overlapped: in the backward every staged operand half serves a dK^T product of chunk c AND a score product of chunk
+// c + 1 (four stagings per chunk instead of seven) and the next region chunk lands under them.
 // Shared memory bounds the shape of the backward: Q and C tiles (128 x 256, hi + lo = 128 KB each) cannot both stay
 // resident, so they pass through ONE 64 KB buffer in feature halves (S and W accumulate over the halves; each half is
-// one M-tile of dK^T).
+// one M-tile of dK^T); a second buffer — the double buffering that would hide the stagings, a third of the backward's
+// cycles in profiles/r02_split_kernels.json — does not fit next to the region chunk and the X / Y tiles (192 KB).
 #include <algorithm>
 
 #include "common.cuh"
