@@ -695,7 +695,7 @@ def main():
         "sustained": sustained,
     }
     # BASELINE config 2 names two modes, "fp32 and bf16-in/fp32-accum": the default line is the bf16 mode; the fp32 mode
-    # (same inputs as fp32 tensors, rel 1e-4: split-bf16 tcgen05 kernels) rides along as a second block, eager launches
+    # (same inputs as fp32 tensors, rel 1e-4: split-bf16 tcgen05 kernels) rides along as a second block
     if world == 1 and precision == "bf16" and not args.no_fp32_block:
         x32 = {k: (v.to(dev).float() if v.dtype.is_floating_point else v.to(dev)) for k, v in make_inputs(B, 1000 + rank).items()}
         precision = "fp32"                                       # step() reads it
@@ -706,10 +706,25 @@ def main():
             timed(lambda: step(x32, use_side=False), 5)
             k32 = ops.kernel_ms()
             ops.enable_timing(False)
-            ms32 = timed(lambda: step(x32), 10)
+            mode32 = "eager"
+            run32 = lambda: step(x32)
+            if not args.no_graph:                                # the same capture as the bf16 line (no host sync in this path either)
+                try:
+                    g32, gl32, _ = capture(x32)
+                    g32.replay(); torch.cuda.synchronize()
+                    el32, _ = step(x32)
+                    if abs(float(gl32.detach()) - float(el32.detach())) > 1e-5 * abs(float(el32.detach())):
+                        raise RuntimeError("graph replay does not reproduce the eager step")
+                    run32, mode32 = g32.replay, "cuda-graph"
+                except Exception as e:                            # noqa: BLE001
+                    print(f"[bench] fp32 block: CUDA-graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+                    torch.cuda.synchronize()
+            for _ in range(3):
+                run32()
+            ms32 = timed(run32, 10)
             f32_bwd = flops_bwd / (k32["wordregion_bwd"][1] * 1e-3) / 1e12
             line["fp32"] = {
-                "value": Bg / (ms32 * 1e-3), "unit": "samples/s", "ms_per_step": ms32, "steps": 10, "launch": "eager", "tol": 1e-4,
+                "value": Bg / (ms32 * 1e-3), "unit": "samples/s", "ms_per_step": ms32, "steps": 10, "launch": mode32, "tol": 1e-4,
                 "arithmetic": "fp32 inputs; word-region products as three bf16 MMAs on hi + lo operand pairs (tcgen05), "
                               "similarity losses fp32 CUDA-core kernels; fp32 accumulation throughout",
                 "kernels_ms": {k: round(v[1], 4) for k, v in k32.items()},

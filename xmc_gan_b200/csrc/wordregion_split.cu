@@ -58,6 +58,11 @@ __device__ __forceinline__ void tma_tile(uint8_t* dst, int blk_bytes, const CUte
   for (int b = 0; b < nblk; ++b) tma_load_3d(dst + b * blk_bytes, m, (blk0 + b) * 64, row0, outer, bar);
 }
 
+__device__ __forceinline__ void bulk_load_1d_s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void st_chunk16(uint8_t* blk, int r, int c, uint4 v) {
   *reinterpret_cast<uint4*>(blk + r * 128 + ((c ^ (r & 7)) << 4)) = v;
 }
@@ -123,7 +128,8 @@ struct SplitParams {
 struct Ctl {
   uint64_t bar;            // MMA completion
   uint64_t ld;             // TMA completion (word / context tiles)
-  uint64_t ldk;            // TMA completion (region chunks: in flight under other work in the backward)
+  uint64_t ldk;            // TMA completion (region chunks: in flight under other work)
+  uint64_t ld2;            // forward: the second region buffer
   uint32_t tmem_slot;
   int abort_flag;
 };
@@ -144,10 +150,13 @@ __device__ __forceinline__ void mma3_ss(uint32_t d, Desc ah, Desc al, Desc bh, D
 // =====================================================================================================
 template <int D>
 struct FwdS {
-  static constexpr int kOffQh = 0, kOffQl = (D / 64) * kABlk, kOffKh = 2 * (D / 64) * kABlk, kOffKl = kOffKh + (D / 64) * kKBlk,
-                       kOffRn = kOffKl + (D / 64) * kKBlk, kOffPart = kOffRn + CHs * 4, kOffCtl = kOffPart + 3 * 2 * TMs * 4,
-                       kBytes = kOffCtl + 64 + 1024;
-  static constexpr int kColC = 0, kColS = D;
+  // the word tile's lo plane (its hi plane lives in tensor memory) and TWO region buffers (hi + lo planes each): the chunk
+  // after the one being multiplied lands under its MMAs and softmax
+  static constexpr int kKBuf = 2 * (D / 64) * kKBlk;           // 64 KB: hi blocks, then lo blocks
+  static constexpr int kOffQl = 0, kOffK = (D / 64) * kABlk, kOffRn = kOffK + 2 * kKBuf, kOffPart = kOffRn + 2 * CHs * 4,
+                       kOffCtl = kOffPart + 3 * 2 * TMs * 4, kBytes = kOffCtl + 64 + 1024;
+  static constexpr int kColC = 0, kColS = D, kColQ = D + CHs;  // C 256 | S 64 | Q_hi 128 (bf16 pairs)
+  static_assert(kColQ + D / 2 <= 512, "TMEM budget");
   static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -156,9 +165,9 @@ __global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(const __grid_
   using L = FwdS<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1k(smem_raw);
-  uint8_t* Qh = smem + L::kOffQh; uint8_t* Ql = smem + L::kOffQl;
-  uint8_t* Kh = smem + L::kOffKh; uint8_t* Kl = smem + L::kOffKl;
-  float* rn_s = reinterpret_cast<float*>(smem + L::kOffRn);
+  uint8_t* Ql = smem + L::kOffQl;
+  uint8_t* Kb = smem + L::kOffK;                                       // [2 buffers][hi blocks | lo blocks]
+  float* rn_s = reinterpret_cast<float*>(smem + L::kOffRn);            // [2 buffers][64]
   float* part = reinterpret_cast<float*>(smem + L::kOffPart);          // [3: l, a, |C|^2][2 halves][128]
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + L::kOffCtl);
   const WaitCtx wc{&ctl->abort_flag, p.err};
@@ -173,42 +182,83 @@ __global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(const __grid_
   const bool has_rn = p.rnorm != nullptr;
   const float c1 = p.rho1 * kLog2eS;
 
-  if (tid == 0) { ctl->abort_flag = 0; mbar_init(&ctl->bar, 1); mbar_init(&ctl->ld, 1); fence_barrier_init(); }
+  // ctl->ld: the word tile's lo plane; ctl->ldk / ctl->bar2: the two region buffers
+  uint64_t* kfull[2] = {&ctl->ldk, &ctl->ld2};
+  if (tid == 0) {
+    ctl->abort_flag = 0;
+    mbar_init(&ctl->bar, 1); mbar_init(&ctl->ld, 1); mbar_init(&ctl->ldk, 1); mbar_init(&ctl->ld2, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 2 * CHs; i += kThreads) rn_s[i] = has_rn ? 0.f : 1.f;      // slots past a chunk's rows stay finite
   if (warp == 0) tmem_alloc(&ctl->tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ctl->tmem_slot;
   const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  uint32_t phase = 0, ld_phase = 0;
-  if (tid == 0) {                                           // the word tile, hi and lo planes: resident for the CTA's lifetime
-    mbar_expect_tx(&ctl->ld, 2 * (D / 64) * kABlk);
-    tma_tile(Qh, kABlk, &maps.qh, 0, D / 64, m0, 0, &ctl->ld);
+  uint32_t phase = 0, kphase[2] = {0, 0};
+
+  // region chunk (img_, c_) -> buffer b_, asynchronously: both planes by TMA (rows past Rpad arrive as zeros), its norms by a bulk copy
+  auto load_regions = [&](int img_, int c_, int b_) {
+    if (tid == 0) {
+      const int n_ = min(CHs, p.Rpad - c_ * CHs);
+      uint8_t* kh = Kb + b_ * L::kKBuf;
+      mbar_expect_tx(kfull[b_], L::kKBuf + (has_rn ? n_ * 4 : 0));
+      tma_tile(kh, kKBlk, &maps.kh, 0, D / 64, c_ * CHs, img_, kfull[b_]);
+      tma_tile(kh + (D / 64) * kKBlk, kKBlk, &maps.kl, 0, D / 64, c_ * CHs, img_, kfull[b_]);
+      if (has_rn) bulk_load_1d_s(rn_s + b_ * CHs, p.rnorm + (size_t)img_ * p.Rpad + c_ * CHs, n_ * 4, kfull[b_]);
+    }
+  };
+
+  // the word tile: lo plane -> shared memory (TMA), hi plane -> tensor memory (this thread's half of its row: 32-bit column c
+  // holds elements 2c, 2c + 1), so that two of the three MMAs of every score k-step read only the region tile from shared memory
+  if (tid == 0) {
+    mbar_expect_tx(&ctl->ld, (D / 64) * kABlk);
     tma_tile(Ql, kABlk, &maps.ql, 0, D / 64, m0, 0, &ctl->ld);
   }
-  mbar_wait(&ctl->ld, ld_phase, wc, 30); ld_phase ^= 1;
+  load_regions(blockIdx.y, 0, 0);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.qh + (size_t)grow * D + half * (D / 2));
+#pragma unroll
+    for (int b = 0; b < D / 64; ++b) {                                  // 32 bf16 = 16 columns per store
+      uint32_t v[16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint4 w = (grow < p.NQ) ? __ldg(src + b * 4 + u) : make_uint4(0, 0, 0, 0);
+        v[4 * u + 0] = w.x; v[4 * u + 1] = w.y; v[4 * u + 2] = w.z; v[4 * u + 3] = w.w;
+      }
+      tmem_st16(lane_base + L::kColQ + half * (D / 4) + b * 16, v);
+    }
+    tmem_wait_st();
+  }
+  mbar_wait(&ctl->ld, 0, wc, 30);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
+  int x = 0;                                                    // running chunk index: buffer x & 1
   for (int img = blockIdx.y; img < p.Bi; img += gridDim.y) {
     float l = 0.f, a = 0.f;
-    for (int c = 0; c < nch; ++c) {
+    for (int c = 0; c < nch; ++c, ++x) {
       const int n = min(CHs, p.Rpad - c * CHs);
-      if (tid == 0) {                                           // region chunk (rows past Rpad arrive as zeros)
-        mbar_expect_tx(&ctl->ld, 2 * (D / 64) * kKBlk);
-        tma_tile(Kh, kKBlk, &maps.kh, 0, D / 64, c * CHs, img, &ctl->ld);
-        tma_tile(Kl, kKBlk, &maps.kl, 0, D / 64, c * CHs, img, &ctl->ld);
-      }
-      if (tid < CHs) rn_s[tid] = (has_rn && tid < n) ? __ldg(p.rnorm + (size_t)img * p.Rpad + c * CHs + tid) : 1.f;
-      mbar_wait(&ctl->ld, ld_phase, wc, 33); ld_phase ^= 1;
-      __syncthreads();
+      const int b = x & 1;
+      uint8_t* Kh = Kb + b * L::kKBuf;
+      uint8_t* Kl = Kh + (D / 64) * kKBlk;
+      // the other buffer is free (the MMAs of the previous chunk were waited for): fetch the next chunk into it
+      if (c + 1 < nch) load_regions(img, c + 1, b ^ 1);
+      else if (img + (int)gridDim.y < p.Bi) load_regions(img + gridDim.y, 0, b ^ 1);
+      mbar_wait(kfull[b], kphase[b], wc, 33); kphase[b] ^= 1;
       if (warp == 0) {
-        if (elect_one()) {                                      // S = Q Khat^T, three MMAs per 16 features
+        if (elect_one()) {                                      // S = Q Khat^T: hi*hi, hi*lo (A from tensor memory), lo*hi (A from shared memory)
           tc_fence_after();
           constexpr uint32_t idesc = idesc_bf16(TMs, CHs, false, false);
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
             const uint32_t ao = (k >> 2) * kABlk + (k & 3) * 32, bo = (k >> 2) * kKBlk + (k & 3) * 32;
-            mma3_ss(tmem + L::kColS, make_desc(smem_u32(Qh) + ao, 16, 1024), make_desc(smem_u32(Ql) + ao, 16, 1024),
-                    make_desc(smem_u32(Kh) + bo, 16, 1024), make_desc(smem_u32(Kl) + bo, 16, 1024), idesc, k > 0);
+            const Desc bh = make_desc(smem_u32(Kh) + bo, 16, 1024), bl = make_desc(smem_u32(Kl) + bo, 16, 1024);
+            mma_ts(tmem + L::kColS, tmem + L::kColQ + k * 8, bh, idesc, k > 0);
+            mma_ts(tmem + L::kColS, tmem + L::kColQ + k * 8, bl, idesc, true);
+            mma_ss(tmem + L::kColS, make_desc(smem_u32(Ql) + ao, 16, 1024), bh, idesc, true);
           }
           mma_commit(&ctl->bar);
         }
@@ -222,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(const __grid_
         tmem_wait_ld();
         uint32_t ph[16], pl[16];
         const int r0 = c * CHs + half * 32;
+        const float* rn = rn_s + b * CHs + half * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float pw[2];
@@ -230,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(const __grid_
             const float s = __uint_as_float(sv[j + e]);
             const float pv = (r0 + j + e) < p.R ? ex2f(fmaf(s, c1, -c1)) : 0.f;
             l += pv;
-            pw[e] = pv * rn_s[half * 32 + j + e];
+            pw[e] = pv * rn[j + e];
             a = fmaf(pw[e], s, a);
           }
           const __nv_bfloat162 hv = __floats2bfloat162_rn(pw[0], pw[1]);
@@ -262,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(const __grid_
         }
         __syncwarp();
       }
-      mbar_wait(&ctl->bar, phase, wc, 32); phase ^= 1;           // region tiles and S are free again
+      mbar_wait(&ctl->bar, phase, wc, 32); phase ^= 1;           // this region buffer and S are free again
       tc_fence_after();
     }
     // ---- per image: context sums -> hi/lo planes, |C|^2; statistics of the row ----
@@ -362,13 +413,17 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
 
   // one feature half of a [128 x D] operand (hi / lo planes) -> the A buffer.  Every MMA that read the buffer has been
   // waited for by all threads (issue()), so one thread may refill it.
-  auto stage_half = [&](const CUtensorMap* hi, const CUtensorMap* lo, int row0, int outer, int h) {
+  auto stage_begin = [&](const CUtensorMap* hi, const CUtensorMap* lo, int row0, int outer, int h) {
     if (tid == 0) {
       mbar_expect_tx(&ctl->ld, 2 * L::kHB * kABlk);
       tma_tile(Ah, kABlk, hi, h * L::kHB, L::kHB, row0, outer, &ctl->ld);
       tma_tile(Al, kABlk, lo, h * L::kHB, L::kHB, row0, outer, &ctl->ld);
     }
-    mbar_wait(&ctl->ld, ld_phase, wc, 40); ld_phase ^= 1;
+  };
+  auto stage_wait = [&]() { mbar_wait(&ctl->ld, ld_phase, wc, 40); ld_phase ^= 1; };
+  auto stage_half = [&](const CUtensorMap* hi, const CUtensorMap* lo, int row0, int outer, int h) {
+    stage_begin(hi, lo, row0, outer, h);
+    stage_wait();
   };
   auto issue = [&](auto&& body) {                       // one elected thread issues, everybody waits for completion
     if (warp == 0) {
@@ -459,19 +514,28 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
         tmem_wait_ld();
         const int r0 = c * CHs + half * 32;
         float z[32];                                                                        // alpha * d alpha' -> d |v_r|
+        // packed fp32x2 arithmetic on column pairs (the same operations in the same order as the scalar form, half the issue slots)
+        const float2 cc = make_float2(c1, c1), ncc = make_float2(-c1, -c1), il2 = make_float2(inv_l, inv_l);
+        const float2 gam2 = make_float2(gam, gam), ng2 = make_float2(ngrl, ngrl), rho2v = make_float2(p.rho1, p.rho1);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float xv[8], yv[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < 8; e += 2) {
             const int j = u * 8 + e;
-            const float s = __uint_as_float(sv[j]), w = __uint_as_float(wv[j]);
-            const float al = (r0 + j) < p.R ? ex2f(fmaf(s, c1, -c1)) * inv_l : 0.f;          // alpha
-            const float alp = al * rn_s[half * 32 + j];                                     // alpha' = alpha |v_r|
-            const float dap = fmaf(ngrl, w, gam * s);                                       // d loss / d alpha'
-            xv[e] = alp * fmaf(p.rho1, dap, gam);
-            yv[e] = ngrl * alp;
-            z[j] = al * dap;
+            const float2 s2 = make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
+            const float2 w2 = make_float2(__uint_as_float(wv[j]), __uint_as_float(wv[j + 1]));
+            const float2 arg = __ffma2_rn(s2, cc, ncc);
+            float2 al = __fmul2_rn(make_float2(ex2f(arg.x), ex2f(arg.y)), il2);               // alpha
+            al.x = (r0 + j) < p.R ? al.x : 0.f;
+            al.y = (r0 + j + 1) < p.R ? al.y : 0.f;
+            const float2 rn2 = *reinterpret_cast<const float2*>(rn_s + half * 32 + j);
+            const float2 alp = __fmul2_rn(al, rn2);                                          // alpha' = alpha |v_r|
+            const float2 dap = __ffma2_rn(ng2, w2, __fmul2_rn(gam2, s2));                    // d loss / d alpha'
+            const float2 x2 = __fmul2_rn(alp, __ffma2_rn(rho2v, dap, gam2));
+            const float2 y2 = __fmul2_rn(ng2, alp);
+            const float2 zz = __fmul2_rn(al, dap);
+            xv[e] = x2.x; xv[e + 1] = x2.y; yv[e] = y2.x; yv[e + 1] = y2.y; z[j] = zz.x; z[j + 1] = zz.y;
           }
           uint4 hi, lo;
           split8(xv, hi, lo);
@@ -529,10 +593,11 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
         __syncthreads();
         tc_fence_after();
       };
+      // ---- A <- Q_0: dK^T[0] = Q_0^T X; S(c+1) += Q_0 K_0^T ----
+      stage_begin(&maps.qh, &maps.ql, m0, 0, 0);                // the MMAs that read the buffer are done: the next half lands under the drain
       drain(1);
       XMC_PHASE(9);
-      // ---- A <- Q_0: dK^T[0] = Q_0^T X; S(c+1) += Q_0 K_0^T ----
-      stage_half(&maps.qh, &maps.ql, m0, 0, 0);
+      stage_wait();
       XMC_PHASE(7);
       issue([&] { dk_half(Xh, Xl, true); if (more) scores_half(L::kColS, 0, false); });
       XMC_PHASE(8);
@@ -541,11 +606,12 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
       XMC_PHASE(7);
       issue([&] { dk_half(Yh, Yl, false); if (more) scores_half(L::kColW, 0, true); });
       XMC_PHASE(8);
+      // ---- A <- C_1: W(c+1) += C_1 K_1^T (and the buffer is where the next chunk's dK^T[1] expects the second half of C) ----
+      if (more) stage_begin(&maps.ch, &maps.cl, m0, img, 1);
       drain(0);
       XMC_PHASE(9);
-      // ---- A <- C_1: W(c+1) += C_1 K_1^T (and the buffer is where the next chunk's dK^T[1] expects the second half of C) ----
       if (more) {
-        stage_half(&maps.ch, &maps.cl, m0, img, 1);
+        stage_wait();
         XMC_PHASE(3);
         issue([&] { scores_half(L::kColW, 1, false); });
         XMC_PHASE(4);
