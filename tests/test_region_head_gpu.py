@@ -32,6 +32,9 @@ CASES = [  # B, Cin, H, W, feat dtype, weight dtype, bias
     (5, 512, 17, 17, torch.float32, torch.float32, True),      # R = 289: unaligned rows, three pixel tiles, pad rows
     (2, 192, 8, 8, torch.float32, torch.bfloat16, False),      # Cin not a multiple of the tiles, R < one tile
     (37, 256, 16, 16, torch.bfloat16, torch.float32, True),
+    (1, 8, 1, 1, torch.float32, torch.float32, True),           # one pixel, one k-block mostly empty
+    (3, 40, 4, 5, torch.bfloat16, torch.bfloat16, False),      # R = 20: rows not 16-byte aligned in bf16 -> generic path
+    (2, 1024, 32, 32, torch.bfloat16, torch.bfloat16, True),   # R = 1024: four pixel tiles per image, dfeat in four column tiles
 ]
 
 
