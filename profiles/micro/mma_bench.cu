@@ -55,6 +55,69 @@ __global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// MMA streams of one 128 x 64 x 256 block of the word-region backward (operands are zeros: timing only), issued back to back:
+//  STREAM 0 — the kernel as built (per 64-region chunk): S, W = 2 x 16 SS N=64; dQ = 4 SS N=256; dK^T = 2 x 2 x 8 SS N=64
+//  STREAM 1 — the transposed formulation of DESIGN 4.6 (per 128 regions x 64 words): S^T|W^T = 16 SS N=128;
+//             dK += X^T Q + Y^T Chat = 2 x 4 TS N=256; dQ^T = 2 x 8 SS N=64
+template <int STREAM>
+__global__ void __launch_bounds__(128, 1) ks(int iters, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ int abort_flag;
+  for (int i = threadIdx.x; i < 131072 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  if (threadIdx.x == 0) { abort_flag = 0; mbar_init(&bar, 1); fence_barrier_init(); }
+  const int warp = warp_index();
+  if (warp == 0) tmem_alloc(&slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const WaitCtx wc{&abort_flag, nullptr};
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t sa = smem_u32(smem), sb = sa + 65536;          // A region 64 KB, B region 64 KB
+      const Desc ak = make_desc(sa, 16, 1024), amn = make_desc(sa, 16384, 1024);
+      const Desc bk = make_desc(sb, 16, 1024), bmn = make_desc(sb, 8192, 1024);
+      constexpr uint32_t i64 = idesc_bf16(128, 64, false, false), i64mn = idesc_bf16(128, 64, true, true);
+      constexpr uint32_t i128 = idesc_bf16(128, 128, false, false), i256 = idesc_bf16(128, 256, false, true);
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        if (STREAM == 0) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) mma_ss(tmem + 256, ak + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), bk + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), i64, true);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) mma_ss(tmem + 320, ak + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), bk + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), i64, true);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(tmem + 0, ak + ((k * 32) >> 4), bmn + ((k * 2048) >> 4), i256, true);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) mma_ss(tmem + 384 + h * 64, amn + (((k & 7) * 2048) >> 4), bmn + (((k & 7) * 2048) >> 4), i64mn, true);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) mma_ss(tmem + 256, ak + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), bk + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), i128, true);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) mma_ts(tmem + 0, tmem + 256 + (k & 3) * 8, bmn + (((k & 3) * 2048) >> 4), i256, true);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_ss(tmem + 384 + h * 64, amn + ((k * 2048) >> 4), bmn + ((k * 2048) >> 4), i64mn, true);
+        }
+      }
+      mma_commit(&bar);
+      mbar_wait(&bar, 0, wc, 1);
+      out[blockIdx.x] = clock64() - t0;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 long long* d;
 template <int N, int A_TMEM, int A_MN, int B_MN, int CHAINS>
 void run() {
@@ -81,5 +144,22 @@ int main() {
   run<128, 0, 0, 0, 1>(); run<128, 0, 1, 1, 1>(); run<128, 0, 0, 0, 2>(); run<128, 1, 0, 0, 1>();
   run<256, 0, 0, 0, 1>(); run<256, 0, 0, 1, 1>(); run<256, 0, 1, 0, 1>(); run<256, 1, 0, 1, 1>();
   run<48, 0, 0, 0, 1>(); run<32, 0, 0, 0, 1>(); run<16, 0, 0, 0, 1>();
+  for (int st = 0; st < 2; ++st) {
+    long long h[148];
+    const int iters = 64;
+    auto kern = st == 0 ? ks<0> : ks<1>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 133000);
+    for (int rep = 0; rep < 2; ++rep) {
+      kern<<<148, 128, 133000>>>(iters, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+    }
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("%s: %.0f clk per 128 x 64 x 256 block (5 GEMM units; tensor-pipe nominal 2560)\n",
+           st == 0 ? "MMA stream of the backward as built   (32 SS N=64 | 4 SS N=256 | 32 SS N=64)" :
+                     "MMA stream of the transposed backward (16 SS N=128 | 8 TS N=256 | 16 SS N=64)", (double)mx / iters);
+  }
   return 0;
 }
