@@ -118,6 +118,98 @@ __global__ void __launch_bounds__(128, 1) ks(int iters, long long* out) {
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// Operand reuse between CONSECUTIVE MMAs (N = 64, SS): pairs of MMAs into two accumulators that share A (different B), share B
+// (different A) or share nothing.  MODE 0: nothing shared, 1: same A, 2: same B, 3: the hi/lo triple of the fp32 path (ah*bh, ah*bl, al*bh)
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) kr(int iters, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ int abort_flag;
+  for (int i = threadIdx.x; i < 131072 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  if (threadIdx.x == 0) { abort_flag = 0; mbar_init(&bar, 1); fence_barrier_init(); }
+  const int warp = warp_index();
+  if (warp == 0) tmem_alloc(&slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const WaitCtx wc{&abort_flag, nullptr};
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t sa = smem_u32(smem), sb = sa + 65536;
+      const Desc a0 = make_desc(sa, 16, 1024), a1 = make_desc(sa + 32768, 16, 1024);
+      const Desc b0 = make_desc(sb, 16, 1024), b1 = make_desc(sb + 32768, 16, 1024);
+      constexpr uint32_t i64 = idesc_bf16(128, 64, false, false);
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t o = (k * 32) >> 4;
+          if (MODE == 0) { mma_ss(tmem, a0 + o, b0 + o, i64, true); mma_ss(tmem + 64, a1 + o, b1 + o, i64, true); }
+          if (MODE == 1) { mma_ss(tmem, a0 + o, b0 + o, i64, true); mma_ss(tmem + 64, a0 + o, b1 + o, i64, true); }
+          if (MODE == 2) { mma_ss(tmem, a0 + o, b0 + o, i64, true); mma_ss(tmem + 64, a1 + o, b0 + o, i64, true); }
+          if (MODE == 3) { mma_ss(tmem, a0 + o, b0 + o, i64, true); mma_ss(tmem, a0 + o, b1 + o, i64, true); mma_ss(tmem, a1 + o, b0 + o, i64, true); }
+        }
+      }
+      mma_commit(&bar);
+      mbar_wait(&bar, 0, wc, 1);
+      out[blockIdx.x] = clock64() - t0;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// weight-stationary form: tcgen05.mma.ws keeps the B tile in a collector buffer; a pair of MMAs that share B marks it fill / lastuse
+__device__ __forceinline__ void mma_ws(uint32_t d, Desc a, Desc b, uint32_t idesc, int mode) {
+  if (mode == 0)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
+  else if (mode == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.ws.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");
+}
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) kw(int iters, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar; __shared__ uint32_t slot; __shared__ int abort_flag;
+  for (int i = threadIdx.x; i < 131072 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  if (threadIdx.x == 0) { abort_flag = 0; mbar_init(&bar, 1); fence_barrier_init(); }
+  const int warp = warp_index();
+  if (warp == 0) tmem_alloc(&slot, 512);
+  fence_proxy_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = slot;
+  const WaitCtx wc{&abort_flag, nullptr};
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t sa = smem_u32(smem), sb = sa + 65536;
+      const Desc a0 = make_desc(sa, 16, 1024), a1 = make_desc(sa + 32768, 16, 1024), b0 = make_desc(sb, 16, 1024);
+      constexpr uint32_t i64 = idesc_bf16(128, 64, false, false);
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t o = (k * 32) >> 4;
+          if (MODE == 0) { mma_ws(tmem, a0 + o, b0 + o, i64, 2); mma_ws(tmem + 64, a1 + o, b0 + o, i64, 2); }      // ws, no hints
+          if (MODE == 1) { mma_ws(tmem, a0 + o, b0 + o, i64, 0); mma_ws(tmem + 64, a1 + o, b0 + o, i64, 1); }      // ws, fill / lastuse
+        }
+      }
+      mma_commit(&bar);
+      mbar_wait(&bar, 0, wc, 1);
+      out[blockIdx.x] = clock64() - t0;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 long long* d;
 template <int N, int A_TMEM, int A_MN, int B_MN, int CHAINS>
 void run() {
@@ -160,6 +252,38 @@ int main() {
     printf("%s: %.0f clk per 128 x 64 x 256 block (5 GEMM units; tensor-pipe nominal 2560)\n",
            st == 0 ? "MMA stream of the backward as built   (32 SS N=64 | 4 SS N=256 | 32 SS N=64)" :
                      "MMA stream of the transposed backward (16 SS N=128 | 8 TS N=256 | 16 SS N=64)", (double)mx / iters);
+  }
+  for (int md = 0; md < 4; ++md) {
+    long long h[148];
+    const int iters = 256;
+    auto kern = md == 0 ? kr<0> : md == 1 ? kr<1> : md == 2 ? kr<2> : kr<3>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 133000);
+    for (int rep = 0; rep < 2; ++rep) {
+      kern<<<148, 128, 133000>>>(iters, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+    }
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    const char* names[4] = {"consecutive N=64 SS MMAs sharing nothing", "consecutive N=64 SS MMAs sharing A      ", "consecutive N=64 SS MMAs sharing B      ",
+                            "hi/lo triple (ah*bh, ah*bl, al*bh)      "};
+    printf("%s: %.1f clk per MMA\n", names[md], (double)mx / (iters * 4 * (md == 3 ? 3 : 2)));
+  }
+  for (int md = 0; md < 2; ++md) {
+    long long h[148];
+    auto kern = md == 0 ? kw<0> : kw<1>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 133000);
+    for (int rep = 0; rep < 2; ++rep) {
+      kern<<<148, 128, 133000>>>(256, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+    }
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("%s: %.1f clk per MMA\n", md == 0 ? "tcgen05.mma.ws N=64 SS pairs sharing B, no collector hints      " :
+                                               "tcgen05.mma.ws N=64 SS pairs sharing B, collector b0 fill/lastuse", (double)mx / (256 * 8));
   }
   return 0;
 }
