@@ -372,8 +372,9 @@ struct BwdS {
   static constexpr int kOffAh = 0, kOffAl = kHB * kABlk, kOffKh = 2 * kHB * kABlk, kOffKl = kOffKh + (D / 64) * kKBlk,
                        kOffXh = kOffKl + (D / 64) * kKBlk, kOffXl = kOffXh + kABlk, kOffYh = kOffXl + kABlk, kOffYl = kOffYh + kABlk,
                        kOffRn = kOffYl + kABlk, kOffCol = kOffRn + CHs * 4, kOffCtl = kOffCol + CHs * 4, kBytes = kOffCtl + 64 + 1024;
+  // dK^T has one 64-column tile per feature half: the drain of one half runs under the MMAs of the other
   static constexpr int kColDQ = 0, kColS = D, kColW = D + CHs, kColDK = D + 2 * CHs;
-  static_assert(kColDK + CHs <= 512, "TMEM budget");
+  static_assert(kColDK + 2 * CHs <= 512, "TMEM budget");
   static_assert(kBytes <= 232448, "shared memory budget");
 };
 
@@ -425,14 +426,17 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
     stage_begin(hi, lo, row0, outer, h);
     stage_wait();
   };
-  auto issue = [&](auto&& body) {                       // one elected thread issues, everybody waits for completion
+  auto issue_start = [&](auto&& body) {                 // one elected thread issues ...
     if (warp == 0) {
       if (elect_one()) { tc_fence_after(); body(); mma_commit(&ctl->bar); }
       __syncwarp();
     }
+  };
+  auto issue_wait = [&]() {                             // ... everybody waits for completion
     mbar_wait(&ctl->bar, phase, wc, 41); phase ^= 1;
     tc_fence_after();
   };
+  auto issue = [&](auto&& body) { issue_start(body); issue_wait(); };
   // [128 x 64] += A_half[128 x kHalf] . Khat_half^T : score product over one feature half
   auto scores_half = [&](uint32_t d_col, int h, bool first) {
     constexpr uint32_t idesc = idesc_bf16(TMs, CHs, false, false);
@@ -444,12 +448,12 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
     }
   };
   // dK^T[half] [kHalf x 64] (+)= A_half^T . Z   (A and Z as MN-major operands; contraction over the 128 word rows)
-  auto dk_half = [&](uint8_t* Zh, uint8_t* Zl, bool first) {
+  auto dk_half = [&](int h, uint8_t* Zh, uint8_t* Zl, bool first) {
     constexpr uint32_t idesc = idesc_bf16(L::kHalf, CHs, true, true);
 #pragma unroll
     for (int kt = 0; kt < TMs / 16; ++kt) {
       const uint32_t o = kt * 2048;
-      mma3_ss(tmem + L::kColDK, make_desc(smem_u32(Ah) + o, kABlk, 1024), make_desc(smem_u32(Al) + o, kABlk, 1024),
+      mma3_ss(tmem + L::kColDK + h * CHs, make_desc(smem_u32(Ah) + o, kABlk, 1024), make_desc(smem_u32(Al) + o, kABlk, 1024),
               make_desc(smem_u32(Zh) + o, kABlk, 1024), make_desc(smem_u32(Zl) + o, kABlk, 1024), idesc, !(first && kt == 0));
     }
   };
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
             mma3_ss(tmem + L::kColDQ, xh, xl, bh, bl, idesc_dq, dq_started || ks > 0);
           }
         }
-        dk_half(Yh, Yl, true);
+        dk_half(1, Yh, Yl, true);
       });
       dq_started = true;
       XMC_PHASE(6);
@@ -576,13 +580,13 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
       stage_half(&maps.qh, &maps.ql, m0, 0, 1);
       if (more) { wait_regions(); regions_pending = false; }    // both loads were in flight together
       XMC_PHASE(7);
-      issue([&] { dk_half(Xh, Xl, false); if (more) scores_half(L::kColS, 1, true); });
+      issue([&] { dk_half(1, Xh, Xl, false); if (more) scores_half(L::kColS, 1, true); });
       XMC_PHASE(8);
       auto drain = [&](int h) {   // thread = feature (TMEM lane) x 32 regions: a warp adds 32 consecutive features of one region
                                   // row (128 bytes).  (Staging the tile transposed in the dead region buffers and one bulk
                                   // reduce-add per region row was tried: 4.03 ms instead of 3.74 ms for the kernel.)
         uint32_t dv[32];
-        tmem_ld32(lane_base + L::kColDK + half * 32, dv);
+        tmem_ld32(lane_base + L::kColDK + h * CHs + half * 32, dv);
         tmem_wait_ld();
         float* dst = p.dkn + ((size_t)img * p.Rpad + c * CHs + half * 32) * D + h * L::kHalf + row;
         const int nr = p.R - (c * CHs + half * 32);
@@ -593,28 +597,32 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
         __syncthreads();
         tc_fence_after();
       };
-      // ---- A <- Q_0: dK^T[0] = Q_0^T X; S(c+1) += Q_0 K_0^T ----
-      stage_begin(&maps.qh, &maps.ql, m0, 0, 0);                // the MMAs that read the buffer are done: the next half lands under the drain
+      // ---- A <- Q_0: dK^T[0] = Q_0^T X; S(c+1) += Q_0 K_0^T; the finished dK^T[1] drains under these MMAs ----
+      stage_half(&maps.qh, &maps.ql, m0, 0, 0);
+      XMC_PHASE(7);
+      issue_start([&] { dk_half(0, Xh, Xl, true); if (more) scores_half(L::kColS, 0, false); });
       drain(1);
       XMC_PHASE(9);
-      stage_wait();
-      XMC_PHASE(7);
-      issue([&] { dk_half(Xh, Xl, true); if (more) scores_half(L::kColS, 0, false); });
+      issue_wait();
       XMC_PHASE(8);
       // ---- A <- C_0: dK^T[0] += C_0^T Y; W(c+1) = C_0 K_0^T ----
       stage_half(&maps.ch, &maps.cl, m0, img, 0);
       XMC_PHASE(7);
-      issue([&] { dk_half(Yh, Yl, false); if (more) scores_half(L::kColW, 0, true); });
+      issue([&] { dk_half(0, Yh, Yl, false); if (more) scores_half(L::kColW, 0, true); });
       XMC_PHASE(8);
-      // ---- A <- C_1: W(c+1) += C_1 K_1^T (and the buffer is where the next chunk's dK^T[1] expects the second half of C) ----
-      if (more) stage_begin(&maps.ch, &maps.cl, m0, img, 1);
-      drain(0);
-      XMC_PHASE(9);
+      // ---- A <- C_1: W(c+1) += C_1 K_1^T (and the buffer is where the next chunk's dK^T[1] expects the second half of C);
+      //      the finished dK^T[0] drains under these MMAs ----
       if (more) {
-        stage_wait();
+        stage_half(&maps.ch, &maps.cl, m0, img, 1);
         XMC_PHASE(3);
-        issue([&] { scores_half(L::kColW, 1, false); });
+        issue_start([&] { scores_half(L::kColW, 1, false); });
+        drain(0);
+        XMC_PHASE(9);
+        issue_wait();
         XMC_PHASE(4);
+      } else {
+        drain(0);
+        XMC_PHASE(9);
       }
     }
   }
