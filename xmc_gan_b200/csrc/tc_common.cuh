@@ -323,5 +323,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+constexpr int kStgPitch = 20;    // words per staged row (16 + 4): rows stay 16-byte aligned, the row-per-lane writes are conflict-free
+// Epilogue stores.  A thread owns one row of the accumulator tile (TMEM lane), so storing from registers sends each
+// 16-byte piece of a warp instruction to a different row: 32 half-used sectors (measured: the epilogues took as long
+// as loads + MMAs together).  Instead the warp parks its [32 rows x W words] block in shared memory, one row per lane, and
+// re-reads it as (row, 16-byte chunk): every instruction then covers whole 64- or 128-byte row segments.
+template <typename F>
+__device__ __forceinline__ void warp_rows_out(uint32_t* stg, int lane, const uint32_t* w, F&& emit) {
+  constexpr int W = 16, CH = W / 4, RPI = 32 / CH;           // 16 words = four 16-byte chunks per row; 8 rows per warp instruction
+  __syncwarp();                                              // the previous block has been read
+#pragma unroll
+  for (int q = 0; q < CH; ++q)
+    *reinterpret_cast<uint4*>(stg + lane * kStgPitch + 4 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32 / RPI; ++i) {
+    const int r = i * RPI + lane / CH, ch = lane % CH;
+    emit(r, 4 * ch, *reinterpret_cast<const uint4*>(stg + r * kStgPitch + 4 * ch));
+  }
+}
+
+
 }  // namespace tc
 }  // namespace xmc

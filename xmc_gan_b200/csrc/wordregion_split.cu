@@ -154,7 +154,8 @@ struct FwdS {
   // after the one being multiplied lands under its MMAs and softmax
   static constexpr int kKBuf = 2 * (D / 64) * kKBlk;           // 64 KB: hi blocks, then lo blocks
   static constexpr int kOffQl = 0, kOffK = (D / 64) * kABlk, kOffRn = kOffK + 2 * kKBuf, kOffPart = kOffRn + 2 * CHs * 4,
-                       kOffCtl = kOffPart + 3 * 2 * TMs * 4, kBytes = kOffCtl + 64 + 1024;
+                       kOffStg = kOffPart + 3 * 2 * TMs * 4, kOffCtl = kOffStg + (kThreads / 32) * 32 * kStgPitch * 4,
+                       kBytes = kOffCtl + 64 + 1024;
   static constexpr int kColC = 0, kColS = D, kColQ = D + CHs;  // C 256 | S 64 | Q_hi 128 (bf16 pairs)
   static_assert(kColQ + D / 2 <= 512, "TMEM budget");
   static_assert(kBytes <= 232448, "shared memory budget");
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(const __grid_
   uint8_t* Kb = smem + L::kOffK;                                       // [2 buffers][hi blocks | lo blocks]
   float* rn_s = reinterpret_cast<float*>(smem + L::kOffRn);            // [2 buffers][64]
   float* part = reinterpret_cast<float*>(smem + L::kOffPart);          // [3: l, a, |C|^2][2 halves][128]
+  uint32_t* stg_all = reinterpret_cast<uint32_t*>(smem + L::kOffStg);  // per warp: [32 rows x 16 words] on their way out
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + L::kOffCtl);
   const WaitCtx wc{&ctl->abort_flag, p.err};
 
@@ -319,23 +321,34 @@ __global__ void __launch_bounds__(kThreads, 1) wr_fwd_split_kernel(const __grid_
     // ---- per image: context sums -> hi/lo planes, |C|^2; statistics of the row ----
     {
       float c2 = 0.f;
-      const size_t o = ((size_t)img * p.NQ + grow) * D + half * (D / 2);
+      // a thread owns one ROW of C: its 16-byte pieces go through the warp's staging block and leave as 64-byte row segments
+      // (stored straight from registers every warp instruction touched 32 rows, half a sector each)
+      const int wrow0 = m0 + (warp & 3) * 32;                   // first row of this warp's 32
+      const size_t ow = ((size_t)img * p.NQ + wrow0) * D + half * (D / 2);
+      uint32_t* stg = stg_all + warp * 32 * kStgPitch;
 #pragma unroll 1
       for (int b = 0; b < D / 64; ++b) {                        // this thread's D/2 columns, 32 at a time
         uint32_t cv[32];
         tmem_ld32(lane_base + L::kColC + half * (D / 2) + b * 32, cv);
         tmem_wait_ld();
+        uint32_t hw[16], lw[16];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float x[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) { x[e] = __uint_as_float(cv[8 * u + e]); c2 = fmaf(x[e], x[e], c2); }
-          if (grow < p.NQ && p.ch) {                           // rows of a live tile past the count: zeros (the backward's TMA reads them)
-            uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-            if (grow < NQv) split8(x, hi, lo);
-            *reinterpret_cast<uint4*>(p.ch + o + b * 32 + u * 8) = hi;
-            *reinterpret_cast<uint4*>(p.cl + o + b * 32 + u * 8) = lo;
-          }
+          uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;          // rows of a live tile past the count: zeros (the backward's TMA reads them)
+          if (grow < NQv) split8(x, hi, lo);
+          hw[4 * u] = hi.x; hw[4 * u + 1] = hi.y; hw[4 * u + 2] = hi.z; hw[4 * u + 3] = hi.w;
+          lw[4 * u] = lo.x; lw[4 * u + 1] = lo.y; lw[4 * u + 2] = lo.z; lw[4 * u + 3] = lo.w;
+        }
+        if (p.ch) {                                            // uniform: the contexts are saved for a backward
+          warp_rows_out(stg, lane, hw, [&](int r, int wo, uint4 val) {
+            if (wrow0 + r < p.NQ) *reinterpret_cast<uint4*>(p.ch + ow + (size_t)r * D + b * 32 + 2 * wo) = val;
+          });
+          warp_rows_out(stg, lane, lw, [&](int r, int wo, uint4 val) {
+            if (wrow0 + r < p.NQ) *reinterpret_cast<uint4*>(p.cl + ow + (size_t)r * D + b * 32 + 2 * wo) = val;
+          });
         }
       }
       part[(0 * 2 + half) * TMs + row] = l;
@@ -626,21 +639,25 @@ __global__ void __launch_bounds__(kThreads, 1) wr_bwd_split_kernel(const __grid_
       }
     }
   }
-  // ---- dQ of this word tile (summed over the CTA's images) -> fp32 adds ----
+  // ---- dQ of this word tile (summed over the CTA's images) -> fp32 adds.  A thread owns one ROW of the tile: its pieces go
+  //      through a per-warp staging block (the X tiles are dead by now) and leave as 64-byte row segments ----
   if (dq_started) {
+    uint32_t* stg = reinterpret_cast<uint32_t*>(Xh) + warp * 32 * kStgPitch;
+    const int wrow0 = m0 + (warp & 3) * 32;
+    float* dstw = p.dqn + (size_t)wrow0 * D + half * (D / 2);
 #pragma unroll 1
     for (int b = 0; b < D / 64; ++b) {
       uint32_t dv[32];
       tmem_ld32(lane_base + L::kColDQ + half * (D / 2) + b * 32, dv);
       tmem_wait_ld();
-      if (grow < NQv) {
-        float* dst = p.dqn + (size_t)grow * D + half * (D / 2) + b * 32;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(dv[4 * q])),
-                       "f"(__uint_as_float(dv[4 * q + 1])), "f"(__uint_as_float(dv[4 * q + 2])), "f"(__uint_as_float(dv[4 * q + 3]))
-                       : "memory");
-      }
+      for (int hf = 0; hf < 2; ++hf)
+        warp_rows_out(stg, lane, dv + 16 * hf, [&](int r, int wo, uint4 val) {
+          if (wrow0 + r < NQv)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dstw + (size_t)r * D + b * 32 + 16 * hf + wo),
+                         "f"(__uint_as_float(val.x)), "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w))
+                         : "memory");
+        });
     }
   }
   tc_fence_before();
