@@ -221,9 +221,7 @@ int xmc_normalize_rows_backward(const void* xn, const float* norm, const float* 
  *   weight [D, Cin]     fp32 or bf16 (a Conv2d(Cin, D, 1) weight, or its spectral-normalised value), bias [D] fp32 or NULL
  * D = 256; bf16 operands run as bf16 MMAs, fp32 operands as tf32 MMAs (fp32 map AND fp32 weight; a mixed pair is rounded
  * to bf16 in registers), fp32 accumulation: the bf16 mode's tolerance, 2e-2.
- * A timed-out pipeline wait inside the kernel turns rnorm (hence the loss) into NaN.
- * Environment (read at launch): XMC_HEAD_PAIR=1 selects the 2-SM form of the forward / _input kernels (thread-block clusters of two,
- * tcgen05.mma.cta_group::2): same results bit for bit, measured no faster; unset = one CTA per tile. */
+ * A timed-out pipeline wait inside the kernel turns rnorm (hence the loss) into NaN. */
 int xmc_region_head_forward(const void* feat, int feat_dtype, const void* weight, int weight_dtype,
                             const float* bias, int B, int Cin, int R, int Rpad, int D,
                             void* kn, float* rnorm, void* stream);

@@ -4,8 +4,11 @@ cuDNN/cuBLAS backward); CUDA events, L2 flushed between launches."""
 import json, sys, torch
 import torch.nn.functional as F
 sys.path.insert(0, '.')
-from xmc_gan_b200.ops import default_ops
-ops = default_ops()
+import os
+from xmc_gan_b200.ops import CudaOps, default_ops
+from xmc_gan_b200 import _lib
+# XMC_HEAD_PAIR=1: the 2-SM form of the kernels, compiled into the hooks build only
+ops = CudaOps(lib=_lib.hooks_lib()) if os.environ.get("XMC_HEAD_PAIR") else default_ops()
 # L2 is flushed by READING a 512 MB buffer: a zero-fill leaves ~126 MB of dirty lines whose write-back is then charged to
 # the timed kernel (measured: +15-20 us on these HBM-bound kernels, enough to hide every difference between variants)
 flush = torch.zeros(512 << 18, dtype=torch.float32, device="cuda")

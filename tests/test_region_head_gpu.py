@@ -200,9 +200,10 @@ def test_pooled_features_match_avg_pool2d(B, C, H, dt):
 
 
 def test_cta_pair_variant_matches(monkeypatch):
-    """XMC_HEAD_PAIR=1: the 2-SM form of the kernel (thread-block clusters of two, one tcgen05.mma.cta_group::2 per 256-row
-    tile, each CTA staging its own A rows and half of the B rows) gives the same forward and dfeat as single CTAs."""
-    ops = _ops()
+    """Hooks build, XMC_HEAD_PAIR=1: the 2-SM form of the kernel (thread-block clusters of two, one tcgen05.mma.cta_group::2
+    per 256-row tile, each CTA staging its own A rows and half of the B rows) gives the same forward and dfeat as single CTAs."""
+    from util import hooks_ops
+    ops = hooks_ops()                                     # the pair form is compiled into libxmcloss_hooks.so only
     g = torch.Generator(device="cuda").manual_seed(11)
     B, Cin, R, D = 6, 512, 256, 256
     for dt in (torch.bfloat16, torch.float32):

@@ -27,7 +27,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
 ]
 # translation units that contain `#ifdef XMC_TEST_HOOKS` code (debug dumps, pipeline traces, A/B switches)
-HOOKED_SOURCES = ("wordregion_tc.cu", "prep.cu", "wordregion_split.cu")
+HOOKED_SOURCES = ("wordregion_tc.cu", "prep.cu", "wordregion_split.cu", "region_head.cu")
 
 XMC_F32, XMC_BF16 = 0, 1
 PATH_FP32_SIMT, PATH_BF16_TCGEN05, PATH_FP32_TCGEN05 = 0, 1, 2

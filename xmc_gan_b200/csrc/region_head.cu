@@ -129,7 +129,7 @@ __device__ __forceinline__ void st_chunk(uint8_t* blk, int r, int c, uint4 v) {
 }
 
 // FAST: cp.async staging (operands of one dtype, aligned); TF32: fp32 operands as kind::tf32 (FAST only)
-// CL = 2 (FAST only, opt-in): CTA pairs (thread-block clusters of two, cta_group::2) on two items that share their B operand
+// CL = 2 (FAST only; instantiated in the hooks build, see launch_head): CTA pairs (thread-block clusters of two, cta_group::2) on two items that share their B operand
 // (the weights in the forward, the image's dy tile in dfeat).  One tcgen05.mma of the pair's leader multiplies a 256-row
 // tile over both SMs: each CTA stages its own 128 A rows and HALF of the B rows, so a k-block brings 32 KB into an SM
 // instead of 48 KB.  The leader's full barrier collects the bytes of both CTAs, its commits release the stage / publish the
@@ -597,15 +597,18 @@ int launch_head(const HeadParams& p, int n_items, cudaStream_t st) {
   if (!fast_ok(p)) return launch_head_as<MODE, false, false, 1>(p, grid, st);
   // pairs: consecutive items must share their B operand and there must be an even number of them
   //   forward: B = the weights, shared by every item;  dfeat: B = dy_b, shared by the channel tiles of one image
-  // Opt-in (XMC_HEAD_PAIR=1): measured no faster than one CTA per tile (forward 43.2 / 32.8 us against 42.0 / 31.7 us) — per
-  // staged byte the kernel writes shared memory once (TMA) and reads it once (MMA operands), 192 B/clk against the SM's
-  // 128 B/clk while the MMAs run, and pairing halves only the B part of it.  Kept as the tested 2-SM form of the kernel.
+#ifdef XMC_TEST_HOOKS
+  // Hooks build only (libxmcloss_hooks.so, XMC_HEAD_PAIR=1): the 2-SM form.  Measured no faster than one CTA per tile (forward
+  // 43.0 / 32.8 us against 43.0 / 30.7 us) — per staged byte the kernel writes shared memory once (TMA) and reads it once (MMA
+  // operands), 192 B/clk against the SM's 128 B/clk while the MMAs run, and pairing halves only the B part of it.  Kept as
+  // the tested 2-SM form of the kernel; the product library has the single-CTA form only.
   const bool pairs = MODE != kDW && n_items % 2 == 0 && n_items >= 2 && (MODE == kFwd || (p.n_tiles == 1 && p.m_tiles % 2 == 0)) &&
                      getenv("XMC_HEAD_PAIR") != nullptr;
   if (pairs) {
     grid &= ~1;
     return p.a_bf16 ? launch_head_as<MODE, true, false, 2>(p, grid, st) : launch_head_as<MODE, true, true, 2>(p, grid, st);
   }
+#endif
   return p.a_bf16 ? launch_head_as<MODE, true, false, 1>(p, grid, st) : launch_head_as<MODE, true, true, 1>(p, grid, st);
 }
 
