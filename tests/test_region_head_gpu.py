@@ -220,3 +220,46 @@ def test_cta_pair_variant_matches(monkeypatch):
         torch.cuda.synchronize()
         assert torch.equal(kn0, kn1) and torch.equal(rn0, rn1)          # same products in the same order
         assert torch.equal(df0, df1)
+
+
+def test_word_loss_with_fused_head_is_cuda_graph_capturable():
+    """The fused head (TMA maps built per call on the host, memsets of the weight gradient, column-sum kernel) inside
+    torch.cuda.graph: nothing synchronises with the host; replays reproduce the eager step."""
+    from xmc_gan_b200 import train_gan as T
+    B, Cin, H, W, T_ = 16, 512, 16, 16, 9
+    feat, w, bias, words, mask = _head_inputs(B, Cin, H, W, T_, seed=21)
+    f = feat.cuda().requires_grad_()
+    wg = w.cuda().view(256, Cin, 1, 1).requires_grad_()
+    bg = bias.cuda().requires_grad_()
+    wd = words.bfloat16().cuda().requires_grad_()
+    m = mask.cuda()
+    labels = T.make_labels(B, None, False)
+    leaves = (f, wg, bg, wd)
+
+    def step():
+        for t in leaves:
+            t.grad = None
+        loss = T.word_loss(f, wd, m, labels, False, precision="bf16", region_head=(wg, bg))
+        loss.backward()
+        return loss
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    ref_loss = float(step().detach())
+    ref = [t.grad.clone() for t in leaves]
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        loss = step()
+    for _ in range(3):
+        for t in leaves:
+            t.grad.zero_()                   # the captured backward accumulates into the captured .grad tensors
+        g.replay()
+    torch.cuda.synchronize()
+    assert abs(float(loss.detach()) - ref_loss) <= 1e-5 * abs(ref_loss)
+    for t, r in zip(leaves, ref):            # fp32 atomics: summation order differs from run to run
+        assert float((t.grad.float() - r.float()).norm() / r.float().norm()) < 1e-2
