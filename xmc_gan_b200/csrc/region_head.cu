@@ -8,27 +8,28 @@
 //   forward   y_b = feat_b^T W^T + bias   (M = pixels, N = D = 256, K = Cin)  ->  epilogue: ||y_r||, unit rows
 //             kn[B, Rpad, D] bf16 + rnorm[B, Rpad] fp32, exactly what wr_fwd_tc_kernel / wr_bwd_tc_kernel consume;
 //             y itself never reaches HBM.
-//   backward  dy[B, R, D] (bf16, from xmc_normalize_rows_backward on the word-region kernels' dkn / drnorm):
+//   backward  dy[B, R, D] (in the map's dtype, from xmc_normalize_rows_backward on the word-region kernels' dkn / drnorm):
 //             dfeat_b = W^T dy_b^T        (M = Cin, N = pixels, K = D)        written in feat's own [B, Cin, H, W] layout
 //             dW      = sum_b dy_b^T feat_b^T (M = D, N = Cin, K = B * R)     split over CTAs, fp32 red into dW
-//             dbias   = sum_{b,r} dy      column sums taken from the staged A tiles of the dW kernel
+//             dbias   = sum_{b,r} dy      a column-sum kernel beside it
 //
 // All three products have ONE operand form on the tensor cores: C[m, n] = sum_k A[k, m] * B[n, k] with A stored
 // [K rows][M contiguous] (MN-major smem tile) and B stored [N rows][K contiguous] (K-major tile) — feat_b is
 // [Cin][pixels], W is [D][Cin], dy_b is [pixels][D]: every operand is consumed where it lies, no transposes.
 // Staging (fast path: both operands of one dtype, rows 16-byte aligned): one thread issues TMA boxes ([k rows x 128 bytes],
-// 3-D maps built per call) straight into the swizzled tiles of a 4-stage ring, 192 KB per SM in flight.  (Two earlier
-// versions staged through the LSU — conversion in registers: 100 us per launch, bound by one load round trip per group of
-// chunks; 16-byte cp.async: 40-60 us, bound by the ~48 KB of requests an SM keeps outstanding on that path.)  bf16 operands run as
-// kind::f16 MMAs (64 k per stage); fp32 operands stay fp32 in shared memory and run as kind::tf32 MMAs (32 k per
-// stage, 10-bit mantissa: inside the bf16 tolerance), so an fp32 discriminator needs neither a cast pass nor a
-// conversion in registers.  (A first version converted in registers: one load round trip per group of four chunks
-// made it latency-bound, 100 us per launch.)  Generic path (mixed dtypes, unaligned rows such as a 17 x 17 map):
-// global -> registers -> bf16 -> swizzled smem by the same warps.  fp32 accumulation in TMEM (two 256-column
-// accumulators: the epilogue of one tile runs under the MMAs of the next).
+// 3-D maps built per call) straight into the swizzled tiles of a 4-stage ring, 192 KB per SM in flight.  bf16 operands
+// run as kind::f16 MMAs (64 k per stage); fp32 operands stay fp32 in shared memory and run as kind::tf32 MMAs (32 k per
+// stage, 10-bit mantissa: inside the bf16 tolerance; the MN-major fp32 tile needs the 128B_BASE32B / 128B_ATOM_32B
+// swizzle), so an fp32 discriminator needs neither a cast pass nor a conversion in registers.  (Two earlier versions
+// staged through the LSU — conversion in registers: 100 us per launch, bound by one load round trip per group of chunks;
+// 16-byte cp.async: 40-60 us, bound by the ~48 KB of requests an SM keeps outstanding on that path.)  Generic path
+// (mixed dtypes, unaligned rows such as a 17 x 17 map): global -> registers -> bf16 -> swizzled smem by eight staging
+// warps.  fp32 accumulation in TMEM, two 256-column accumulators: the epilogue of one tile (eight warps: lane quadrant x
+// column half) runs under the MMAs of the next and stores whole 64-byte row segments through a per-warp staging block.
 //
-// Roofline: HBM.  Forward at B = 256, 16 x 16, Cin = 512, D = 256: 134 MB (fp32 map) or 67 MB (bf16) in + 33.6 MB
-// out against 17.2 GFLOP (12 us of tensor time); the staging path is sized for bytes in flight, not for the MMAs.
+// Roofline: HBM by bytes (forward at B = 256, 16 x 16, Cin = 512, D = 256: 134 MB (fp32 map) or 67 MB (bf16) in + 33.6 MB
+// out against 17.2 GFLOP); measured bound: shared-memory bandwidth — with K = Cin = 512 every staged byte is written once
+// (TMA) and read once (MMA operand), 192 B/clk against the SM's 128 B/clk while the MMAs run.
 #include <cstdlib>
 
 #include "common.cuh"
